@@ -1,0 +1,273 @@
+/*
+ * pht_b200.h -- C ABI of libpht_b200.so: the B200 (sm_100a) kernels behind the
+ * AFGSA denoiser hot path of goodbadwolf/pixel_heal_thyself (PHT).
+ *
+ * The reference has no native code: every entry point below replaces a stock
+ * torch call site of the reference (cited as file:line relative to the
+ * reference checkout).  The host side (pixel_heal_thyself_b200/, Python) binds
+ * these with ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless
+ *     the name ends in _host.  No allocation, no ownership transfer: every
+ *     buffer (workspaces included) is owned by the caller.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 on success, negative pht_status on failure
+ *     (pht_last_error() returns a thread-local message).  Python raises.
+ *   - activations are channels-last ("NHWC") with an explicit strided view so
+ *     that padded buffers, interior views and channel slices need no copies.
+ *   - dtype: PHT_F32 (parity mode, CUDA-core fp32 math) or PHT_BF16 (production:
+ *     bf16 storage, fp32 accumulation, tcgen05 tensor cores where shapes allow).
+ */
+#ifndef PHT_B200_H
+#define PHT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHT_ABI_VERSION 1
+
+enum pht_status {
+  PHT_OK = 0,
+  PHT_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  PHT_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+  PHT_ERR_UNSUPPORTED = -3
+};
+
+enum pht_dtype { PHT_F32 = 0, PHT_BF16 = 1 };
+enum pht_pad_mode { PHT_PAD_REPLICATE = 0, PHT_PAD_REFLECT = 1 };
+
+/* Strided channels-last view.  Element (b, y, x, c) lives at
+ * ptr + b*sb + y*sy + x*sx + c  (strides in ELEMENTS, channel stride 1).
+ * Reads outside 0<=y<H, 0<=x<W return 0 (this is how zero padding, dgrad's
+ * implicit zero border and ragged tiles are expressed).  (oy, ox) is added to
+ * the pixel coordinate before the bounds test: an output pixel (y, x) with tap
+ * (dy, dx) reads view pixel (y + dy + oy, x + dx + ox). */
+typedef struct pht_view {
+  void* ptr;
+  int32_t H, W, C;
+  int32_t oy, ox;
+  int32_t dtype;            /* pht_dtype of the elements */
+  int64_t sb, sy, sx;
+} pht_view;
+
+/* Epilogue flags of pht_conv_gemm */
+#define PHT_EPI_RESID_PRE  1u  /* v += resid before the activation            */
+#define PHT_EPI_RESID_POST 2u  /* out2 = v + resid                            */
+#define PHT_EPI_MASK       4u  /* out2 *= (mask > 0 ? 1 : mslope[n])          */
+
+/* Implicit-GEMM convolution over pixels with virtual concat:
+ *   acc[p, n] = sum_t sum_s sum_k src[s](p + tap_t)[k] * w[t][n][koff_s + k]
+ *   v    = act(acc + bias[n] (+ resid[p,n] if RESID_PRE)),  act(v) = v>0 ? v : v*slope[n]
+ *   out1 = v                                   (if out1.ptr)
+ *   out2 = (v (+ resid if RESID_POST)) (* dact(mask) if MASK)   (if out2.ptr)
+ * Taps are the ksize x ksize centred stencil (ksize in {1,3,5}), t = ky*ksize+kx.
+ * Weights are packed [ksize*ksize][N][Ktot] in `dtype`, Ktot = sum of src[s].C.
+ * bias / slope / mslope are fp32 [N] or NULL (NULL slope = no activation).
+ * Output domain is B x Ho x Wo pixels, N channels.
+ *
+ * Replaces: nn.Conv2d(+ReLU/LeakyReLU) forward and data-gradient for every
+ * 1x1 / 3x3 conv of AFGSANet (model.py:606-658, 449-452, 552-569, 690-706),
+ * torch.cat (model.py:462,722,727), the residual adds (model.py:576-581) and
+ * the ReLU backward masks (autograd). */
+typedef struct pht_conv_gemm_args {
+  int32_t dtype;            /* compute/storage dtype of src, w, out            */
+  int32_t B, Ho, Wo, N;
+  int32_t ksize;
+  int32_t n_src;
+  uint32_t flags;
+  pht_view src[3];
+  const void* w;
+  const float* bias;
+  const float* slope;
+  const float* mslope;
+  pht_view resid;
+  pht_view mask;
+  pht_view out1;
+  pht_view out2;
+} pht_conv_gemm_args;
+
+int pht_conv_gemm(const pht_conv_gemm_args* args, void* stream);
+
+/* Weight gradient of the op above:
+ *   dw[t][n][koff_s + k] (+)= sum_p dy[p, n] * src[s](p + tap_t)[k],  dbias[n] = sum_p dy[p, n]
+ * dw is fp32 [ksize*ksize][N][Ktot] and is OVERWRITTEN; dbias fp32 [N] or NULL.
+ * workspace: pht_wgrad_workspace_bytes(args) bytes (split-K partials).
+ * Replaces cuDNN convolution_backward(weight, bias) (autograd of model.py convs). */
+typedef struct pht_wgrad_args {
+  int32_t dtype;
+  int32_t B, Ho, Wo, N;
+  int32_t ksize;
+  int32_t n_src;
+  pht_view dy;
+  pht_view src[3];
+  float* dw;
+  float* dbias;
+  void* workspace;
+  size_t workspace_bytes;
+} pht_wgrad_args;
+
+size_t pht_wgrad_workspace_bytes(const pht_wgrad_args* args);
+int pht_wgrad(const pht_wgrad_args* args, void* stream);
+
+/* Fill the 1-pixel border of a padded NHWC buffer [B][H+2][W+2][C] from its
+ * interior (replicate = clamp to edge, reflect = mirror without the edge).
+ * Replaces F.pad inside nn.Conv2d(padding_mode=...) (model.py:607-622, 552-569,
+ * 690-706; mode chosen at base_trainer.py:334). */
+int pht_border_fill(void* buf, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode, void* stream);
+
+/* Backward of the padding: fold the border of a padded-domain gradient
+ * gpad[B][H+2][W+2][C] into the interior, then
+ *   out1 = fold(gpad) (+ resid)          (if out1.ptr)
+ *   out2 = out1 * dact(mask)             (if out2.ptr; mslope as in conv_gemm)
+ * Replaces replication_pad2d_backward / reflection_pad2d_backward + ReLU bwd. */
+int pht_pad_fold(const void* gpad, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode,
+                 const pht_view* resid, const pht_view* mask, const float* mslope,
+                 const pht_view* out1, const pht_view* out2, void* stream);
+
+/* 5x5 im2col of a tiny-channel NCHW fp32 image (Cin = 3 or 7) into a row-major
+ * [B*H*W][Kpad] matrix of `dtype`, k = (ky*5+kx)*Cin + ci, zero-filled to Kpad;
+ * out-of-image taps follow `mode` (clamp / mirror).  The 1x1, 3x3 and 5x5
+ * encoder branches (model.py:606-646, 719-726) then run as ONE dense GEMM with
+ * their kernels embedded in the 5x5 tap grid. */
+int pht_im2col5(const float* x_nchw, void* col, int32_t dtype, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                int32_t Kpad, int32_t mode, void* stream);
+
+/* Block-local auxiliary-feature-guided self attention, model.py:474-516.
+ * q (pre-scaled by d^-1/2), k, v: views of C = heads*64 channels; window =
+ * block + 2*halo; keys outside the image are zero but NOT masked; rel_h /
+ * rel_w fp32 [win][d/2] are added to the key halves after padding.
+ *   out[p, h*d+j] = resid[p, ...] + sum_key softmax(q.k')[key] v[key]
+ * lse: fp32 [B*H*W][heads] (log-sum-exp per query/head, saved for backward). */
+typedef struct pht_attn_args {
+  int32_t dtype;
+  int32_t B, H, W;
+  int32_t heads, head_dim, block, halo;
+  pht_view q, k, v;
+  const float* rel_h;
+  const float* rel_w;
+  pht_view resid;           /* optional (ptr may be NULL)                      */
+  pht_view out;
+  float* lse;
+} pht_attn_args;
+
+int pht_attn_fwd(const pht_attn_args* args, void* stream);
+
+/* Recompute-based backward of the op above (autograd of model.py:474-516):
+ * given d_out, recomputes P from q, k, lse and produces dq (view), dk / dv as
+ * fp32 accumulators [B*H*W][C] (caller zeroes them; halo overlap is summed
+ * with atomics), and d_rel_h / d_rel_w fp32 [win][d/2] (OVERWRITTEN).
+ * workspace: pht_attn_bwd_workspace_bytes() for the per-block rel partials. */
+typedef struct pht_attn_bwd_args {
+  pht_attn_args fwd;        /* q, k, v, rel_*, lse as in the forward; out/resid unused */
+  pht_view d_out;
+  pht_view dq;
+  float* dk_acc;
+  float* dv_acc;
+  float* d_rel_h;
+  float* d_rel_w;
+  void* workspace;
+  size_t workspace_bytes;
+} pht_attn_bwd_args;
+
+size_t pht_attn_bwd_workspace_bytes(const pht_attn_bwd_args* args);
+int pht_attn_bwd(const pht_attn_bwd_args* args, void* stream);
+
+/* Decoder tail: 3x3 conv 256->3 with ZERO padding, no activation, plus the
+ * residual with the network input (model.py:707-714, 732).
+ *   out_nchw[b,co,y,x] = x_nchw[b,co,y,x] + bias[co] + sum_{t,c} h(y+dy,x+dx)[c] * w[co][t][c]
+ * w fp32 [3][9][C]. */
+int pht_dec_tail_fwd(const pht_view* h, const float* w, const float* bias, const float* x_nchw, float* out_nchw,
+                     int32_t B, int32_t H, int32_t W, void* stream);
+/* dh_pre[p,c] = (sum_{t,co} dout(p - tap_t)[co] * w[co][t][c]) * (h[p,c] > 0)  (ReLU of decoder.1 fused) */
+int pht_dec_tail_bwd_data(const float* dout_nchw, const float* w, const pht_view* h, const pht_view* dh_pre,
+                          int32_t B, int32_t H, int32_t W, void* stream);
+/* dw fp32 [3][9][C] and dbias fp32 [3], both OVERWRITTEN. workspace >= pht_dec_tail_ws_bytes(). */
+size_t pht_dec_tail_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t C);
+int pht_dec_tail_bwd_weight(const float* dout_nchw, const pht_view* h, float* dw, float* dbias, void* workspace,
+                            size_t workspace_bytes, int32_t B, int32_t H, int32_t W, void* stream);
+
+/* L1 reconstruction loss, fused forward+backward (losses.py:175-184,
+ * base_trainer.py:423):  loss[0] = mean|a-b| (OVERWRITTEN),
+ * grad[i] = grad_scale * sign(a[i]-b[i]) / n  (grad may be NULL). */
+int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, float* loss, float* grad, void* stream);
+
+/* Batch preprocessing (base_trainer.py:373-383; preprocessing.py:19-22,34-38):
+ * NHWC fp32 patches -> NCHW fp32: noisy/gt = log(v+1); aux[0:3] =
+ * clamp((nan_to_num(n)+1)/2, 0, 1); aux[3:7] unchanged.  gt may be NULL. */
+int pht_preprocess(const float* noisy_nhwc, const float* gt_nhwc, const float* aux_nhwc, float* noisy_nchw,
+                   float* gt_nchw, float* aux_nchw, int32_t B, int32_t H, int32_t W, void* stream);
+
+/* Patch crop + the preprocessing above in one pass (preprocessing.py:325-344,
+ * gen_hdf5.py:135-139 + base_trainer.py:373-383): frames NHWC fp32
+ * [n_img][Hf][Wf][3|7] resident in HBM; patch i is the PxP window centred at
+ * centres[i] = (x, y) (int32 [n][2]) of frame img_idx[i] (int32 [n], NULL = frame 0);
+ * output NCHW fp32 [n][C][P][P]. */
+int pht_crop_preprocess(const float* noisy_f, const float* gt_f, const float* aux_f, int32_t Hf, int32_t Wf,
+                        const int32_t* centres, const int32_t* img_idx, int32_t n, int32_t P, float* noisy_nchw,
+                        float* gt_nchw, float* aux_nchw, void* stream);
+
+/* Adam over a flat fp32 parameter arena (base_trainer.py:182-187; torch.optim
+ * Adam, betas (0.9,0.999), eps 1e-8, no weight decay).  step is 1-based. */
+int pht_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+             int32_t step, float grad_scale, void* stream);
+
+/* Weight (re)packing between the reference's OIHW fp32 parameters and the
+ * kernels' [tap][N][K] layout.
+ *   pack:    dst[t][n_off+o][k_off+i] = scale * w[o][i][ky][kx]   (transpose=0)
+ *            dst[t'][n_off+i][k_off+o] = scale * w[o][i][ky][kx], t' = flipped tap (transpose=1, dgrad)
+ *   embed:   the ksize x ksize kernel is centred inside a `grid` x `grid` tap
+ *            grid whose taps are folded into K (used for the im2col5 encoders):
+ *            dst[n_off+o][((ky+e)*grid + kx+e)*I + i], e = (grid-ksize)/2.
+ *   unpack:  the inverse, accumulating nothing: w_grad[o][i][ky][kx] = scale * src[...]. */
+typedef struct pht_pack_args {
+  const float* w;           /* OIHW fp32 (pack: source; unpack: destination, cast away const) */
+  void* packed;             /* packed tensor (dtype below for pack; fp32 for unpack)          */
+  int32_t dtype;
+  int32_t O, I, ksize;
+  int32_t Ntot, Ktot;       /* extents of the packed tensor                                   */
+  int32_t n_off, k_off;
+  int32_t transpose;
+  int32_t grid;             /* 0 = taps stay a separate leading dim; 5 = embed into K         */
+  int32_t i_begin, i_count; /* input-channel slice of w that is packed (i_count 0 = all of I);  */
+                            /* packed input index = i - i_begin                                 */
+  float scale;
+} pht_pack_args;
+
+int pht_pack_weight(const pht_pack_args* a, void* stream);
+int pht_unpack_wgrad(const pht_pack_args* a, void* stream);
+
+/* dtype conversion of a contiguous array (fp32 <-> bf16), n elements. */
+int pht_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+/* same for a rows x cols matrix with leading dimensions (elements) src_ld / dst_ld */
+int pht_cast2d(const void* src, int32_t src_dtype, int64_t src_ld, void* dst, int32_t dst_dtype, int64_t dst_ld,
+               int64_t rows, int64_t cols, void* stream);
+
+/* NHWC(dtype, C = 3) -> NCHW fp32 and back are folded into the ops above. */
+
+/* Poisson-disk dart throwing, bit-exact with
+ * sample_patches_dart_throwing(shape, P, n, random.Random(seed)) of
+ * preprocessing.py:179-213 (CPython MT19937 randint semantics).  One CTA per
+ * image: seeds int64 [n_img]; out int32 [n_img][n][2] = (x, y). */
+int pht_sample_patches(const int64_t* seeds, int32_t n_img, int32_t Hf, int32_t Wf, int32_t P, int32_t n,
+                       int32_t max_iter, int32_t* out, void* stream);
+
+/* Introspection */
+int pht_abi_version(void);
+const char* pht_last_error(void);
+/* counters[0] = tcgen05 conv_gemm launches, [1] = CUDA-core conv_gemm launches,
+ * [2] = tcgen05 wgrad, [3] = CUDA-core wgrad, [4] = tcgen05 attention, [5] = CUDA-core attention,
+ * [6] = all other kernel launches.  Reset with pht_reset_counters(). */
+void pht_get_counters(uint64_t* counters8);
+void pht_reset_counters(void);
+/* 1 = never use tcgen05 paths (debug / A-B testing) */
+void pht_set_force_simple(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHT_B200_H */

@@ -1,0 +1,721 @@
+// Bandwidth-bound kernels of the AFGSA hot path: padding border fill / fold,
+// encoder im2col, decoder tail, L1 loss, preprocessing, Adam, weight packing.
+// All are vectorised (16-byte accesses along the channel dim), coalesced and
+// use warp-shuffle reductions; grids are sized in multiples of the SM count
+// where a grid-stride loop is used.
+#include "common.cuh"
+
+namespace pht {
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void ld(const float* p, float* o) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  __device__ static void st(float* p, const float* o) { *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]); }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  __device__ static void ld(const bf16* p, float* o) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __bfloat1622float2(h[i]);
+      o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+  }
+  __device__ static void st(bf16* p, const float* o) {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// border fill: buf [B][H+2][W+2][C]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void border_fill_kernel(T* buf, int B, int H, int W, int C, int mode) {
+  constexpr int V = Vec<T>::N;
+  const int Wp = W + 2, Hp = H + 2;
+  const int per_img = 2 * Wp + 2 * H;  // top row, bottom row, left col, right col (without corners)
+  const int cv = C / V;
+  long long total = (long long)B * per_img * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    long long r = i / cv;
+    int e = (int)(r % per_img);
+    int b = (int)(r / per_img);
+    int qy, qx;
+    if (e < Wp) { qy = 0; qx = e; }
+    else if (e < 2 * Wp) { qy = Hp - 1; qx = e - Wp; }
+    else if (e < 2 * Wp + H) { qy = e - 2 * Wp + 1; qx = 0; }
+    else { qy = e - 2 * Wp - H + 1; qx = Wp - 1; }
+    int sy = pad_src_index(qy, H, mode) + 1, sx = pad_src_index(qx, W, mode) + 1;
+    const T* src = buf + (((long long)b * Hp + sy) * Wp + sx) * C + c;
+    T* dst = buf + (((long long)b * Hp + qy) * Wp + qx) * C + c;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pad fold (backward of the border fill) + residual + activation-derivative mask
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pad_fold_kernel(const T* gpad, int B, int H, int W, int C, int mode, View resid, View mask,
+                                const float* __restrict__ mslope, View out1, View out2) {
+  constexpr int V = Vec<T>::N;
+  const int Wp = W + 2, Hp = H + 2;
+  const int cv = C / V;
+  long long total = (long long)B * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V;
+    long long r = i / cv;
+    int x = (int)(r % W); r /= W;
+    int y = (int)(r % H);
+    int b = (int)(r / H);
+    int qys[3], qxs[3], ny = 0, nx = 0;
+    qys[ny++] = y + 1;
+    if (pad_src_index(0, H, mode) == y) qys[ny++] = 0;
+    if (pad_src_index(Hp - 1, H, mode) == y) qys[ny++] = Hp - 1;
+    qxs[nx++] = x + 1;
+    if (pad_src_index(0, W, mode) == x) qxs[nx++] = 0;
+    if (pad_src_index(Wp - 1, W, mode) == x) qxs[nx++] = Wp - 1;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int d = 0; d < nx; ++d) {
+        float t[V];
+        Vec<T>::ld(gpad + (((long long)b * Hp + qys[a]) * Wp + qxs[d]) * C + c, t);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += t[j];
+      }
+    if (resid.ptr) {
+      float t[V];
+      Vec<T>::ld((const T*)resid.ptr + view_off(resid, b, y, x) + c, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += t[j];
+    }
+    if (out1.ptr) Vec<T>::st((T*)out1.ptr + view_off(out1, b, y, x) + c, acc);
+    if (out2.ptr) {
+      if (mask.ptr) {
+        float t[V];
+        Vec<T>::ld((const T*)mask.ptr + view_off(mask, b, y, x) + c, t);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] *= (t[j] > 0.f ? 1.f : (mslope ? mslope[c + j] : 0.f));
+      }
+      Vec<T>::st((T*)out2.ptr + view_off(out2, b, y, x) + c, acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col 5x5 for the tiny-channel encoders
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col5_kernel(const float* __restrict__ x, T* col, int B, int Cin, int H, int W, int Kpad, int mode) {
+  long long total = (long long)B * H * W * Kpad;
+  const int kreal = 25 * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % Kpad);
+    long long p = i / Kpad;
+    float v = 0.f;
+    if (k < kreal) {
+      int ci = k % Cin, t = k / Cin;
+      int ky = t / 5, kx = t % 5;
+      int px = (int)(p % W);
+      long long r = p / W;
+      int py = (int)(r % H);
+      int b = (int)(r / H);
+      int sy = pad_index(py + ky - 2, H, mode), sx = pad_index(px + kx - 2, W, mode);
+      v = x[(((long long)b * Cin + ci) * H + sy) * W + sx];
+    }
+    col[i] = from_f<T>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder tail (256 -> 3, zero padding) forward / data-grad / weight-grad
+// ---------------------------------------------------------------------------------------------
+// one warp per pixel; lanes split the channels; weights [3][9][C] staged in smem
+template <typename T>
+__global__ void dec_tail_fwd_kernel(View h, const float* __restrict__ w, const float* __restrict__ bias,
+                                    const float* __restrict__ x, float* __restrict__ out, int B, int H, int W) {
+  extern __shared__ float sw[];  // [27][C]
+  const int C = h.C;
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  constexpr int V = Vec<T>::N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  long long npx = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * wpb + warp; p < npx; p += (long long)gridDim.x * wpb) {
+    int px = (int)(p % W);
+    long long r = p / W;
+    int py = (int)(r % H);
+    int b = (int)(r / H);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int t = 0; t < 9; ++t) {
+      int yy = py + t / 3 - 1 + h.oy, xx = px + t % 3 - 1 + h.ox;
+      if (!view_inb(h, yy, xx)) continue;
+      const T* hp = (const T*)h.ptr + view_off(h, b, yy, xx);
+      for (int c = lane * V; c < C; c += 32 * V) {
+        float hv[V];
+        Vec<T>::ld(hp + c, hv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          a0 += hv[j] * sw[(0 * 9 + t) * C + c + j];
+          a1 += hv[j] * sw[(1 * 9 + t) * C + c + j];
+          a2 += hv[j] * sw[(2 * 9 + t) * C + c + j];
+        }
+      }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane < 3) {
+      float a = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+      long long o = (((long long)b * 3 + lane) * H + py) * W + px;
+      out[o] = a + bias[lane] + x[o];
+    }
+  }
+}
+
+template <typename T>
+__global__ void dec_tail_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w, View h,
+                                         View dh, int B, int H, int W) {
+  extern __shared__ float sw[];  // [27][C]
+  const int C = h.C;
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  constexpr int V = Vec<T>::N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  long long npx = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * wpb + warp; p < npx; p += (long long)gridDim.x * wpb) {
+    int px = (int)(p % W);
+    long long r = p / W;
+    int py = (int)(r % H);
+    int b = (int)(r / H);
+    // dh[p,c] = sum_t sum_co dout(p - tap_t)[co] * w[co][t][c]
+    float d[27];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      int yy = py - (t / 3 - 1), xx = px - (t % 3 - 1);
+      bool in = (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
+#pragma unroll
+      for (int co = 0; co < 3; ++co) d[co * 9 + t] = in ? dout[(((long long)b * 3 + co) * H + yy) * W + xx] : 0.f;
+    }
+    for (int c = lane * V; c < C; c += 32 * V) {
+      float acc[V], hv[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 27; ++q) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += d[q] * sw[q * C + c + j];
+      }
+      Vec<T>::ld((const T*)h.ptr + view_off(h, b, py + h.oy, px + h.ox) + c, hv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = hv[j] > 0.f ? acc[j] : 0.f;
+      Vec<T>::st((T*)dh.ptr + view_off(dh, b, py + dh.oy, px + dh.ox) + c, acc);
+    }
+  }
+}
+
+// thread per channel, block per pixel chunk; partial [nblk][27][C] then reduce
+template <typename T>
+__global__ void dec_tail_bwd_weight_partial(const float* __restrict__ dout, View h, float* __restrict__ part,
+                                            float* __restrict__ bpart, int B, int H, int W, int chunk) {
+  const int C = h.C;
+  long long npx = (long long)B * H * W;
+  long long p0 = (long long)blockIdx.x * chunk, p1 = p0 + chunk < npx ? p0 + chunk : npx;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc[q] = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      int px = (int)(p % W);
+      long long r = p / W;
+      int py = (int)(r % H);
+      int b = (int)(r / H);
+      float d0 = dout[(((long long)b * 3 + 0) * H + py) * W + px];
+      float d1 = dout[(((long long)b * 3 + 1) * H + py) * W + px];
+      float d2 = dout[(((long long)b * 3 + 2) * H + py) * W + px];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        int yy = py + t / 3 - 1 + h.oy, xx = px + t % 3 - 1 + h.ox;
+        float hv = view_inb(h, yy, xx) ? to_f<T>(((const T*)h.ptr)[view_off(h, b, yy, xx) + c]) : 0.f;
+        acc[0 * 9 + t] += d0 * hv;
+        acc[1 * 9 + t] += d1 * hv;
+        acc[2 * 9 + t] += d2 * hv;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 27; ++q) part[((long long)blockIdx.x * 27 + q) * C + c] = acc[q];
+  }
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      int px = (int)(p % W);
+      long long r = p / W;
+      int py = (int)(r % H);
+      int b = (int)(r / H);
+      s += dout[(((long long)b * 3 + threadIdx.x) * H + py) * W + px];
+    }
+    bpart[blockIdx.x * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int nblk, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += part[(long long)b * n + i];
+  out[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// L1 loss fused fwd + bwd; deterministic two-level reduction (ticket pattern)
+// ---------------------------------------------------------------------------------------------
+#define L1_MAX_BLOCKS 2048
+__device__ float g_l1_partials[L1_MAX_BLOCKS];
+__device__ unsigned int g_l1_ticket = 0;
+
+__global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float gscale,
+                          float* __restrict__ loss, float* __restrict__ grad) {
+  float s = 0.f;
+  const float gs = gscale / (float)n;
+  long long n4 = n >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  float4* g4 = reinterpret_cast<float4*>(grad);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 x = a4[i], y = b4[i];
+    float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+    s += fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+    if (grad) {
+      float4 g;
+      g.x = d0 > 0.f ? gs : (d0 < 0.f ? -gs : 0.f);
+      g.y = d1 > 0.f ? gs : (d1 < 0.f ? -gs : 0.f);
+      g.z = d2 > 0.f ? gs : (d2 < 0.f ? -gs : 0.f);
+      g.w = d3 > 0.f ? gs : (d3 < 0.f ? -gs : 0.f);
+      g4[i] = g;
+    }
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = a[i] - b[i];
+    s += fabsf(d);
+    if (grad) grad[i] = d > 0.f ? gs : (d < 0.f ? -gs : 0.f);
+  }
+  __shared__ float ws[32];
+  __shared__ bool last;
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      g_l1_partials[blockIdx.x] = t;
+      __threadfence();
+      unsigned int tk = atomicAdd(&g_l1_ticket, 1u);
+      last = (tk == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    double t = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += (double)((volatile float*)g_l1_partials)[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) {
+      loss[0] = (float)(t / (double)n);
+      g_l1_ticket = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// preprocessing (+ optional crop)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float prep_normal(float v) {
+  // np.nan_to_num: nan -> 0, +-inf -> +-FLT_MAX; then (v+1)/2 clamped to [0,1]
+  if (isnan(v)) v = 0.f;
+  else if (isinf(v)) v = v > 0.f ? 3.4028234664e38f : -3.4028234664e38f;
+  v = (v + 1.0f) * 0.5f;
+  return fmaxf(fminf(v, 1.0f), 0.0f);
+}
+
+// frames NHWC [Hf][Wf][C] (or patches [n][P][P][C] when centres == NULL) -> NCHW [n][C][P][P]
+__global__ void crop_preprocess_kernel(const float* __restrict__ src, float* __restrict__ dst, int Hf, int Wf, int C,
+                                       const int* __restrict__ centres, const int* __restrict__ img_idx, int n, int P,
+                                       int kind /*0 log1p, 1 aux*/) {
+  long long total = (long long)n * C * P * P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % P);
+    long long r = i / P;
+    int y = (int)(r % P); r /= P;
+    int c = (int)(r % C);
+    int b = (int)(r / C);
+    float v;
+    if (centres) {
+      int cx = centres[2 * b], cy = centres[2 * b + 1];
+      long long f = img_idx ? (long long)img_idx[b] * Hf * Wf : 0;
+      v = src[(f + (long long)(cy - P / 2 + y) * Wf + (cx - P / 2 + x)) * C + c];
+    } else {
+      v = src[(((long long)b * P + y) * P + x) * C + c];
+    }
+    if (kind == 0) v = logf(v + 1.0f);
+    else if (c < 3) v = prep_normal(v);
+    dst[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (flat arena)
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float step_size, float beta1, float beta2, float eps,
+                            float inv_sqrt_bc2, float gscale) {
+  long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg *= gscale;
+    mm = mm + (1.0f - beta1) * (gg - mm);            // torch: exp_avg.lerp_(grad, 1 - beta1)
+    vv = vv * beta2 + (1.0f - beta2) * gg * gg;      // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;    // (sqrt(v) / sqrt(bc2)) + eps
+    pp = pp - step_size * (mm / denom);              // p.addcdiv_(m, denom, value=-lr/bc1)
+  };
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    upd(p[i], g[i], m[i], v[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight pack / unpack
+// ---------------------------------------------------------------------------------------------
+struct PackP {
+  int O, I, ks, Ntot, Ktot, n_off, k_off, transpose, grid, i_begin, i_count;
+  float scale;
+};
+__device__ __forceinline__ long long packed_index(const PackP& a, int o, int i, int ky, int kx) {
+  if (a.grid > 0) {
+    int e = (a.grid - a.ks) / 2;
+    int k = a.k_off + ((ky + e) * a.grid + (kx + e)) * a.i_count + i;
+    return (long long)(a.n_off + o) * a.Ktot + k;
+  }
+  int t = ky * a.ks + kx, T = a.ks * a.ks;
+  if (!a.transpose) return ((long long)t * a.Ntot + a.n_off + o) * a.Ktot + a.k_off + i;
+  return ((long long)(T - 1 - t) * a.Ntot + a.n_off + i) * a.Ktot + a.k_off + o;
+}
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* dst, PackP a) {
+  long long total = (long long)a.O * a.I * a.ks * a.ks;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int kx = (int)(idx % a.ks);
+    long long r = idx / a.ks;
+    int ky = (int)(r % a.ks); r /= a.ks;
+    int i = (int)(r % a.I);
+    int o = (int)(r / a.I);
+    if (i < a.i_begin || i >= a.i_begin + a.i_count) continue;
+    dst[packed_index(a, o, i - a.i_begin, ky, kx)] = from_f<T>(w[idx] * a.scale);
+  }
+}
+__global__ void unpack_wgrad_kernel(float* __restrict__ wg, const float* __restrict__ src, PackP a) {
+  long long total = (long long)a.O * a.I * a.ks * a.ks;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int kx = (int)(idx % a.ks);
+    long long r = idx / a.ks;
+    int ky = (int)(r % a.ks); r /= a.ks;
+    int i = (int)(r % a.I);
+    int o = (int)(r / a.I);
+    if (i < a.i_begin || i >= a.i_begin + a.i_count) continue;
+    wg[idx] = src[packed_index(a, o, i - a.i_begin, ky, kx)] * a.scale;
+  }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ s, long long sld, D* __restrict__ d, long long dld, long long rows,
+                            long long cols) {
+  long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / cols, c = i % cols;
+    d[r * dld + c] = from_f<D>(to_f<S>(s[r * sld + c]));
+  }
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace pht
+
+using namespace pht;
+
+extern "C" {
+
+int pht_border_fill(void* buf, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode, void* stream) {
+  PHT_CHECK_ARG(buf && B > 0 && H > 0 && W > 0, "border_fill: bad args");
+  PHT_CHECK_ARG(mode == PHT_PAD_REPLICATE || (mode == PHT_PAD_REFLECT && H > 1 && W > 1), "border_fill: bad mode");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PHT_F32) {
+    PHT_CHECK_ARG(C % 4 == 0, "border_fill: C %% 4 != 0");
+    long long items = (long long)B * (2 * (W + 2) + 2 * H) * (C / 4);
+    border_fill_kernel<float><<<grid_for(items, 256), 256, 0, st>>>((float*)buf, B, H, W, C, mode);
+  } else {
+    PHT_CHECK_ARG(C % 8 == 0, "border_fill: C %% 8 != 0");
+    long long items = (long long)B * (2 * (W + 2) + 2 * H) * (C / 8);
+    border_fill_kernel<bf16><<<grid_for(items, 256), 256, 0, st>>>((bf16*)buf, B, H, W, C, mode);
+  }
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_pad_fold(const void* gpad, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode,
+                 const pht_view* resid, const pht_view* mask, const float* mslope, const pht_view* out1,
+                 const pht_view* out2, void* stream) {
+  PHT_CHECK_ARG(gpad && B > 0 && H > 0 && W > 0, "pad_fold: bad args");
+  PHT_CHECK_ARG((out1 && out1->ptr) || (out2 && out2->ptr), "pad_fold: no output");
+  cudaStream_t st = (cudaStream_t)stream;
+  View r = make_view(resid), m = make_view(mask), o1 = make_view(out1), o2 = make_view(out2);
+  if (dtype == PHT_F32) {
+    PHT_CHECK_ARG(C % 4 == 0, "pad_fold: C %% 4 != 0");
+    long long items = (long long)B * H * W * (C / 4);
+    pad_fold_kernel<float><<<grid_for(items, 256), 256, 0, st>>>((const float*)gpad, B, H, W, C, mode, r, m, mslope, o1, o2);
+  } else {
+    PHT_CHECK_ARG(C % 8 == 0, "pad_fold: C %% 8 != 0");
+    long long items = (long long)B * H * W * (C / 8);
+    pad_fold_kernel<bf16><<<grid_for(items, 256), 256, 0, st>>>((const bf16*)gpad, B, H, W, C, mode, r, m, mslope, o1, o2);
+  }
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_im2col5(const float* x, void* col, int32_t dtype, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Kpad,
+                int32_t mode, void* stream) {
+  PHT_CHECK_ARG(x && col && Kpad >= 25 * Cin, "im2col5: bad args");
+  PHT_CHECK_ARG(mode == PHT_PAD_REPLICATE || (H > 2 && W > 2), "im2col5: reflect needs H,W > 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long items = (long long)B * H * W * Kpad;
+  if (dtype == PHT_F32) im2col5_kernel<float><<<grid_for(items, 256), 256, 0, st>>>(x, (float*)col, B, Cin, H, W, Kpad, mode);
+  else im2col5_kernel<bf16><<<grid_for(items, 256), 256, 0, st>>>(x, (bf16*)col, B, Cin, H, W, Kpad, mode);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_dec_tail_fwd(const pht_view* h, const float* w, const float* bias, const float* x, float* out, int32_t B,
+                     int32_t H, int32_t W, void* stream) {
+  PHT_CHECK_ARG(h && h->ptr && w && bias && x && out, "dec_tail_fwd: null arg");
+  View hv = make_view(h);
+  size_t smem = (size_t)27 * hv.C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for((long long)B * H * W * 32, 256);
+  if (hv.dtype == PHT_F32) {
+    PHT_CHECK_ARG(hv.C % 4 == 0, "dec_tail: C %% 4");
+    PHT_CUDA(cudaFuncSetAttribute(dec_tail_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dec_tail_fwd_kernel<float><<<grid, 256, smem, st>>>(hv, w, bias, x, out, B, H, W);
+  } else {
+    PHT_CHECK_ARG(hv.C % 8 == 0, "dec_tail: C %% 8");
+    PHT_CUDA(cudaFuncSetAttribute(dec_tail_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dec_tail_fwd_kernel<bf16><<<grid, 256, smem, st>>>(hv, w, bias, x, out, B, H, W);
+  }
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_dec_tail_bwd_data(const float* dout, const float* w, const pht_view* h, const pht_view* dh, int32_t B,
+                          int32_t H, int32_t W, void* stream) {
+  PHT_CHECK_ARG(dout && w && h && h->ptr && dh && dh->ptr, "dec_tail_bwd_data: null arg");
+  View hv = make_view(h), dv = make_view(dh);
+  PHT_CHECK_ARG(hv.dtype == dv.dtype && hv.C == dv.C, "dec_tail_bwd_data: view mismatch");
+  size_t smem = (size_t)27 * hv.C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for((long long)B * H * W * 32, 256);
+  if (hv.dtype == PHT_F32) {
+    PHT_CUDA(cudaFuncSetAttribute(dec_tail_bwd_data_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dec_tail_bwd_data_kernel<float><<<grid, 256, smem, st>>>(dout, w, hv, dv, B, H, W);
+  } else {
+    PHT_CUDA(cudaFuncSetAttribute(dec_tail_bwd_data_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dec_tail_bwd_data_kernel<bf16><<<grid, 256, smem, st>>>(dout, w, hv, dv, B, H, W);
+  }
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+static int dec_tail_blocks(long long npx, int* chunk) {
+  int nb = num_sms() * 4;
+  if (npx < nb * 32) nb = (int)((npx + 31) / 32);
+  if (nb < 1) nb = 1;
+  *chunk = (int)((npx + nb - 1) / nb);
+  return (int)((npx + *chunk - 1) / *chunk);
+}
+size_t pht_dec_tail_ws_bytes(int32_t B, int32_t H, int32_t W, int32_t C) {
+  int chunk;
+  int nb = dec_tail_blocks((long long)B * H * W, &chunk);
+  return (size_t)nb * (27 * (size_t)C + 3) * sizeof(float);
+}
+int pht_dec_tail_bwd_weight(const float* dout, const pht_view* h, float* dw, float* dbias, void* workspace,
+                            size_t workspace_bytes, int32_t B, int32_t H, int32_t W, void* stream) {
+  PHT_CHECK_ARG(dout && h && h->ptr && dw && dbias && workspace, "dec_tail_bwd_weight: null arg");
+  View hv = make_view(h);
+  int chunk;
+  int nb = dec_tail_blocks((long long)B * H * W, &chunk);
+  PHT_CHECK_ARG(workspace_bytes >= pht_dec_tail_ws_bytes(B, H, W, hv.C), "dec_tail_bwd_weight: workspace too small");
+  float* part = (float*)workspace;
+  float* bpart = part + (size_t)nb * 27 * hv.C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hv.dtype == PHT_F32) dec_tail_bwd_weight_partial<float><<<nb, 256, 0, st>>>(dout, hv, part, bpart, B, H, W, chunk);
+  else dec_tail_bwd_weight_partial<bf16><<<nb, 256, 0, st>>>(dout, hv, part, bpart, B, H, W, chunk);
+  PHT_LAUNCH_CHECK();
+  int n = 27 * hv.C;
+  reduce_partials_kernel<<<ceil_div(n, 256), 256, 0, st>>>(part, dw, nb, n);
+  reduce_partials_kernel<<<1, 32, 0, st>>>(bpart, dbias, nb, 3);
+  count_launch(CNT_OTHER, 3);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, float* loss, float* grad, void* stream) {
+  PHT_CHECK_ARG(a && b && loss && n > 0, "l1_loss: bad args");
+  PHT_CHECK_ARG((((uintptr_t)a | (uintptr_t)b | (uintptr_t)grad) & 15) == 0, "l1_loss: pointers must be 16B aligned");
+  int grid = grid_for((n + 3) / 4, 256);
+  if (grid > L1_MAX_BLOCKS) grid = L1_MAX_BLOCKS;
+  l1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, (long long)n, grad_scale, loss, grad);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_preprocess(const float* noisy, const float* gt, const float* aux, float* noisy_o, float* gt_o, float* aux_o,
+                   int32_t B, int32_t H, int32_t W, void* stream) {
+  PHT_CHECK_ARG(noisy && aux && noisy_o && aux_o && H == W, "preprocess: bad args (square patches only)");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long n3 = (long long)B * 3 * H * W, n7 = (long long)B * 7 * H * W;
+  crop_preprocess_kernel<<<grid_for(n3, 256), 256, 0, st>>>(noisy, noisy_o, 0, 0, 3, nullptr, nullptr, B, H, 0);
+  if (gt) crop_preprocess_kernel<<<grid_for(n3, 256), 256, 0, st>>>(gt, gt_o, 0, 0, 3, nullptr, nullptr, B, H, 0);
+  crop_preprocess_kernel<<<grid_for(n7, 256), 256, 0, st>>>(aux, aux_o, 0, 0, 7, nullptr, nullptr, B, H, 1);
+  count_launch(CNT_OTHER, gt ? 3 : 2);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_crop_preprocess(const float* noisy_f, const float* gt_f, const float* aux_f, int32_t Hf, int32_t Wf,
+                        const int32_t* centres, const int32_t* img_idx, int32_t n, int32_t P, float* noisy_o,
+                        float* gt_o, float* aux_o, void* stream) {
+  PHT_CHECK_ARG(noisy_f && aux_f && centres && noisy_o && aux_o && n > 0 && P > 0, "crop_preprocess: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long n3 = (long long)n * 3 * P * P, n7 = (long long)n * 7 * P * P;
+  crop_preprocess_kernel<<<grid_for(n3, 256), 256, 0, st>>>(noisy_f, noisy_o, Hf, Wf, 3, centres, img_idx, n, P, 0);
+  if (gt_f) crop_preprocess_kernel<<<grid_for(n3, 256), 256, 0, st>>>(gt_f, gt_o, Hf, Wf, 3, centres, img_idx, n, P, 0);
+  crop_preprocess_kernel<<<grid_for(n7, 256), 256, 0, st>>>(aux_f, aux_o, Hf, Wf, 7, centres, img_idx, n, P, 1);
+  count_launch(CNT_OTHER, gt_f ? 3 : 2);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+             int32_t step, float grad_scale, void* stream) {
+  PHT_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adam: bad args");
+  PHT_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam: pointers must be 16B aligned");
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  float step_size = (float)((double)lr / bc1);
+  float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (long long)n, step_size, beta1,
+                                                                          beta2, eps, inv_sqrt_bc2, grad_scale);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+static int check_pack(const pht_pack_args* a, PackP* p) {
+  PHT_CHECK_ARG(a && a->w && a->packed, "pack: null arg");
+  PHT_CHECK_ARG(a->ksize == 1 || a->ksize == 3 || a->ksize == 5, "pack: ksize");
+  p->O = a->O; p->I = a->I; p->ks = a->ksize; p->Ntot = a->Ntot; p->Ktot = a->Ktot; p->n_off = a->n_off;
+  p->k_off = a->k_off; p->transpose = a->transpose; p->grid = a->grid; p->scale = a->scale;
+  p->i_begin = a->i_begin; p->i_count = a->i_count > 0 ? a->i_count : a->I - a->i_begin;
+  PHT_CHECK_ARG(p->i_begin >= 0 && p->i_count > 0 && p->i_begin + p->i_count <= a->I, "pack: bad input-channel slice");
+  const int Ic = p->i_count;
+  if (a->grid > 0) {
+    PHT_CHECK_ARG(a->grid >= a->ksize && !a->transpose, "pack: bad embed");
+    PHT_CHECK_ARG(a->k_off + a->grid * a->grid * Ic <= a->Ktot && a->n_off + a->O <= a->Ntot, "pack: embed out of range");
+  } else if (!a->transpose) {
+    PHT_CHECK_ARG(a->n_off + a->O <= a->Ntot && a->k_off + Ic <= a->Ktot, "pack: out of range");
+  } else {
+    PHT_CHECK_ARG(a->n_off + Ic <= a->Ntot && a->k_off + a->O <= a->Ktot, "pack: out of range (T)");
+  }
+  return PHT_OK;
+}
+int pht_pack_weight(const pht_pack_args* a, void* stream) {
+  PackP p;
+  int rc = check_pack(a, &p);
+  if (rc) return rc;
+  long long total = (long long)p.O * p.I * p.ks * p.ks;
+  if (a->dtype == PHT_F32) pack_weight_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a->w, (float*)a->packed, p);
+  else pack_weight_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a->w, (bf16*)a->packed, p);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+int pht_unpack_wgrad(const pht_pack_args* a, void* stream) {
+  PackP p;
+  int rc = check_pack(a, &p);
+  if (rc) return rc;
+  PHT_CHECK_ARG(!a->transpose, "unpack: transpose unsupported");
+  long long total = (long long)p.O * p.I * p.ks * p.ks;
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((float*)a->w, (const float*)a->packed, p);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_cast2d(const void* src, int32_t sd, int64_t sld, void* dst, int32_t dd, int64_t dld, int64_t rows, int64_t cols,
+               void* stream) {
+  PHT_CHECK_ARG(src && dst && rows > 0 && cols > 0 && sld >= cols && dld >= cols, "cast: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = grid_for(rows * cols, 256);
+  if (sd == PHT_F32 && dd == PHT_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, sld, (bf16*)dst, dld, rows, cols);
+  else if (sd == PHT_BF16 && dd == PHT_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, sld, (float*)dst, dld, rows, cols);
+  else if (sd == PHT_F32 && dd == PHT_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, sld, (float*)dst, dld, rows, cols);
+  else if (sd == PHT_BF16 && dd == PHT_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, sld, (bf16*)dst, dld, rows, cols);
+  else PHT_CHECK_ARG(false, "cast: bad dtype");
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+int pht_cast(const void* src, int32_t sd, void* dst, int32_t dd, int64_t n, void* stream) {
+  return pht_cast2d(src, sd, n, dst, dd, n, 1, n, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Error reporting, launch counters, ABI introspection.
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pht {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_counters[8];
+static std::atomic<int> g_force_simple{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int slot, uint64_t n) { g_counters[slot & 7].fetch_add(n, std::memory_order_relaxed); }
+bool force_simple() { return g_force_simple.load(std::memory_order_relaxed) != 0; }
+
+}  // namespace pht
+
+extern "C" {
+
+int pht_abi_version(void) { return PHT_ABI_VERSION; }
+const char* pht_last_error(void) { return pht::g_err; }
+void pht_get_counters(uint64_t* c) {
+  for (int i = 0; i < 8; ++i) c[i] = pht::g_counters[i].load(std::memory_order_relaxed);
+}
+void pht_reset_counters(void) {
+  for (int i = 0; i < 8; ++i) pht::g_counters[i].store(0, std::memory_order_relaxed);
+}
+void pht_set_force_simple(int on) { pht::g_force_simple.store(on ? 1 : 0, std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,368 @@
+"""Kernel orchestration for the AFGSA generator (forward, backward, weight packing).
+
+This is the host-side schedule of C-ABI launches that replaces the reference's
+``AFGSANet.forward`` (pht/models/afgsa/model.py:717-733) and its autograd
+backward.  Layout decisions:
+
+* activations are channels-last, in the compute dtype (bf16 production / fp32
+  parity); inputs of 3x3 convolutions live in padded buffers [B, H+2, W+2, C]
+  whose 1-px border is filled by ``pht_border_fill`` (replicate / reflect), so
+  the convolution itself is a plain shifted-window GEMM (TMA friendly);
+* ``torch.cat`` never materialises: concatenated inputs are extra K-sources;
+* the 1x1/3x3/5x5 encoder branches are one GEMM over a 5x5 im2col;
+* data-gradients of padded convolutions are computed over the padded domain and
+  folded back by ``pht_pad_fold`` (which also applies the residual add and the
+  activation-derivative mask of the producing layer).
+"""
+from __future__ import annotations
+
+import torch
+
+from ... import ops
+from ..._lib import PAD_MODES
+
+LEAKY = 0.2
+ENC_KPAD = {3: 128, 7: 192}  # 25*Cin rounded up to a multiple of 64
+
+
+class _Arena:
+    """Named persistent device buffers for one (B, H, W, dtype, tag)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: dict[str, torch.Tensor] = {}
+
+    def get(self, name, shape, dtype, zero=False):
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+class AfgsaEngine:
+    def __init__(self, net):
+        self.net = net
+        self.C = net.base_ch
+        self.heads, self.block, self.halo = net.num_heads, net.block_size, net.halo_size
+        self.num_sa = net.num_sa
+        self.d = self.C // self.heads
+        self.win = self.block + 2 * self.halo
+        self.scale = float(self.d) ** -0.5
+        self.pad_mode = PAD_MODES[net.padding_mode]
+        self._arenas: dict[tuple, _Arena] = {}
+        self._packed: dict[str, torch.Tensor] = {}
+        self._consts: dict[str, torch.Tensor] = {}
+        self._packed_key = None
+        self._saved_gen = {}
+        self._gen = 0
+        # data-parallel hook: called with "decoder" / "block<i>" / "encoders" as soon as that group's
+        # parameter gradients are final in net.flat_grad (parallel.GradBucketer.ready)
+        self.grad_ready_hook = None
+
+    def _ready(self, tag):
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(tag)
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def dtype(self):
+        return self.net.compute_dtype
+
+    @property
+    def device(self):
+        return self.net.flat_param.device
+
+    def _arena(self, B, H, W, tag):
+        key = (B, H, W, self.dtype, tag)
+        a = self._arenas.get(key)
+        if a is None:
+            a = self._arenas[key] = _Arena(self.device)
+        return a
+
+    def _const(self, name, values):
+        t = self._consts.get(name)
+        if t is None or t.device != self.device:
+            t = self._consts[name] = torch.tensor(values, dtype=torch.float32, device=self.device)
+        return t
+
+    def _pk(self, name, shape):
+        t = self._packed.get(name)
+        if t is None or t.dtype != self.dtype or t.device != self.device or tuple(t.shape) != tuple(shape):
+            t = self._packed[name] = torch.zeros(shape, dtype=self.dtype, device=self.device)
+        return t
+
+    # ------------------------------------------------------------------ weights
+    def pack_weights(self, backward: bool):
+        """(Re)pack the fp32 OIHW master weights into the kernels' [tap][N][K]
+        layout (and the flipped/transposed copies the data-gradients use)."""
+        net, C = self.net, self.C
+        P = dict(net.named_parameters())
+        pw = ops.pack_weight
+        # encoders: 1x1 / 3x3 / 5x5 kernels embedded in the 5x5 im2col K axis
+        for tag, names, cin in (("encN", ("conv1", "conv3", "conv5"), net.input_channels),
+                                ("encA", ("conv_a1", "conv_a3", "conv_a5"), net.aux_input_channels)):
+            kpad = ENC_KPAD.get(cin, ((25 * cin + 63) // 64) * 64)
+            wp = self._pk(tag, (1, 768, kpad))
+            for j, (nm, ks) in enumerate(zip(names, (1, 3, 5))):
+                pw(P[f"{nm}.0.weight"], wp, ksize=ks, Ntot=768, Ktot=kpad, n_off=256 * j, grid=5)
+        for nm, I in (("conv_map", 768), ("conv_aenc1", 768), ("conv_aenc2", C)):
+            pw(P[f"{nm}.0.weight"], self._pk(nm, (1, C, I)), ksize=1, Ntot=C, Ktot=I)
+            if backward:
+                pw(P[f"{nm}.0.weight"], self._pk(nm + ".T", (1, I, C)), ksize=1, Ntot=I, Ktot=C, transpose=1)
+        for i in range(self.num_sa):
+            pre = f"transformer_blocks.{i}."
+            wmap, wq, wk, wv = (P[pre + "attention.conv_map.0.weight"], P[pre + "attention.q_conv.weight"],
+                                P[pre + "attention.k_conv.weight"], P[pre + "attention.v_conv.weight"])
+            pw(wmap, self._pk(f"b{i}.map", (1, C, 2 * C)), ksize=1, Ntot=C, Ktot=2 * C)
+            wqk = self._pk(f"b{i}.qk", (1, 2 * C, C))
+            pw(wq, wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=0, scale=self.scale)
+            pw(wk, wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=C)
+            pw(wv, self._pk(f"b{i}.v", (1, C, C)), ksize=1, Ntot=C, Ktot=C)
+            for j in (0, 1):
+                w = P[pre + f"feed_forward.{j}.0.weight"]
+                pw(w, self._pk(f"b{i}.ff{j}", (9, C, C)), ksize=3, Ntot=C, Ktot=C)
+                if backward:
+                    pw(w, self._pk(f"b{i}.ff{j}.T", (9, C, C)), ksize=3, Ntot=C, Ktot=C, transpose=1)
+            if backward:
+                wqkT = self._pk(f"b{i}.qk.T", (1, C, 2 * C))       # dM = [dQ | dK] @ [s*Wq ; Wk]
+                pw(wq, wqkT, ksize=1, Ntot=C, Ktot=2 * C, k_off=0, transpose=1, scale=self.scale)
+                pw(wk, wqkT, ksize=1, Ntot=C, Ktot=2 * C, k_off=C, transpose=1)
+                wx = self._pk(f"b{i}.x.T", (1, C, 2 * C))          # dX = [dV | dMpre] @ [Wv ; Wmap[:, :C]]
+                pw(wv, wx, ksize=1, Ntot=C, Ktot=2 * C, k_off=0, transpose=1)
+                pw(wmap, wx, ksize=1, Ntot=C, Ktot=2 * C, k_off=C, transpose=1, i_begin=0, i_count=C)
+                pw(wmap, self._pk(f"b{i}.a.T", (1, C, C)), ksize=1, Ntot=C, Ktot=C, transpose=1, i_begin=C, i_count=C)
+        for j in (0, 1):
+            w = P[f"decoder.{j}.0.weight"]
+            pw(w, self._pk(f"dec{j}", (9, C, C)), ksize=3, Ntot=C, Ktot=C)
+            if backward:
+                pw(w, self._pk(f"dec{j}.T", (9, C, C)), ksize=3, Ntot=C, Ktot=C, transpose=1)
+        # decoder tail weights stay fp32: [3][9][C]
+        self._packed["dec2"] = P["decoder.2.0.weight"].detach().permute(0, 2, 3, 1).reshape(3, 9, C).contiguous()
+        self._packed["encN.bias"] = torch.cat([P[f"{n}.0.bias"].detach() for n in ("conv1", "conv3", "conv5")])
+        self._packed["encA.bias"] = torch.cat([P[f"{n}.0.bias"].detach() for n in ("conv_a1", "conv_a3", "conv_a5")])
+
+    def _maybe_pack(self, backward: bool):
+        key = (self.net.weights_version(), backward or (self._packed_key is not None and self._packed_key[1]),
+               self.dtype, str(self.device))
+        if key != self._packed_key:
+            self.pack_weights(key[1])
+            self._packed_key = key
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, aux, save: bool):
+        """x [B,3,H,W], aux [B,7,H,W] fp32 NCHW -> out [B,3,H,W] fp32 NCHW."""
+        net, C, T = self.net, self.C, self.dtype
+        B, _, H, W = x.shape
+        if H % self.block or W % self.block:
+            raise AssertionError("feature map dimensions must be divisible by the block size")  # model.py:469-471
+        x = x.contiguous().float()
+        aux = aux.contiguous().float()
+        self._maybe_pack(backward=save)
+        A = self._arena(B, H, W, "train" if save else "eval")
+        pk, P = self._packed, dict(net.named_parameters())
+        relu = self._const("relu", [0.0] * C)
+        leaky = self._const("leaky", [LEAKY] * C)
+        slopeN = self._const("slopeN", [0.0] * 768)
+        slopeA = self._const("slopeA", [0.0] * 256 + [LEAKY] * 512)
+        mode = self.pad_mode
+        nb = lambda i: i if save else 0          # per-block buffers only when saving for backward
+        g = A.get
+
+        colN = g("colN", (B, H, W, pk["encN"].shape[-1]), T)
+        colA = g("colA", (B, H, W, pk["encA"].shape[-1]), T)
+        catN = g("catN", (B, H, W, 768), T)
+        catA = g("catA", (B, H, W, 768), T)
+        ops.im2col5(x, colN, mode)
+        ops.im2col5(aux, colA, mode)
+        ops.conv_gemm([colN], pk["encN"], 768, bias=pk["encN.bias"], slope=slopeN, out1=catN)
+        ops.conv_gemm([colA], pk["encA"], 768, bias=pk["encA.bias"], slope=slopeA, out1=catA)
+        Xp = g("Xp0", (B, H + 2, W + 2, C), T)
+        X = Xp[:, 1:-1, 1:-1, :]
+        ops.conv_gemm([catN], pk["conv_map"], C, bias=P["conv_map.0.bias"], slope=relu, out1=X)
+        A1 = g("A1", (B, H, W, C), T)
+        Af = g("A", (B, H, W, C), T)
+        ops.conv_gemm([catA], pk["conv_aenc1"], C, bias=P["conv_aenc1.0.bias"], slope=leaky, out1=A1)
+        ops.conv_gemm([A1], pk["conv_aenc2"], C, bias=P["conv_aenc2.0.bias"], slope=leaky, out1=Af)
+
+        for i in range(self.num_sa):
+            pre = f"transformer_blocks.{i}."
+            j = nb(i)
+            M = g(f"M{j}", (B, H, W, C), T)
+            QK = g(f"QK{j}", (B, H, W, 2 * C), T)
+            V = g(f"V{j}", (B, H, W, C), T)
+            X1p = g(f"X1p{j}", (B, H + 2, W + 2, C), T)
+            H1p = g(f"H1p{j}", (B, H + 2, W + 2, C), T)
+            H2 = g(f"H2{j}", (B, H, W, C), T)
+            lse = g(f"lse{j}", (B, H, W, self.heads), torch.float32)
+            Xn = g(f"Xp{(i + 1) if save else (i + 1) % 2}", (B, H + 2, W + 2, C), T)
+            X1 = X1p[:, 1:-1, 1:-1, :]
+            ops.conv_gemm([X, Af], pk[f"b{i}.map"], C, bias=P[pre + "attention.conv_map.0.bias"], slope=relu, out1=M)
+            ops.conv_gemm([M], pk[f"b{i}.qk"], 2 * C, out1=QK)
+            ops.conv_gemm([X], pk[f"b{i}.v"], C, out1=V)
+            ops.attn_fwd(QK[..., :C], QK[..., C:], V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], X1,
+                         heads=self.heads, block=self.block, halo=self.halo, resid=X, lse=lse)
+            ops.border_fill(X1p, mode)
+            ops.conv_gemm([X1p], pk[f"b{i}.ff0"], C, ksize=3, src_offsets=[(1, 1)],
+                          bias=P[pre + "feed_forward.0.0.bias"], slope=relu, out1=H1p[:, 1:-1, 1:-1, :])
+            ops.border_fill(H1p, mode)
+            ops.conv_gemm([H1p], pk[f"b{i}.ff1"], C, ksize=3, src_offsets=[(1, 1)],
+                          bias=P[pre + "feed_forward.1.0.bias"], slope=relu, resid=X1, resid_mode="post",
+                          out1=H2, out2=Xn[:, 1:-1, 1:-1, :])
+            Xp, X = Xn, Xn[:, 1:-1, 1:-1, :]
+
+        ops.border_fill(Xp, mode)
+        D1p = g("D1p", (B, H + 2, W + 2, C), T)
+        D2 = g("D2", (B, H, W, C), T)
+        ops.conv_gemm([Xp], pk["dec0"], C, ksize=3, src_offsets=[(1, 1)], bias=P["decoder.0.0.bias"], slope=relu,
+                      out1=D1p[:, 1:-1, 1:-1, :])
+        ops.border_fill(D1p, mode)
+        ops.conv_gemm([D1p], pk["dec1"], C, ksize=3, src_offsets=[(1, 1)], bias=P["decoder.1.0.bias"], slope=relu,
+                      out1=D2)
+        out = torch.empty_like(x)
+        ops.dec_tail_fwd(D2, pk["dec2"], P["decoder.2.0.bias"], x, out)
+        if save:
+            self._gen += 1
+            self._saved_gen[(B, H, W)] = self._gen
+            return out, (B, H, W, self._gen)
+        return out, None
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, token, d_out):
+        """d_out [B,3,H,W] fp32 -> writes every parameter gradient into
+        ``net.flat_grad`` (views of it are returned by the autograd Function)."""
+        B, H, W, gen = token
+        if self._saved_gen.get((B, H, W)) != gen:
+            raise RuntimeError("AFGSANet backward: the saved activations were overwritten by a later forward "
+                               "of the same shape (run backward before the next grad-enabled forward)")
+        net, C, T = self.net, self.C, self.dtype
+        d_out = d_out.contiguous().float()
+        A = self._arena(B, H, W, "train")
+        g, pk, mode = A.get, self._packed, self.pad_mode
+        G = net.grad_views()
+        P = dict(net.named_parameters())
+        relu0 = self._const("relu", [0.0] * C)
+        leaky = self._const("leaky", [LEAKY] * C)
+        slopeN = self._const("slopeN", [0.0] * 768)
+        slopeA = self._const("slopeA", [0.0] * 256 + [LEAKY] * 512)
+        npx = B * H * W
+
+        G0, G1, G2, GX, GA = (g(n, (B, H, W, C), T) for n in ("G0", "G1", "G2", "GX", "GA"))
+        GP = g("GP", (B, H + 2, W + 2, C), T)
+        dQK = g("dQK", (B, H, W, 2 * C), T)
+        dV = g("dV", (B, H, W, C), T)
+        dcat = g("dcat", (B, H, W, 768), T)
+        dk_acc = g("dk_acc", (npx, C), torch.float32)
+        dv_acc = g("dv_acc", (npx, C), torch.float32)
+        wtmp = g("wtmp", (9 * C * 768,), torch.float32)
+        btmp = g("btmp", (768,), torch.float32)
+        attn_ws = g("attn_ws", (max(ops.attn_bwd_workspace_bytes(dQK[..., :C], self.heads, self.block, self.halo), 16) // 4,),
+                    torch.float32)
+        tail_ws = g("tail_ws", (max(ops.dec_tail_ws_bytes(B, H, W, C), 16) // 4,), torch.float32)
+        wg_ws = g("wg_ws", (64 * 1024 * 1024 // 4,), torch.float32)
+        pdom = (B, H + 2, W + 2)
+
+        def conv3_wgrad(dy, src_pad, name):
+            w = wtmp[: 9 * C * C].view(9, C, C)
+            ops.wgrad(dy, [src_pad], w, ksize=3, dbias=G[name + ".bias"], workspace=wg_ws, src_offsets=[(1, 1)])
+            ops.unpack_wgrad(G[name + ".weight"], w, ksize=3, Ntot=C, Ktot=C)
+
+        def conv3_dgrad(dy, wT):
+            ops.conv_gemm([dy], wT, C, ksize=3, out_domain=pdom, src_offsets=[(-1, -1)], out1=GP)
+
+        # ---- decoder -------------------------------------------------------------------------
+        D1p, D2 = g("D1p", (B, H + 2, W + 2, C), T), g("D2", (B, H, W, C), T)
+        dw2 = wtmp[: 27 * C].view(3, 9, C)
+        ops.dec_tail_bwd_weight(d_out, D2, dw2, G["decoder.2.0.bias"], tail_ws)
+        G["decoder.2.0.weight"].copy_(dw2.view(3, 3, 3, C).permute(0, 3, 1, 2))
+        ops.dec_tail_bwd_data(d_out, pk["dec2"], D2, G0)                       # G0 = d(D2 pre-act)
+        conv3_wgrad(G0, D1p, "decoder.1.0")
+        conv3_dgrad(G0, pk["dec1.T"])
+        ops.pad_fold(GP, mode, mask=D1p[:, 1:-1, 1:-1, :], mslope=relu0, out2=G1)   # G1 = d(D1 pre-act)
+        Xlast = g(f"Xp{self.num_sa}", (B, H + 2, W + 2, C), T)
+        conv3_wgrad(G1, Xlast, "decoder.0.0")
+        self._ready("decoder")
+        conv3_dgrad(G1, pk["dec0.T"])
+        if self.num_sa > 0:
+            ops.pad_fold(GP, mode, mask=g(f"H2{self.num_sa - 1}", (B, H, W, C), T), mslope=relu0, out1=GX, out2=G0)
+        else:
+            ops.pad_fold(GP, mode, mask=Xlast[:, 1:-1, 1:-1, :], mslope=relu0, out2=G0)
+
+        Af, A1 = g("A", (B, H, W, C), T), g("A1", (B, H, W, C), T)
+        # ---- transformer blocks, last to first ------------------------------------------------
+        for i in reversed(range(self.num_sa)):
+            pre = f"transformer_blocks.{i}."
+            M, QK, V = g(f"M{i}", (B, H, W, C), T), g(f"QK{i}", (B, H, W, 2 * C), T), g(f"V{i}", (B, H, W, C), T)
+            X1p, H1p = g(f"X1p{i}", (B, H + 2, W + 2, C), T), g(f"H1p{i}", (B, H + 2, W + 2, C), T)
+            lse = g(f"lse{i}", (B, H, W, self.heads), torch.float32)
+            X = g(f"Xp{i}", (B, H + 2, W + 2, C), T)[:, 1:-1, 1:-1, :]
+            # GX = d(block output) raw, G0 = d(H2 pre-act)
+            conv3_wgrad(G0, H1p, pre + "feed_forward.1.0")
+            conv3_dgrad(G0, pk[f"b{i}.ff1.T"])
+            ops.pad_fold(GP, mode, mask=H1p[:, 1:-1, 1:-1, :], mslope=relu0, out2=G1)     # G1 = d(H1 pre-act)
+            conv3_wgrad(G1, X1p, pre + "feed_forward.0.0")
+            conv3_dgrad(G1, pk[f"b{i}.ff0.T"])
+            ops.pad_fold(GP, mode, resid=GX, out1=G2)                                      # G2 = dX1 = dO
+            # attention
+            dk_acc.zero_()
+            dv_acc.zero_()
+            ops.attn_bwd(QK[..., :C], QK[..., C:], V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], lse, G2,
+                         dQK[..., :C], dk_acc, dv_acc, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,
+                         heads=self.heads, block=self.block, halo=self.halo)
+            ops.cast2d(dk_acc, dQK.view(npx, 2 * C)[:, C:])
+            ops.cast2d(dv_acc, dV.view(npx, C))
+            wqk = wtmp[: 2 * C * C].view(1, 2 * C, C)
+            ops.wgrad(dQK, [M], wqk, workspace=wg_ws)
+            ops.unpack_wgrad(G[pre + "attention.q_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=0, scale=self.scale)
+            ops.unpack_wgrad(G[pre + "attention.k_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=C)
+            ops.wgrad(dV, [X], G[pre + "attention.v_conv.weight"], workspace=wg_ws)
+            ops.conv_gemm([dQK], pk[f"b{i}.qk.T"], C, mask=M, mslope=relu0, out2=G1)       # G1 = d(M pre-act)
+            ops.wgrad(G1, [X, Af], G[pre + "attention.conv_map.0.weight"], dbias=G[pre + "attention.conv_map.0.bias"],
+                      workspace=wg_ws)
+            self._ready(f"block{i}")
+            # d(block input) = dX1 + dV Wv + dMpre Wmap[:, :C]; also emit the next layer's masked gradient
+            if i > 0:
+                ops.conv_gemm([dV, G1], pk[f"b{i}.x.T"], C, resid=G2, resid_mode="pre",
+                              mask=g(f"H2{i - 1}", (B, H, W, C), T), mslope=relu0, out1=GX, out2=G0)
+            else:
+                ops.conv_gemm([dV, G1], pk[f"b{i}.x.T"], C, resid=G2, resid_mode="pre", mask=X, mslope=relu0, out2=G0)
+            # dA accumulates over blocks; the last accumulation applies LeakyReLU' of conv_aenc2
+            first = i == self.num_sa - 1
+            if i > 0:
+                ops.conv_gemm([G1], pk[f"b{i}.a.T"], C, resid=None if first else GA, resid_mode="pre", out1=GA)
+            else:
+                ops.conv_gemm([G1], pk[f"b{i}.a.T"], C, resid=None if first else GA, resid_mode="pre",
+                              mask=Af, mslope=leaky, out2=G2)                              # G2 = d(A pre-act)
+
+        # ---- noisy encoder: G0 = d(conv_map pre-act) -----------------------------------------------
+        catN, catA = g("catN", (B, H, W, 768), T), g("catA", (B, H, W, 768), T)
+        colN = g("colN", (B, H, W, pk["encN"].shape[-1]), T)
+        colA = g("colA", (B, H, W, pk["encA"].shape[-1]), T)
+        ops.wgrad(G0, [catN], G["conv_map.0.weight"], dbias=G["conv_map.0.bias"], workspace=wg_ws)
+        ops.conv_gemm([G0], pk["conv_map.T"], 768, mask=catN, mslope=slopeN, out2=dcat)
+        self._encoder_wgrad(dcat, colN, ("conv1", "conv3", "conv5"), net.input_channels, wtmp, btmp, wg_ws, G)
+        # ---- aux encoder: G2 = d(conv_aenc2 pre-act) ------------------------------------------------
+        if self.num_sa > 0:
+            ops.wgrad(G2, [A1], G["conv_aenc2.0.weight"], dbias=G["conv_aenc2.0.bias"], workspace=wg_ws)
+            ops.conv_gemm([G2], pk["conv_aenc2.T"], C, mask=A1, mslope=leaky, out2=G1)   # G1 = d(aenc1 pre-act)
+            ops.wgrad(G1, [catA], G["conv_aenc1.0.weight"], dbias=G["conv_aenc1.0.bias"], workspace=wg_ws)
+            ops.conv_gemm([G1], pk["conv_aenc1.T"], 768, mask=catA, mslope=slopeA, out2=dcat)
+            self._encoder_wgrad(dcat, colA, ("conv_a1", "conv_a3", "conv_a5"), net.aux_input_channels, wtmp, btmp,
+                                wg_ws, G)
+        else:  # no attention block consumes the aux features: their gradient is zero
+            for n in ("conv_a1", "conv_a3", "conv_a5", "conv_aenc1", "conv_aenc2"):
+                G[n + ".0.weight"].zero_()
+                G[n + ".0.bias"].zero_()
+        self._ready("encoders")
+        del self._saved_gen[(B, H, W)]
+
+    def _encoder_wgrad(self, dcat, col, names, cin, wtmp, btmp, wg_ws, G):
+        kpad = col.shape[-1]
+        w = wtmp[: 768 * kpad].view(1, 768, kpad)
+        ops.wgrad(dcat, [col], w, dbias=btmp, workspace=wg_ws)
+        for j, (nm, ks) in enumerate(zip(names, (1, 3, 5))):
+            ops.unpack_wgrad(G[f"{nm}.0.weight"], w, ksize=ks, Ntot=768, Ktot=kpad, n_off=256 * j, grid=5)
+            G[f"{nm}.0.bias"].copy_(btmp[256 * j: 256 * (j + 1)])

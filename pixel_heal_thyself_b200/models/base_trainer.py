@@ -1,0 +1,214 @@
+"""GAN trainer driving the B200 generator (reference: pht/models/base_trainer.py).
+
+Same template-method API as the reference's ``BaseTrainer`` -- abstract
+``create_generator()`` (the plug-in point, base_trainer.py:102-110), overridable
+``create_discriminator / create_losses / create_optimizers`` and ``train()`` --
+and the same per-iteration arithmetic (base_trainer.py:371-457), restated as
+``train_step`` so the benchmark can time exactly one step.  Differences, all
+B200-side: batches are preprocessed on the device by ``pht_preprocess`` /
+``pht_crop_preprocess`` instead of numpy on the host; the generator optimiser is
+the fused flat Adam; under torchrun the batch is sharded over ranks and the
+generator gradients are all-reduced bucket-by-bucket during backward; loss
+scalars are read back once per logging interval instead of every iteration.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+import random
+import time
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+from torch import optim
+from torch.optim import lr_scheduler
+
+from .. import parallel
+from ..config import Config
+from ..data import PatchDataset, synthetic_frames
+from ..optim import FlatAdam
+from .afgsa.discriminator import DiscriminatorVGG
+from .losses import GANLoss, GradientPenaltyLoss, L1ReconstructionLoss
+
+logger = logging.getLogger("pht")
+
+
+def set_determinism(seed: int, deterministic: bool = True) -> None:
+    """reference: base_trainer.py:50-67."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    if deterministic:
+        torch.backends.cudnn.deterministic = True
+        torch.backends.cudnn.benchmark = False
+
+
+class BaseTrainer(ABC):
+    def __init__(self, cfg: Config) -> None:
+        self.cfg = cfg
+        self.deterministic = cfg.trainer.deterministic
+        self.model_name = self.__class__.__name__.replace("Trainer", "")
+        self.rank, self.local_rank, self.world = parallel.init_distributed()
+        if not torch.cuda.is_available():
+            raise RuntimeError("the B200 trainer needs a CUDA device (there is no CPU path)")
+        self.device = torch.device("cuda", self.local_rank)
+        set_determinism(cfg.seed, self.deterministic)
+        self.padding_mode = "replicate" if self.deterministic else "reflect"  # base_trainer.py:334
+        self.G = self.D = None
+        self.g_only = False
+
+    # ------------------------------------------------------------------ factories (reference API)
+    @abstractmethod
+    def create_generator(self) -> torch.nn.Module:
+        """Create and return the generator (reference: base_trainer.py:102-110)."""
+
+    def create_discriminator(self) -> torch.nn.Module:
+        if self.cfg.model.discriminator.use_multiscale_discriminator:
+            raise NotImplementedError("multiscale discriminator is outside the AFGSA hot path")
+        return DiscriminatorVGG(3, 64, self.cfg.data.patches.patch_size).to(self.device)
+
+    def create_losses(self):
+        """(l1_loss, gan_loss, gp_loss, lpips_loss, ssim_loss) as in base_trainer.py:127-154."""
+        lc = self.cfg.model.losses
+        if lc.use_lpips_loss or lc.use_ssim_loss:
+            raise NotImplementedError("LPIPS / MS-SSIM losses need third-party weights/arithmetic that are not "
+                                      "available offline (SURVEY 8c: parity unpinned)")
+        return (L1ReconstructionLoss().to(self.device), GANLoss("wgan").to(self.device),
+                GradientPenaltyLoss(self.device).to(self.device), None, None)
+
+    def create_optimizers(self, G, D):  # noqa: N803
+        """Adam x2 + MultiStepLR(gamma 0.5) with the reference's milestones (base_trainer.py:177-204)."""
+        t = self.cfg.trainer
+        milestones = [i * t.lr_milestone - 1 for i in range(1, t.epochs // t.lr_milestone)]
+        opt_g = FlatAdam(G, lr=t.lr_g, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0 / self.world)
+        sch_g = lr_scheduler.MultiStepLR(opt_g, milestones=milestones, gamma=0.5)
+        opt_d = optim.Adam(D.parameters(), lr=t.lr_d, betas=(0.9, 0.999), eps=1e-8)
+        sch_d = lr_scheduler.MultiStepLR(opt_d, milestones=milestones, gamma=0.5)
+        return opt_g, sch_g, opt_d, sch_d
+
+    # ------------------------------------------------------------------ setup
+    def setup(self, g_only: bool = False) -> None:
+        self.g_only = g_only
+        self.G = self.create_generator()
+        self.D = None if g_only else self.create_discriminator()
+        self.l1_loss, self.gan_loss, self.gp_loss, _, _ = self.create_losses()
+        if g_only:
+            t = self.cfg.trainer
+            self.opt_g = FlatAdam(self.G, lr=t.lr_g, grad_scale=1.0 / self.world)
+            self.sch_g = self.opt_d = self.sch_d = None
+        else:
+            self.opt_g, self.sch_g, self.opt_d, self.sch_d = self.create_optimizers(self.G, self.D)
+        self.bucketer = None
+        if self.world > 1:
+            self.G._flatten()
+            self.bucketer = parallel.GradBucketer(lambda: self.G.flat_grad, self.G._offsets,
+                                                  [n for n, _ in self.G.named_parameters()], self.G.flat_param.numel())
+            self.G.engine.grad_ready_hook = self.bucketer.ready
+            # identical initial weights on every rank
+            torch.distributed.broadcast(self.G.flat_param, 0)
+            if self.D is not None:
+                for p in list(self.D.parameters()) + list(self.D.buffers()):
+                    torch.distributed.broadcast(p.data, 0)
+
+    def setup_data(self) -> PatchDataset:
+        d = self.cfg.data
+        if d.source != "synthetic":
+            raise NotImplementedError("only data.source=synthetic is available (no EXR / HDF5 readers in this image)")
+        s = d.synthetic
+        frames = synthetic_frames(s.num_images, s.height, s.width, self.cfg.seed, self.device)
+        return PatchDataset(frames, d.patches.patch_size, d.patches.num_patches, self.cfg.seed)
+
+    # ------------------------------------------------------------------ one iteration
+    def train_step(self, noisy, gt, aux):
+        """One iteration of base_trainer.py:388-457 on preprocessed NCHW device tensors.
+        Returns (g_loss, d_loss) as 0-dim device tensors (no host sync)."""
+        lw = self.cfg.model.losses
+        output = self.G(noisy, aux)
+        d_loss = None
+        if not self.g_only:
+            self.opt_d.zero_grad()
+            pred_fake = self.D(output.detach())
+            pred_real = self.D(gt)
+            d_loss = (self.gan_loss(pred_fake, False) + self.gan_loss(pred_real, True)) / 2 \
+                + lw.gp_loss_w * self.gp_loss(self.D, gt, output.detach())
+            d_loss.backward()
+            parallel.allreduce_module_grads(self.D, self.world)
+            self.opt_d.step()
+        self.opt_g.zero_grad()
+        g_loss = lw.l1_loss_w * self.l1_loss(output, gt)
+        if not self.g_only:
+            g_loss = lw.gan_loss_w * self.gan_loss(self.D(output), True) + g_loss
+        g_loss.backward()
+        if self.bucketer is not None:
+            self.bucketer.finish()
+        self.opt_g.step()
+        return g_loss.detach(), (d_loss.detach() if d_loss is not None else None)
+
+    # ------------------------------------------------------------------ full loop
+    def train(self) -> None:
+        cfg = self.cfg
+        if self.G is None:
+            self.setup()
+        ds = self.setup_data()
+        bs = cfg.trainer.batch_size
+        n = len(ds)
+        n_val = max(1, int(n * (1 - cfg.data_ratio)))
+        n_train = n - n_val
+        gen = torch.Generator().manual_seed(cfg.seed)
+        out_dir = cfg.paths.output_dir
+        if self.rank == 0:
+            os.makedirs(out_dir, exist_ok=True)
+        logger.info(f"Starting training: model={self.model_name}, seed={cfg.seed}, batch_size={bs}, "
+                    f"epochs={cfg.trainer.epochs}, world={self.world}, patches={n_train}")
+        for epoch in range(cfg.trainer.epochs):
+            start = time.time()
+            perm = torch.randperm(n_train, generator=gen)
+            idx = parallel.shard_indices(n_train, self.rank, self.world, bs, perm).to(self.device)
+            iters = idx.numel() // bs
+            acc_g = torch.zeros((), device=self.device)
+            acc_d = torch.zeros((), device=self.device)
+            for it in range(iters):
+                noisy, gt, aux = ds.batch_device(idx[it * bs:(it + 1) * bs])
+                g_loss, d_loss = self.train_step(noisy, gt, aux)
+                acc_g += g_loss / bs
+                if d_loss is not None:
+                    acc_d += d_loss / bs
+                if it % 10 == 0 or it == iters - 1:
+                    logger.debug(f"[Train] epoch={epoch + 1} iter={it + 1}/{iters}")
+            g_avg, d_avg = float(acc_g) / max(iters, 1), float(acc_d) / max(iters, 1)
+            logger.info(f"[Train] epoch={epoch + 1} summary: g_loss={g_avg:.4f} d_loss={d_avg:.4f} "
+                        f"time={int(time.time() - start)}s")
+            if self.rank == 0:
+                with open(os.path.join(out_dir, "train_loss.txt"), "a") as f:  # format: base_trainer.py:475-479
+                    f.write(f"Epoch: {epoch + 1} \tG loss: {g_avg:.4f} \tD Loss: {d_avg:.4f}\n")
+            if self.sch_g is not None:
+                self.sch_d.step()
+                self.sch_g.step()
+            if self.rank == 0 and epoch % cfg.trainer.save_interval == 0:
+                self._validate_and_save(epoch, ds, n_train, n_val, out_dir)
+
+    def _validate_and_save(self, epoch, ds, n_train, n_val, out_dir) -> None:
+        """Checkpoint (same file names / state_dict keys as base_trainer.py:521-533) and a patch-level
+        validation pass (mean relative-MSE and PSNR on the log-domain output)."""
+        path = os.path.join(out_dir, f"model_epoch{epoch + 1}")
+        os.makedirs(path, exist_ok=True)
+        torch.save(self.G.state_dict(), os.path.join(path, "G.pt"))
+        if self.D is not None:
+            torch.save(self.D.state_dict(), os.path.join(path, "D.pt"))
+        self.G.eval()
+        mse, cnt = 0.0, 0
+        with torch.no_grad():
+            for k in range(n_train, n_train + n_val):
+                noisy, gt, aux = ds.batch_device(torch.tensor([k], device=self.device))
+                out = self.G(noisy, aux)
+                mse += float(((out - gt) ** 2).mean())
+                cnt += 1
+        self.G.train()
+        psnr = 10 * math.log10(1.0 / max(mse / max(cnt, 1), 1e-12))
+        logger.info(f"[Val] epoch={epoch + 1} summary: log-domain mse={mse / max(cnt, 1):.6f} psnr={psnr:.3f}")
+        with open(os.path.join(out_dir, "evaluation.txt"), "a") as f:
+            f.write(f"Validation: {epoch + 1} \tAvg MSE(log): {mse / max(cnt, 1):.6f} \tAvg PSNR(log): {psnr:.4f}\n")

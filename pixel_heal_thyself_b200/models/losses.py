@@ -1,0 +1,66 @@
+"""Losses of the PHT trainer (reference: pht/models/losses.py).
+
+``L1ReconstructionLoss`` -- the image loss on the hot path -- runs the fused
+forward+backward CUDA kernel ``pht_l1_loss``.  The adversarial terms (WGAN
+critic loss, gradient penalty) belong to the PyTorch discriminator, which is
+adjacent to the hot path and stays stock PyTorch.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class _L1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, target):
+        a = inp.detach().contiguous().float()
+        b = target.detach().contiguous().float()
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        grad = torch.empty_like(a) if inp.requires_grad else None
+        ops.l1_loss(a, b, loss, grad)          # loss = mean|a-b|, grad = sign(a-b)/n in one pass
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        return (ctx.grad * go if ctx.grad is not None else None), None
+
+
+class L1ReconstructionLoss(nn.Module):
+    """mean(|input - target|) (reference: losses.py:175-184)."""
+
+    def forward(self, input_data: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return _L1Fn.apply(input_data, target)
+
+
+class GANLoss(nn.Module):
+    """WGAN critic loss (reference: losses.py:103-172, loss_type "wgan" as used at base_trainer.py:141)."""
+
+    def __init__(self, loss_type: str = "wgan") -> None:
+        super().__init__()
+        if loss_type != "wgan":
+            raise NotImplementedError("only the WGAN loss the AFGSA trainer uses is provided")
+        self.type = loss_type
+
+    def forward(self, input_data: torch.Tensor, target_is_real: bool) -> torch.Tensor:
+        return -input_data.mean() if target_is_real else input_data.mean()
+
+
+class GradientPenaltyLoss(nn.Module):
+    """WGAN-GP penalty (reference: losses.py:12-57): ((||grad_x D(x_hat)||_2 - 1)^2).mean()."""
+
+    def __init__(self, device: torch.device) -> None:
+        super().__init__()
+        self.device = device
+
+    def forward(self, D: nn.Module, real_data: torch.Tensor, fake_data: torch.Tensor) -> torch.Tensor:  # noqa: N803
+        alpha = torch.rand((real_data.shape[0], 1, 1, 1), dtype=torch.float32, device=self.device)
+        x_hat = (alpha * fake_data.detach() + (1 - alpha) * real_data).requires_grad_(True)
+        pred = D(x_hat)
+        grad = torch.autograd.grad(pred, x_hat, torch.ones_like(pred), create_graph=True, retain_graph=True)[0]
+        norm = grad.reshape(grad.size(0), -1).norm(2, dim=1)
+        return ((norm - 1) ** 2).mean()

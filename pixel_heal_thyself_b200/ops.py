@@ -1,0 +1,241 @@
+"""Tensor-level wrappers over the C ABI (one function per include/pht_b200.h op).
+
+All tensors are CUDA tensors; activations are channels-last [B, H, W, C]
+(possibly strided views of padded buffers).  Nothing here computes on the CPU
+or through torch ops: each function marshals pointers and launches kernels on
+the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import lib
+
+
+def conv_gemm(srcs, w, N, *, ksize=1, out_domain=None, bias=None, slope=None, resid=None, resid_mode=None, mask=None,
+              mslope=None, out1=None, out2=None, src_offsets=None):
+    """pht_conv_gemm.  srcs: list of [B,H,W,C] tensors (virtual concat along C).
+    out_domain: (B, Ho, Wo), default = shape of the first output.
+    src_offsets: list of (oy, ox) per source (default 0,0).
+    resid_mode: None | "pre" | "post"."""
+    a = L.ConvGemmArgs()
+    ref = out1 if out1 is not None else out2
+    L.require_cuda(*srcs, w, ref)
+    if out_domain is None:
+        out_domain = (ref.shape[0], ref.shape[1], ref.shape[2])
+    a.dtype = L.DTYPES[srcs[0].dtype]
+    a.B, a.Ho, a.Wo = out_domain
+    a.N, a.ksize, a.n_src = N, ksize, len(srcs)
+    flags = 0
+    for i, s in enumerate(srcs):
+        oy, ox = src_offsets[i] if src_offsets else (0, 0)
+        a.src[i] = L.view(s, oy, ox)
+    a.w = w.data_ptr()
+    a.bias, a.slope, a.mslope = L.ptr(bias), L.ptr(slope), L.ptr(mslope)
+    if resid is not None:
+        a.resid = L.view(resid)
+        flags |= L.EPI_RESID_PRE if resid_mode == "pre" else L.EPI_RESID_POST
+    if mask is not None:
+        a.mask = L.view(mask)
+        flags |= L.EPI_MASK
+    a.flags = flags
+    a.out1, a.out2 = L.view(out1), L.view(out2)
+    L.check(lib.pht_conv_gemm(C.byref(a), L.stream_ptr()), "pht_conv_gemm")
+
+
+def _wgrad_args(dy, srcs, ksize, dw, dbias, src_offsets):
+    a = L.WgradArgs()
+    a.dtype = L.DTYPES[dy.dtype]
+    a.B, a.Ho, a.Wo, a.N = dy.shape
+    a.ksize, a.n_src = ksize, len(srcs)
+    a.dy = L.view(dy)
+    for i, s in enumerate(srcs):
+        oy, ox = src_offsets[i] if src_offsets else (0, 0)
+        a.src[i] = L.view(s, oy, ox)
+    a.dw, a.dbias = L.ptr(dw), L.ptr(dbias)
+    return a
+
+
+def wgrad_workspace_bytes(dy, srcs, ksize=1, src_offsets=None) -> int:
+    a = _wgrad_args(dy, srcs, ksize, None, None, src_offsets)
+    return int(lib.pht_wgrad_workspace_bytes(C.byref(a)))
+
+
+def wgrad(dy, srcs, dw, *, ksize=1, dbias=None, workspace=None, src_offsets=None):
+    """pht_wgrad: dw fp32 [ksize*ksize][N][Ktot] (overwritten), dbias fp32 [N]."""
+    L.require_cuda(dy, *srcs, dw)
+    a = _wgrad_args(dy, srcs, ksize, dw, dbias, src_offsets)
+    if workspace is not None:
+        a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    L.check(lib.pht_wgrad(C.byref(a), L.stream_ptr()), "pht_wgrad")
+
+
+def border_fill(buf, mode):
+    """buf: padded [B, H+2, W+2, C] contiguous."""
+    L.require_cuda(buf)
+    assert buf.is_contiguous()
+    B, Hp, Wp, Cc = buf.shape
+    L.check(lib.pht_border_fill(buf.data_ptr(), L.DTYPES[buf.dtype], B, Hp - 2, Wp - 2, Cc, mode, L.stream_ptr()),
+            "pht_border_fill")
+
+
+def pad_fold(gpad, mode, *, resid=None, mask=None, mslope=None, out1=None, out2=None):
+    L.require_cuda(gpad)
+    assert gpad.is_contiguous()
+    B, Hp, Wp, Cc = gpad.shape
+    vs = [L.view(t) if t is not None else None for t in (resid, mask, out1, out2)]
+    refs = [C.byref(v) if v is not None else None for v in vs]
+    L.check(lib.pht_pad_fold(gpad.data_ptr(), L.DTYPES[gpad.dtype], B, Hp - 2, Wp - 2, Cc, mode, refs[0], refs[1],
+                             L.ptr(mslope), refs[2], refs[3], L.stream_ptr()), "pht_pad_fold")
+
+
+def im2col5(x_nchw, col, mode):
+    """x_nchw fp32 [B,Cin,H,W] -> col [B,H,W,Kpad] (dtype of col)."""
+    L.require_cuda(x_nchw, col)
+    assert x_nchw.is_contiguous() and col.is_contiguous() and x_nchw.dtype == torch.float32
+    B, Cin, H, W = x_nchw.shape
+    L.check(lib.pht_im2col5(x_nchw.data_ptr(), col.data_ptr(), L.DTYPES[col.dtype], B, Cin, H, W, col.shape[-1], mode,
+                            L.stream_ptr()), "pht_im2col5")
+
+
+def _attn_args(q, k, v, rel_h, rel_w, heads, block, halo, resid=None, out=None, lse=None):
+    a = L.AttnArgs()
+    a.dtype = L.DTYPES[q.dtype]
+    a.B, a.H, a.W = q.shape[0], q.shape[1], q.shape[2]
+    a.heads, a.head_dim, a.block, a.halo = heads, q.shape[3] // heads, block, halo
+    a.q, a.k, a.v = L.view(q), L.view(k), L.view(v)
+    a.rel_h, a.rel_w = rel_h.data_ptr(), rel_w.data_ptr()
+    a.resid, a.out = L.view(resid), L.view(out)
+    a.lse = L.ptr(lse)
+    return a
+
+
+def attn_fwd(q, k, v, rel_h, rel_w, out, *, heads=4, block=8, halo=3, resid=None, lse=None):
+    L.require_cuda(q, k, v, rel_h, rel_w, out)
+    a = _attn_args(q, k, v, rel_h, rel_w, heads, block, halo, resid, out, lse)
+    L.check(lib.pht_attn_fwd(C.byref(a), L.stream_ptr()), "pht_attn_fwd")
+
+
+def attn_bwd_workspace_bytes(q, heads=4, block=8, halo=3) -> int:
+    a = L.AttnBwdArgs()
+    a.fwd.B, a.fwd.H, a.fwd.W = q.shape[0], q.shape[1], q.shape[2]
+    a.fwd.heads, a.fwd.head_dim, a.fwd.block, a.fwd.halo = heads, q.shape[3] // heads, block, halo
+    return int(lib.pht_attn_bwd_workspace_bytes(C.byref(a)))
+
+
+def attn_bwd(q, k, v, rel_h, rel_w, lse, d_out, dq, dk_acc, dv_acc, d_rel_h, d_rel_w, workspace, *, heads=4, block=8,
+             halo=3):
+    L.require_cuda(q, k, v, d_out, dq, dk_acc, dv_acc)
+    a = L.AttnBwdArgs()
+    a.fwd = _attn_args(q, k, v, rel_h, rel_w, heads, block, halo, None, None, lse)
+    a.d_out, a.dq = L.view(d_out), L.view(dq)
+    a.dk_acc, a.dv_acc = dk_acc.data_ptr(), dv_acc.data_ptr()
+    a.d_rel_h, a.d_rel_w = d_rel_h.data_ptr(), d_rel_w.data_ptr()
+    a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    L.check(lib.pht_attn_bwd(C.byref(a), L.stream_ptr()), "pht_attn_bwd")
+
+
+def dec_tail_fwd(h, w, bias, x_nchw, out_nchw):
+    L.require_cuda(h, w, bias, x_nchw, out_nchw)
+    B, H, W, _ = h.shape
+    hv = L.view(h)
+    L.check(lib.pht_dec_tail_fwd(C.byref(hv), w.data_ptr(), bias.data_ptr(), x_nchw.data_ptr(), out_nchw.data_ptr(),
+                                 B, H, W, L.stream_ptr()), "pht_dec_tail_fwd")
+
+
+def dec_tail_bwd_data(dout_nchw, w, h, dh_pre):
+    L.require_cuda(dout_nchw, w, h, dh_pre)
+    B, H, W, _ = h.shape
+    hv, dv = L.view(h), L.view(dh_pre)
+    L.check(lib.pht_dec_tail_bwd_data(dout_nchw.data_ptr(), w.data_ptr(), C.byref(hv), C.byref(dv), B, H, W,
+                                      L.stream_ptr()), "pht_dec_tail_bwd_data")
+
+
+def dec_tail_ws_bytes(B, H, W, Cc) -> int:
+    return int(lib.pht_dec_tail_ws_bytes(B, H, W, Cc))
+
+
+def dec_tail_bwd_weight(dout_nchw, h, dw, dbias, workspace):
+    L.require_cuda(dout_nchw, h, dw, dbias, workspace)
+    B, H, W, _ = h.shape
+    hv = L.view(h)
+    L.check(lib.pht_dec_tail_bwd_weight(dout_nchw.data_ptr(), C.byref(hv), dw.data_ptr(), dbias.data_ptr(),
+                                        workspace.data_ptr(), workspace.numel() * workspace.element_size(), B, H, W,
+                                        L.stream_ptr()), "pht_dec_tail_bwd_weight")
+
+
+def l1_loss(a, b, loss, grad=None, grad_scale=1.0):
+    L.require_cuda(a, b, loss)
+    assert a.is_contiguous() and b.is_contiguous() and a.dtype == torch.float32 and b.dtype == torch.float32
+    L.check(lib.pht_l1_loss(a.data_ptr(), b.data_ptr(), a.numel(), float(grad_scale), loss.data_ptr(), L.ptr(grad),
+                            L.stream_ptr()), "pht_l1_loss")
+
+
+def preprocess(noisy_nhwc, gt_nhwc, aux_nhwc, noisy_out, gt_out, aux_out):
+    L.require_cuda(noisy_nhwc, aux_nhwc, noisy_out, aux_out)
+    B, H, W, _ = noisy_nhwc.shape
+    L.check(lib.pht_preprocess(noisy_nhwc.data_ptr(), L.ptr(gt_nhwc), aux_nhwc.data_ptr(), noisy_out.data_ptr(),
+                               L.ptr(gt_out), aux_out.data_ptr(), B, H, W, L.stream_ptr()), "pht_preprocess")
+
+
+def crop_preprocess(noisy_f, gt_f, aux_f, centres, P, noisy_out, gt_out, aux_out, img_idx=None):
+    """frames [n_img, Hf, Wf, C] (or [Hf, Wf, C]) fp32 resident on the device; centres int32 [n, 2] = (x, y)."""
+    L.require_cuda(noisy_f, aux_f, centres, noisy_out, aux_out)
+    Hf, Wf = noisy_f.shape[-3], noisy_f.shape[-2]
+    assert centres.dtype == torch.int32 and centres.is_contiguous()
+    assert img_idx is None or (img_idx.dtype == torch.int32 and img_idx.is_contiguous())
+    L.check(lib.pht_crop_preprocess(noisy_f.data_ptr(), L.ptr(gt_f), aux_f.data_ptr(), Hf, Wf, centres.data_ptr(),
+                                    L.ptr(img_idx), centres.shape[0], P, noisy_out.data_ptr(), L.ptr(gt_out),
+                                    aux_out.data_ptr(), L.stream_ptr()), "pht_crop_preprocess")
+
+
+def adam(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, grad_scale=1.0):
+    L.require_cuda(p, g, m, v)
+    L.check(lib.pht_adam(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2, eps,
+                         step, grad_scale, L.stream_ptr()), "pht_adam")
+
+
+def _pack_args(w, packed, *, ksize, Ntot, Ktot, n_off=0, k_off=0, transpose=0, grid=0, i_begin=0, i_count=0,
+               scale=1.0):
+    a = L.PackArgs()
+    a.w, a.packed = w.data_ptr(), packed.data_ptr()
+    a.dtype = L.DTYPES[packed.dtype]
+    a.O, a.I, a.ksize = w.shape[0], w.shape[1], ksize
+    a.Ntot, a.Ktot, a.n_off, a.k_off = Ntot, Ktot, n_off, k_off
+    a.transpose, a.grid, a.i_begin, a.i_count, a.scale = transpose, grid, i_begin, i_count, scale
+    return a
+
+
+def pack_weight(w, packed, **kw):
+    L.require_cuda(w, packed)
+    assert w.is_contiguous() and w.dtype == torch.float32
+    a = _pack_args(w, packed, **kw)
+    L.check(lib.pht_pack_weight(C.byref(a), L.stream_ptr()), "pht_pack_weight")
+
+
+def unpack_wgrad(w_grad, packed, **kw):
+    L.require_cuda(w_grad, packed)
+    assert w_grad.is_contiguous() and w_grad.dtype == torch.float32 and packed.dtype == torch.float32
+    a = _pack_args(w_grad, packed, **kw)
+    L.check(lib.pht_unpack_wgrad(C.byref(a), L.stream_ptr()), "pht_unpack_wgrad")
+
+
+def cast2d(src, dst):
+    """src/dst: 2-D [rows, cols] with unit column stride (row stride free)."""
+    L.require_cuda(src, dst)
+    assert src.dim() == 2 and dst.shape == src.shape and src.stride(1) == 1 and dst.stride(1) == 1
+    L.check(lib.pht_cast2d(src.data_ptr(), L.DTYPES[src.dtype], src.stride(0), dst.data_ptr(), L.DTYPES[dst.dtype],
+                           dst.stride(0), src.shape[0], src.shape[1], L.stream_ptr()), "pht_cast2d")
+
+
+def sample_patches(seeds, frame_hw, P, n, max_iter=5000):
+    """seeds int64 [n_img] (CUDA) -> int32 [n_img, n, 2] top-left corners (x, y)."""
+    L.require_cuda(seeds)
+    assert seeds.dtype == torch.int64
+    out = torch.empty(seeds.numel(), n, 2, dtype=torch.int32, device=seeds.device)
+    L.check(lib.pht_sample_patches(seeds.data_ptr(), seeds.numel(), frame_hw[0], frame_hw[1], P, n, max_iter,
+                                   out.data_ptr(), L.stream_ptr()), "pht_sample_patches")
+    return out

@@ -1,0 +1,193 @@
+"""Host-side logic that needs no GPU: C-ABI surface, config, model containers, tiling plan, DP plumbing."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from pixel_heal_thyself_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "pht_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pht_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in pht_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert raw.pht_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """sizeof of every ABI struct as gcc sees the header == sizeof of the ctypes mirror."""
+    from pixel_heal_thyself_b200 import _lib
+    names = ["pht_view", "pht_conv_gemm_args", "pht_wgrad_args", "pht_attn_args", "pht_attn_bwd_args", "pht_pack_args"]
+    mirrors = [_lib.PhtView, _lib.ConvGemmArgs, _lib.WgradArgs, _lib.AttnArgs, _lib.AttnBwdArgs, _lib.PackArgs]
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "pht_b200.h"\nint main(void){' +
+                   "".join(f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors]
+
+
+def test_ops_refuse_cpu_tensors():
+    from pixel_heal_thyself_b200 import ops
+    a = torch.zeros(16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.l1_loss(a, a, torch.zeros(1))
+
+
+def test_invalid_arguments_return_error_not_crash():
+    from pixel_heal_thyself_b200 import _lib
+    rc = _lib.lib.pht_conv_gemm(None, None)
+    assert rc == -1 and b"null" in _lib.lib.pht_last_error()
+    with pytest.raises(RuntimeError, match="pht_conv_gemm failed"):
+        _lib.check(rc, "pht_conv_gemm")
+
+
+def test_param_init_matches_reference(golden_meta):
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    torch.manual_seed(golden_meta["seed"])
+    net = AFGSANet(3, 7, 256, num_gcp=0, padding_mode="replicate")
+    names = [n for n, _ in net.named_parameters()]
+    assert names == golden_meta["param_order"]
+    assert sum(p.numel() for p in net.parameters()) == golden_meta["num_params"] == 9282691
+    for n, p in net.named_parameters():
+        assert list(p.shape) == golden_meta["param_shapes"][n]
+        s, a, first = golden_meta["param_checksums"][n]
+        assert float(p.detach().flatten()[0]) == first, n
+        assert abs(float(p.detach().double().sum()) - s) < 1e-9 * max(1.0, abs(s)), n
+    bufs = {k: v.tolist() for k, v in net.named_buffers()}
+    assert bufs == golden_meta["buffers"]
+
+
+def test_curve_indices_are_permutations():
+    from pixel_heal_thyself_b200.models.afgsa.model import CurveOrder, make_curve_indices
+    for mode in CurveOrder:
+        idx = make_curve_indices(8, mode)
+        assert sorted(idx.tolist()) == list(range(64))
+    assert make_curve_indices(8, CurveOrder.ZORDER)[:4].tolist() == [0, 1, 8, 9]
+    assert make_curve_indices(8, CurveOrder.HILBERT)[0].item() == 0
+
+
+def test_generator_needs_cuda():
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    net = AFGSANet(3, 7, 256, num_sa=1, num_gcp=0, padding_mode="replicate")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 3, 8, 8), torch.zeros(1, 7, 8, 8))
+    with pytest.raises(NotImplementedError):
+        AFGSANet(3, 7, 256, num_gcp=0, use_film=True)
+
+
+def test_config_presets_and_overrides():
+    from pixel_heal_thyself_b200.config import load_config
+    prod, stag, dev, ci = (load_config(n) for n in ("prod", "stag", "dev", "ci"))
+    assert (prod.data.patches.patch_size, prod.data.patches.num_patches) == (128, 400)
+    assert (stag.data.patches.patch_size, stag.data.patches.num_patches, stag.data.images.scale) == (64, 200, 0.5)
+    assert (dev.data.patches.patch_size, dev.data.patches.num_patches) == (32, 100)
+    assert (ci.trainer.batch_size, ci.trainer.epochs) == (2, 2)
+    assert prod.seed == 990819 and prod.trainer.batch_size == 8 and prod.trainer.deterministic
+    assert prod.model.losses.l1_loss_w == 1.0 and prod.model.losses.gan_loss_w == 0.005
+    c = load_config("dev", ["trainer.batch_size=4", "+model.afgsa.compute_dtype=fp32", "seed=7"])
+    assert c.trainer.batch_size == 4 and c.model.compute_dtype == "fp32" and c.seed == 7
+    with pytest.raises(FileNotFoundError):
+        load_config("nope")
+    with pytest.raises(KeyError):
+        load_config("dev", ["trainer.bogus=1"])
+
+
+def test_tile_plan_covers_frame_exactly():
+    from pixel_heal_thyself_b200.inference import plan_tiles
+    for (H, W, r, c) in ((2048, 2048, 2, 4), (256, 320, 3, 2), (64, 64, 1, 1), (72, 40, 4, 4)):
+        tiles = plan_tiles(H, W, r, c)
+        cover = torch.zeros(H, W, dtype=torch.int32)
+        for t in tiles:
+            cover[t.y0:t.y1, t.x0:t.x1] += 1
+            assert t.y0 % 8 == 0 and t.x0 % 8 == 0 and t.ty0 % 8 == 0 and t.tx0 % 8 == 0
+            assert (t.ty1 - t.ty0) % 8 == 0 and (t.tx1 - t.tx0) % 8 == 0
+            assert t.ty0 == max(0, t.y0 - 48) and t.ty1 == min(H, t.y1 + 48)
+        assert int(cover.min()) == 1 and int(cover.max()) == 1
+    with pytest.raises(AssertionError):
+        plan_tiles(100, 64, 2, 2)
+
+
+def test_tiled_stitching_is_exact_for_bounded_receptive_field():
+    from pixel_heal_thyself_b200.inference import denoise_frame
+    torch.manual_seed(0)
+    w = torch.randn(3, 10, 31, 31, dtype=torch.float64) * 0.01     # receptive radius 15 << halo 48
+
+    def net(x, aux):
+        return torch.nn.functional.conv2d(torch.cat([x, aux], 1), w, padding=15)
+
+    x = torch.randn(1, 3, 128, 192, dtype=torch.float64)
+    aux = torch.randn(1, 7, 128, 192, dtype=torch.float64)
+    full = net(x, aux)
+    tiled = denoise_frame(net, x, aux, rows=2, cols=3)
+    assert (full - tiled).abs().max() < 1e-12
+
+
+def test_bucket_ranges_follow_backward_order():
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    from pixel_heal_thyself_b200.parallel import bucket_ranges
+    net = AFGSANet(3, 7, 256, num_sa=2, num_gcp=0, padding_mode="replicate")
+    order, offsets, off = [], {}, 0
+    for n, p in net.named_parameters():
+        order.append(n)
+        offsets[n] = (off, p.numel())
+        off += (p.numel() + 63) // 64 * 64
+    r = bucket_ranges(offsets, order, off)
+    assert [k for k, _, _ in r] == ["decoder", "block1", "block0", "encoders"]
+    spans = sorted((lo, hi) for _, lo, hi in r)
+    assert spans[0][0] == 0 and spans[-1][1] == off
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+
+
+_DP_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pixel_heal_thyself_b200 import parallel
+rank, local, world = parallel.init_distributed()
+assert world == 2 and dist.get_backend() == "gloo"
+offsets = {"conv1.0.weight": (0, 100), "transformer_blocks.0.attention.rel_h": (128, 60),
+           "transformer_blocks.1.attention.rel_h": (192, 60), "decoder.0.0.weight": (256, 200)}
+order = list(offsets)
+flat = torch.arange(512, dtype=torch.float32) * (rank + 1)
+b = parallel.GradBucketer(lambda: flat, offsets, order, 512)
+for tag in ("decoder", "block1", "block0", "encoders"):
+    b.ready(tag)
+assert b.launched == ["decoder", "block1", "block0", "encoders"]
+b.finish()
+assert torch.equal(flat, torch.arange(512, dtype=torch.float32) * 3), "all-reduce(sum) over 2 ranks"
+perm = torch.randperm(1000, generator=torch.Generator().manual_seed(5))
+mine = parallel.shard_indices(1000, rank, world, 8, perm)
+allidx = [torch.zeros_like(mine) for _ in range(2)]
+dist.all_gather(allidx, mine)
+both = torch.cat(allidx)
+assert mine.numel() == 496 and both.unique().numel() == 992, "disjoint equal shards"
+lin = torch.nn.Linear(4, 4)
+torch.manual_seed(rank); lin(torch.randn(3, 4)).sum().backward()
+g0 = lin.weight.grad.clone(); parallel.allreduce_module_grads(lin, world)
+gs = [torch.zeros_like(g0) for _ in range(2)]; dist.all_gather(gs, g0)
+assert torch.allclose(lin.weight.grad, (gs[0] + gs[1]) / 2)
+dist.barrier(); dist.destroy_process_group()
+print("DP_OK", rank)
+"""
+
+
+def test_data_parallel_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"DP_OK {r}" in o, o[-2000:]

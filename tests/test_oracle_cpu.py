@@ -1,0 +1,102 @@
+"""The CPU oracle against the golden fixtures generated from the real reference
+(tests/golden/make_golden.py).  No GPU needed."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_json, load_npz
+from oracle import afgsa_oracle as O
+from oracle import sampler_oracle as S
+
+
+def _ref_init_state_dict(mode="replicate"):
+    """The reference's random init under the reference seed, reproduced by the product model's
+    parameter containers (pinned by test_host_cpu.test_param_init_matches_reference)."""
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    torch.manual_seed(990819)
+    net = AFGSANet(3, 7, 256, num_gcp=0, padding_mode=mode)
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+def test_pins_recorded(golden_meta):
+    pins = golden_meta["pins"]
+    assert pins["sampler_bit_exact"] is True
+    assert pins["zorder_vs_raster_maxdiff"] == 0.0
+    for k, v in pins.items():
+        if k.endswith("maxdiff") or k.endswith("diff"):
+            assert v < 2e-6, (k, v)
+
+
+def test_preprocess_matches_reference():
+    g = load_npz("preprocess.npz")
+    n, t, a = O.preprocess_batch(torch.from_numpy(g["noisy_hwc"]), torch.from_numpy(g["gt_hwc"]),
+                                 torch.from_numpy(g["aux_hwc"]))
+    assert np.abs(n.numpy() - g["noisy"]).max() < 1e-6
+    assert np.abs(t.numpy() - g["gt"]).max() < 1e-6
+    assert np.abs(a.numpy() - g["aux"]).max() < 1e-6
+    assert not np.isnan(a.numpy()).any()
+
+
+def test_afgsa_module_matches_reference():
+    g = load_npz("afgsa_module.npz")
+    sd = {k.replace("__", "."): torch.from_numpy(v) for k, v in g.items() if k.startswith("p__")}
+    out = O.afgsa(torch.from_numpy(g["noisy"]), torch.from_numpy(g["aux"]), sd, "p.", 8, 3, 4)
+    assert (out - torch.from_numpy(g["out"])).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["replicate", "reflect"])
+def test_net_forward_backward_matches_reference(mode):
+    g = load_npz(f"net_{mode}.npz")
+    grads_ref = load_json(f"net_{mode}_grads.json")
+    sd = _ref_init_state_dict(mode)
+    x, aux, gt = (torch.from_numpy(g[k]) for k in ("x", "aux", "gt"))
+    out, loss, grads = O.g_only_train_step(x, aux, gt, sd, mode)
+    assert (out - torch.from_numpy(g["out"])).abs().max() < 1e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    for name, ref in grads_ref.items():
+        gr = grads[name].flatten()
+        scale = ref["absmax"] + 1e-30
+        probe = torch.tensor([float(gr[i]) for i in ref["probe_idx"]])
+        assert (probe - torch.tensor(ref["probe"])).abs().max() / scale < 1e-4, name
+        assert abs(float(gr.double().abs().sum()) - ref["abssum"]) / (ref["abssum"] + 1e-30) < 1e-4, name
+
+
+def test_mt19937_matches_cpython(golden_meta):
+    kat = golden_meta["mt_kat"]
+    m = S.MT19937(990819)
+    assert [m.getrandbits(32) for _ in range(3)] == kat["getrandbits32"]
+    assert [m.randint(0, 479) for _ in range(4)] == kat["randint_0_479"]
+    assert m.random() == kat["random"]
+    for seed in (0, 1, 990819, 2 ** 32 + 5, 123456789012345):
+        a, b = S.MT19937(seed), random.Random(seed)
+        for n in (1, 2, 3, 100, 479, 895, 1 << 20):
+            assert a.randint(0, n) == b.randint(0, n)
+        assert a.random() == b.random()
+        assert [a.getrandbits(32) for _ in range(700)] == [b.getrandbits(32) for _ in range(700)]
+
+
+def test_sampler_matches_reference_golden():
+    g = load_npz("sampler.npz")
+    for key, ref in g.items():
+        parts = key.split("_")
+        h, w, p, n = int(parts[0][1:]), int(parts[1][1:]), int(parts[2][1:]), int(parts[3][1:])
+        if n > 200:
+            continue  # the 400-patch case is covered on the GPU; keep the CPU suite fast
+        pts = S.dart_throwing((h, w), p, n, S.MT19937(990819))
+        assert np.array_equal(pts, ref.astype(np.int64)), key
+
+
+def test_adam_oracle_matches_torch():
+    torch.manual_seed(0)
+    p = torch.randn(1000)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(1000)
+        ref.grad = g.clone()
+        opt.step()
+        O.adam_step(p, g, m, v, step, 1e-3)
+    assert (p - ref.detach()).abs().max() < 1e-6
