@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""Benchmark of the AFGSA hot path (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload prod|stag|dev]
+
+Own arm: one "step" is one pass of the hot path over one patch batch -- generator
+forward, L1 image loss, generator backward and the fused Adam update -- on the
+prod configuration (128x128 patches, batch 8 per GPU, bf16), weak scaling over N
+GPUs (one process per GPU under torchrun, bucketed NCCL all-reduce overlapped
+with backward).  `value` is timed with inputs resident in HBM; `e2e` is the same
+metric through the trainer's public API starting from pinned host buffers.
+Reference arm (--impl reference): the CPU restatement of the reference's path
+(oracle/) on the host cores, on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # name -> (patch, per-GPU batch, preset)
+    "prod": (128, 8, "prod"),
+    "stag": (64, 8, "stag"),
+    "dev": (32, 8, "dev"),
+}
+TRAIN_FLOP_PER_PX = 58_639_872      # fwd + dgrad + wgrad, BASELINE.md section 4
+CONV3_FLOP_PER_PX = 2 * 9 * 256 * 256
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_step_time(patch: int, steps: int, warmup: int):
+    """Times the CPU restatement of the reference path (oracle/) on all host cores: one G-only training step
+    (forward, L1, backward, Adam) on ONE patch of the workload.  Returns (seconds per step, cores)."""
+    import torch
+    from oracle import afgsa_oracle as O
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(990819)
+    net = AFGSANet(3, 7, 256, num_gcp=0, padding_mode="replicate")   # parameter container only (CPU)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items() if v.dtype.is_floating_point}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 3, patch, patch, generator=g) * 0.5
+    aux = torch.rand(1, 7, patch, patch, generator=g)
+    gt = torch.randn(1, 3, patch, patch, generator=g) * 0.5
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    v2 = {k: torch.zeros_like(v) for k, v in sd.items()}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, grads = O.g_only_train_step(x, aux, gt, sd, "replicate")
+        for k in sd:
+            O.adam_step(sd[k], grads[k], m[k], v2[k], it + 1, 1e-4)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    patch, batch, preset = WORKLOADS[args.workload]
+    sec, cores = cpu_reference_step_time(patch, args.steps, args.warmup)
+    val = 1.0 / sec
+    sample = f"1 patch {patch}x{patch} per step (G fwd + L1 + G bwd + Adam), oracle port of the reference on {cores} host threads"
+    line = {
+        "impl": "reference", "metric": "AFGSA train patches/sec", "value": val, "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{preset}: AFGSA G-only training step, {patch}x{patch} patches", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pixel_heal_thyself_b200 import _lib, ops, parallel
+    from pixel_heal_thyself_b200.config import load_config
+    from pixel_heal_thyself_b200.data import preprocess_host_batch
+    from pixel_heal_thyself_b200.models.afgsa.train import AFGSATrainer
+
+    patch, batch, preset = WORKLOADS[args.workload]
+    n_img = 2
+    cfg = load_config(preset, [f"trainer.batch_size={batch}", f"data.synthetic.num_images={n_img}",
+                               "data.synthetic.height=1024", "data.synthetic.width=1024",
+                               f"model.afgsa.compute_dtype={args.dtype}"])
+    tr = AFGSATrainer(cfg)
+    rank, world, dev = tr.rank, tr.world, tr.device
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    tr.setup(g_only=not args.gan)
+    ds = tr.setup_data()
+    gen = torch.Generator().manual_seed(cfg.seed + rank)
+    total = args.warmup + args.steps
+    order = torch.randperm(len(ds), generator=gen)
+    need = 2 * total * batch
+    order = order.repeat((need + len(ds) - 1) // len(ds))[:need].to(dev)
+    npx = batch * patch * patch
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident arm ("value") ----------------
+    batches = [ds.batch_device(order[i * batch:(i + 1) * batch]) for i in range(total)]
+    for i in range(args.warmup):
+        tr.train_step(*batches[i])
+    sink = []
+    sync_all()
+    clocks = ClockSampler(tr.local_rank)
+    if rank == 0:
+        clocks.start()
+    _lib.lib.pht_reset_counters()
+    ops.set_launch_profiler(sink, lambda tag: tag[0] == 3 and tag[1] == 256 and tag[2] == 256)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, total):
+        tr.train_step(*batches[i])
+    e1.record()
+    sync_all()
+    ops.set_launch_profiler(None)
+    counters = _lib.counters()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    conv_ms = [a.elapsed_time(b) for _, a, b in sink]
+    conv_px = [t[3] for t, _, _ in sink]
+
+    # ---------------- end-to-end arm ("e2e"): pinned host NHWC patches -> H2D -> preprocess -> step -> D2H loss
+    host = ds.host_patches()
+    hidx = order.cpu()
+    for i in range(args.warmup):
+        sel = hidx[i * batch:(i + 1) * batch]
+        tr.train_step(*preprocess_host_batch({k: v[sel].pin_memory() for k, v in host.items()}, dev))
+    staged = [{k: v[hidx[(total + i) * batch:(total + i + 1) * batch]].pin_memory() for k, v in host.items()}
+              for i in range(args.steps)]
+    sync_all()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    last = 0.0
+    for i in range(args.steps):
+        g_loss, _ = tr.train_step(*preprocess_host_batch(staged[i], dev))
+        last = float(g_loss)                      # device -> host read of the step's result, every step
+    h1.record()
+    sync_all()
+    ms_e2e = h0.elapsed_time(h1)
+    h2d = sum(v.numel() * v.element_size() for v in staged[0].values())
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    peaks = _peaks()
+    patches = batch * world * args.steps
+    value = patches / (ms * 1e-3)
+    e2e = patches / (ms_e2e * 1e-3)
+    conv_avg_ms = sum(conv_ms) / max(len(conv_ms), 1)
+    conv_flop = CONV3_FLOP_PER_PX * npx
+    ach = conv_flop / (conv_avg_ms * 1e-3) / 1e12 if conv_ms else None
+    step_tflops = TRAIN_FLOP_PER_PX * npx * world / (ms / args.steps * 1e-3) / 1e12
+    cpu_sec, cores = (cpu_reference_step_time(patch, 1, 1) if (world == 1 and not args.no_cpu_baseline)
+                      else (None, os.cpu_count()))
+    launches = sum(counters.values())
+    line = {
+        "metric": "AFGSA train patches/sec", "value": value, "unit": "patches/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{preset}: AFGSA {'GAN' if args.gan else 'G-only (hot path)'} training step, "
+                               f"{patch}x{patch} patches, batch {batch}/GPU, {n_img} synthetic 1024x1024 frames/GPU",
+                   "global_batch": batch * world, "parallelism": f"dp{world}",
+                   "l2": f"per-step working set ~{3.3 * npx / 131072:.1f} GB >> 126 MB L2 (no explicit flush)",
+                   "step": "G forward + L1 + G backward + fused Adam" + (" + critic step (PyTorch)" if args.gan else "")},
+        "clocks": clk,
+        "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+        "gpu_launches": launches,
+        "launch_counters": counters,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm 3x3 256->256 (forward + data-grad launches)",
+                     "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": (ach / peaks["tf_sustained"]) if ach else None, "traffic": None,
+                     "peak_source": f"{peaks['src']} sustained bf16", "launches_timed": len(conv_ms),
+                     "avg_launch_ms": conv_avg_ms, "algorithmic_flop_per_launch": conv_flop,
+                     "share_of_step": (sum(conv_ms) / ms) if conv_ms else None},
+        "step_tflops": step_tflops,
+        "cpu_baseline": ({"value": 1.0 / cpu_sec, "unit": "patches/s", "cores": cores, "kind": "port",
+                          "sample": f"1 patch {patch}x{patch}, 1 warm-up + 1 timed G-only step of the oracle port"}
+                         if cpu_sec else None),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="prod", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--gan", action="store_true", help="time the full GAN iteration (adds the PyTorch critic step)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

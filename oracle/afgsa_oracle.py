@@ -156,12 +156,12 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     p.addcdiv_(m, denom, value=-(lr / bc1))
 
 
-def g_only_train_step(x, aux, gt, sd, padding_mode="replicate"):
+def g_only_train_step(x, aux, gt, sd, padding_mode="replicate", num_sa=5):
     """One generator-only step (G fwd, L1, backward): the part of
     base_trainer.py:388-457 that runs on hand-written kernels.  Returns
     (output, loss, grads dict)."""
     params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point}
-    out = afgsa_net_forward(x, aux, params, padding_mode)
+    out = afgsa_net_forward(x, aux, params, padding_mode, num_sa=num_sa)
     loss = l1_loss(out, gt)
     loss.backward()
     return out.detach(), loss.detach(), {k: p.grad for k, p in params.items()}

@@ -14,6 +14,16 @@ import torch
 from . import _lib as L
 from ._lib import lib
 
+# optional per-launch CUDA-event timing of conv_gemm (bench.py's roofline leg): a list that receives
+# (tag, start_event, end_event) for every launch whose tag passes `_profile_filter`
+_profile_sink = None
+_profile_filter = None
+
+
+def set_launch_profiler(sink, flt=None):
+    global _profile_sink, _profile_filter
+    _profile_sink, _profile_filter = sink, flt
+
 
 def conv_gemm(srcs, w, N, *, ksize=1, out_domain=None, bias=None, slope=None, resid=None, resid_mode=None, mask=None,
               mslope=None, out1=None, out2=None, src_offsets=None):
@@ -43,6 +53,15 @@ def conv_gemm(srcs, w, N, *, ksize=1, out_domain=None, bias=None, slope=None, re
         flags |= L.EPI_MASK
     a.flags = flags
     a.out1, a.out2 = L.view(out1), L.view(out2)
+    if _profile_sink is not None:
+        tag = (ksize, N, sum(s.shape[-1] for s in srcs), a.B * a.Ho * a.Wo)
+        if _profile_filter is None or _profile_filter(tag):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(lib.pht_conv_gemm(C.byref(a), L.stream_ptr()), "pht_conv_gemm")
+            e1.record()
+            _profile_sink.append((tag, e0, e1))
+            return
     L.check(lib.pht_conv_gemm(C.byref(a), L.stream_ptr()), "pht_conv_gemm")
 
 

@@ -1,0 +1,393 @@
+"""Per-op parity of the CUDA kernels (through the C ABI) against the CPU oracle / a torch fp32 reference.
+
+fp32 ops: tolerance 1e-5 relative to the reference's max magnitude (north_star's fp32 bar).
+bf16 ops: inputs are bf16-rounded first, the reference is computed in fp32 from those rounded inputs,
+and the result may differ by bf16 output rounding (2^-8 relative) plus accumulation-order noise.
+Integer work (sampler) is bit-exact.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_npz
+from oracle import afgsa_oracle as O
+from oracle import sampler_oracle as S
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+F32_TOL = 1e-5
+BF16_TOL = 1.2e-2
+
+
+def _ops():
+    from pixel_heal_thyself_b200 import ops
+    return ops
+
+
+def rel_err(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-30))
+
+
+def tol(dtype):
+    return F32_TOL if dtype == torch.float32 else BF16_TOL
+
+
+def nhwc(t):  # NCHW -> NHWC contiguous
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+def pack(w, dtype, **kw):
+    ops = _ops()
+    O_, I_, ks, _ = w.shape
+    T = ks * ks
+    if kw.get("transpose"):
+        packed = torch.zeros(T, I_, O_, dtype=dtype, device=DEV)
+        ops.pack_weight(w, packed, ksize=ks, Ntot=I_, Ktot=O_, **kw)
+    else:
+        packed = torch.zeros(T, O_, I_, dtype=dtype, device=DEV)
+        ops.pack_weight(w, packed, ksize=ks, Ntot=O_, Ktot=I_, **kw)
+    return packed
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ks,cin,cout,B,H,W", [(1, 64, 64, 2, 8, 16), (3, 64, 128, 2, 16, 24), (3, 256, 256, 1, 16, 16),
+                                                (1, 768, 256, 1, 8, 8)])
+def test_conv_gemm_zero_pad_matches_conv2d(dtype, ks, cin, cout, B, H, W):
+    ops = _ops()
+    torch.manual_seed(1)
+    x = torch.randn(B, cin, H, W, device=DEV).to(dtype)
+    w = (torch.randn(cout, cin, ks, ks, device=DEV) / (cin * ks * ks) ** 0.5)
+    bias = torch.randn(cout, device=DEV)
+    wp = pack(w, dtype)
+    ref = F.relu(F.conv2d(x.float(), wp.float().view(ks, ks, cout, cin).permute(2, 3, 0, 1), bias, padding=ks // 2))
+    out = torch.empty(B, H, W, cout, dtype=dtype, device=DEV)
+    ops.conv_gemm([nhwc(x)], wp, cout, ksize=ks, bias=bias, slope=torch.zeros(cout, device=DEV), out1=out)
+    assert rel_err(nchw(out), ref) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["replicate", "reflect"])
+def test_padded_conv_forward_and_backward(dtype, mode):
+    """3x3 conv with replicate/reflect padding: forward through border_fill + conv_gemm, data-grad through the
+    padded-domain conv_gemm + pad_fold, weight-grad through wgrad.  Reference: autograd of F.pad + F.conv2d."""
+    ops = _ops()
+    from pixel_heal_thyself_b200._lib import PAD_MODES
+    torch.manual_seed(2)
+    B, C, N, H, W = 2, 64, 64, 16, 24
+    x = torch.randn(B, C, H, W, device=DEV).to(dtype)
+    w = torch.randn(N, C, 3, 3, device=DEV) / (9 * C) ** 0.5
+    bias = torch.randn(N, device=DEV)
+    dy = torch.randn(B, N, H, W, device=DEV).to(dtype)
+    wq = pack(w, dtype).float().view(3, 3, N, C).permute(2, 3, 0, 1).contiguous()  # weights as the kernel sees them
+    xr = x.float().requires_grad_(True)
+    wr = wq.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    yr = F.relu(F.conv2d(F.pad(xr, (1, 1, 1, 1), mode=mode), wr, br))
+    # fused: d(pre-activation) = dy * (y > 0)
+    yr.backward(dy.float())
+    m = PAD_MODES[mode]
+    xp = torch.zeros(B, H + 2, W + 2, C, dtype=dtype, device=DEV)
+    xp[:, 1:-1, 1:-1, :] = nhwc(x)
+    ops.border_fill(xp, m)
+    assert torch.equal(nchw(xp).float(), F.pad(x.float(), (1, 1, 1, 1), mode=mode))
+    y = torch.empty(B, H, W, N, dtype=dtype, device=DEV)
+    ops.conv_gemm([xp], pack(w, dtype), N, ksize=3, src_offsets=[(1, 1)], bias=bias, slope=torch.zeros(N, device=DEV), out1=y)
+    assert rel_err(nchw(y), yr) < tol(dtype)
+    # backward: dpre = dy * (y>0) (reference mask), dgrad over padded domain, fold
+    dpre = (dy.float() * (yr > 0)).to(dtype)
+    gp = torch.empty(B, H + 2, W + 2, C, dtype=dtype, device=DEV)
+    ops.conv_gemm([nhwc(dpre)], pack(w, dtype, transpose=1), C, ksize=3, out_domain=(B, H + 2, W + 2),
+                  src_offsets=[(-1, -1)], out1=gp)
+    dx = torch.empty(B, H, W, C, dtype=dtype, device=DEV)
+    ops.pad_fold(gp, m, out1=dx)
+    assert rel_err(nchw(dx), xr.grad) < (tol(dtype) if dtype == torch.float32 else 2.5e-2)
+    dw = torch.empty(9, N, C, dtype=torch.float32, device=DEV)
+    db = torch.empty(N, dtype=torch.float32, device=DEV)
+    ws = torch.empty(1 << 22, dtype=torch.float32, device=DEV)
+    ops.wgrad(nhwc(dpre), [xp], dw, ksize=3, dbias=db, workspace=ws, src_offsets=[(1, 1)])
+    dw_oihw = torch.empty(N, C, 3, 3, device=DEV)
+    ops.unpack_wgrad(dw_oihw, dw, ksize=3, Ntot=N, Ktot=C)
+    wgrad_ref = torch.autograd.grad(F.conv2d(F.pad(x.float(), (1, 1, 1, 1), mode=mode), wr), wr, dpre.float())[0]
+    assert rel_err(dw_oihw, wgrad_ref) < (1e-4 if dtype == torch.float32 else 1e-3)
+    assert rel_err(db, dpre.float().sum((0, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_gemm_virtual_concat_and_epilogues(dtype):
+    ops = _ops()
+    torch.manual_seed(3)
+    B, H, W, C1, C2, N = 2, 8, 8, 64, 128, 64
+    a = torch.randn(B, H, W, C1, device=DEV).to(dtype)
+    b = torch.randn(B, H, W, C2, device=DEV).to(dtype)
+    w = torch.randn(N, C1 + C2, 1, 1, device=DEV) / (C1 + C2) ** 0.5
+    bias = torch.randn(N, device=DEV)
+    slope = torch.full((N,), 0.2, device=DEV)
+    resid = torch.randn(B, H, W, N, device=DEV).to(dtype)
+    mask = torch.randn(B, H, W, N, device=DEV).to(dtype)
+    wp = pack(w, dtype)
+    acc = torch.cat([a, b], -1).float() @ wp.float()[0].t() + bias
+    # forward-style: out1 = act(acc), out2 = out1 + resid
+    o1 = torch.empty(B, H, W, N, dtype=dtype, device=DEV)
+    o2 = torch.empty_like(o1)
+    ops.conv_gemm([a, b], wp, N, bias=bias, slope=slope, resid=resid, resid_mode="post", out1=o1, out2=o2)
+    ref1 = F.leaky_relu(acc, 0.2)
+    assert rel_err(o1, ref1) < tol(dtype)
+    assert rel_err(o2, ref1.to(dtype).float() + resid.float()) < tol(dtype)
+    # backward-style: v = acc + resid ; out1 = v ; out2 = v * dact(mask) (leaky 0.2)
+    ops.conv_gemm([a, b], wp, N, bias=bias, resid=resid, resid_mode="pre", mask=mask, mslope=slope, out1=o1, out2=o2)
+    v = acc + resid.float()
+    assert rel_err(o1, v) < tol(dtype)
+    assert rel_err(o2, v.to(dtype).float() * torch.where(mask.float() > 0, 1.0, 0.2)) < tol(dtype)
+    # strided views: write into the interior of a padded buffer and read a channel slice
+    buf = torch.zeros(B, H + 2, W + 2, N, dtype=dtype, device=DEV)
+    wide = torch.cat([a, b], -1).contiguous()
+    ops.conv_gemm([wide[..., :C1], wide[..., C1:]], wp, N, bias=bias, out1=buf[:, 1:-1, 1:-1, :])
+    assert rel_err(buf[:, 1:-1, 1:-1, :], acc) < tol(dtype)
+    assert float(buf[:, 0].abs().max()) == 0.0 and float(buf[:, :, 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_wgrad_1x1_two_sources(dtype):
+    ops = _ops()
+    torch.manual_seed(4)
+    B, H, W, C1, C2, N = 2, 16, 16, 64, 64, 128
+    a = torch.randn(B, H, W, C1, device=DEV).to(dtype)
+    b = torch.randn(B, H, W, C2, device=DEV).to(dtype)
+    dy = torch.randn(B, H, W, N, device=DEV).to(dtype)
+    dw = torch.empty(1, N, C1 + C2, device=DEV)
+    db = torch.empty(N, device=DEV)
+    ops.wgrad(dy, [a, b], dw, dbias=db, workspace=torch.empty(1 << 22, device=DEV))
+    ref = dy.float().reshape(-1, N).t() @ torch.cat([a, b], -1).float().reshape(-1, C1 + C2)
+    assert rel_err(dw[0], ref) < (1e-4 if dtype == torch.float32 else 1e-3)
+    assert rel_err(db, dy.float().sum((0, 1, 2))) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["replicate", "reflect"])
+def test_encoder_im2col_gemm_matches_three_convs(dtype, mode):
+    """conv1 / conv3 / conv5 (model.py:606-622) as one GEMM over the 5x5 im2col."""
+    ops = _ops()
+    from pixel_heal_thyself_b200._lib import PAD_MODES
+    torch.manual_seed(5)
+    B, Cin, H, W = 2, 7, 16, 24
+    x = torch.randn(B, Cin, H, W, device=DEV)
+    ws = [torch.randn(256, Cin, k, k, device=DEV) / (Cin * k * k) ** 0.5 for k in (1, 3, 5)]
+    kpad = 192
+    wp = torch.zeros(1, 768, kpad, dtype=dtype, device=DEV)
+    for j, (w, k) in enumerate(zip(ws, (1, 3, 5))):
+        ops.pack_weight(w, wp, ksize=k, Ntot=768, Ktot=kpad, n_off=256 * j, grid=5)
+    col = torch.empty(B, H, W, kpad, dtype=dtype, device=DEV)
+    ops.im2col5(x, col, PAD_MODES[mode])
+    out = torch.empty(B, H, W, 768, dtype=dtype, device=DEV)
+    ops.conv_gemm([col], wp, 768, out1=out)
+    xq = x.to(dtype).float()
+    refs = []
+    for w, k in zip(ws, (1, 3, 5)):
+        wq = w.to(dtype).float()
+        xp_ = F.pad(xq, (k // 2,) * 4, mode=mode) if k > 1 else xq
+        refs.append(F.conv2d(xp_, wq))
+    assert rel_err(nchw(out), torch.cat(refs, 1)) < tol(dtype)
+    # the embedded kernels unpack back to the original OIHW gradients layout
+    back = torch.empty_like(ws[1])
+    ops.unpack_wgrad(back, wp.float(), ksize=3, Ntot=768, Ktot=kpad, n_off=256, grid=5)
+    assert rel_err(back, ws[1].to(dtype)) < 1e-6
+
+
+def _attn_inputs(B, C, H, W, dtype, seed):
+    torch.manual_seed(seed)
+    heads, d = 4, C // 4
+    q = (torch.randn(B, C, H, W) * d ** -0.5).to(dtype)
+    k = torch.randn(B, C, H, W).to(dtype)
+    v = torch.randn(B, C, H, W).to(dtype)
+    rel_h = torch.randn(1, 14, 1, d // 2)
+    rel_w = torch.randn(1, 1, 14, d // 2)
+    return q, k, v, rel_h, rel_w
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,C,H,W", [(1, 256, 16, 24), (2, 32, 8, 8), (1, 256, 8, 8)])
+def test_attention_forward_backward_matches_oracle(dtype, B, C, H, W):
+    ops = _ops()
+    q, k, v, rel_h, rel_w = _attn_inputs(B, C, H, W, dtype, 6)
+    do = torch.randn(B, C, H, W).to(dtype)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    rh, rw = rel_h.clone().requires_grad_(True), rel_w.clone().requires_grad_(True)
+    ref = O.attention_core(qr, kr, vr, rh, rw, 8, 3, 4)
+    ref.backward(do.float())
+    g = lambda t: nhwc(t).to(DEV)
+    qd, kd, vd = g(q), g(k), g(v)
+    out = torch.empty(B, H, W, C, dtype=dtype, device=DEV)
+    lse = torch.empty(B, H, W, 4, device=DEV)
+    rhd, rwd = rel_h.to(DEV), rel_w.to(DEV)
+    ops.attn_fwd(qd, kd, vd, rhd, rwd, out, lse=lse)
+    assert rel_err(nchw(out).cpu(), ref.detach()) < (1e-5 if dtype == torch.float32 else 1e-2)
+    if dtype == torch.float32:  # fused residual (x + attention, model.py:579)
+        resid = torch.randn(B, H, W, C, device=DEV)
+        out2 = torch.empty_like(out)
+        ops.attn_fwd(qd, kd, vd, rhd, rwd, out2, resid=resid)
+        assert rel_err(out2 - resid, out) < 1e-5
+    dq = torch.empty_like(qd)
+    dk = torch.zeros(B * H * W, C, device=DEV)
+    dv = torch.zeros(B * H * W, C, device=DEV)
+    drh, drw = torch.empty_like(rhd), torch.empty_like(rwd)
+    ws = torch.empty(max(ops.attn_bwd_workspace_bytes(qd), 16) // 4, device=DEV)
+    ops.attn_bwd(qd, kd, vd, rhd, rwd, lse, g(do), dq, dk, dv, drh, drw, ws)
+    t = 2e-5 if dtype == torch.float32 else 3e-2
+    assert rel_err(nchw(dq).cpu(), qr.grad) < t
+    assert rel_err(dk.view(B, H, W, C).permute(0, 3, 1, 2).cpu(), kr.grad) < t
+    assert rel_err(dv.view(B, H, W, C).permute(0, 3, 1, 2).cpu(), vr.grad) < t
+    assert rel_err(drh.cpu(), rh.grad) < t
+    assert rel_err(drw.cpu(), rw.grad) < t
+
+
+def test_attention_rejects_unaligned_maps():
+    ops = _ops()
+    q = torch.zeros(1, 12, 16, 256, device=DEV)
+    with pytest.raises(RuntimeError, match="divisible by the block size"):
+        ops.attn_fwd(q, q, q, torch.zeros(14, 32, device=DEV), torch.zeros(14, 32, device=DEV), torch.empty_like(q))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decoder_tail_forward_backward(dtype):
+    ops = _ops()
+    torch.manual_seed(7)
+    B, C, H, W = 2, 256, 16, 24
+    h = torch.relu(torch.randn(B, C, H, W, device=DEV)).to(dtype)
+    w = torch.randn(3, C, 3, 3, device=DEV) / (9 * C) ** 0.5
+    bias = torch.randn(3, device=DEV)
+    x = torch.randn(B, 3, H, W, device=DEV)
+    dout = torch.randn(B, 3, H, W, device=DEV)
+    hr = h.float().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    ref = F.conv2d(hr, wr, br, padding=1) + x
+    ref.backward(dout)
+    wk = w.permute(0, 2, 3, 1).reshape(3, 9, C).contiguous()
+    out = torch.empty_like(x)
+    hn = nhwc(h)
+    ops.dec_tail_fwd(hn, wk, bias, x, out)
+    assert rel_err(out, ref) < 1e-5
+    dh = torch.empty_like(hn)
+    ops.dec_tail_bwd_data(dout, wk, hn, dh)
+    assert rel_err(nchw(dh), hr.grad * (h.float() > 0)) < tol(dtype)
+    dw = torch.empty(3, 9, C, device=DEV)
+    db = torch.empty(3, device=DEV)
+    ws = torch.empty(ops.dec_tail_ws_bytes(B, H, W, C) // 4, device=DEV)
+    ops.dec_tail_bwd_weight(dout, hn, dw, db, ws)
+    assert rel_err(dw.view(3, 3, 3, C).permute(0, 3, 1, 2), wr.grad) < 1e-4
+    assert rel_err(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("n", [1, 7, 3 * 128 * 128 * 8 + 3, 5_000_000])
+def test_l1_loss_and_grad(n):
+    ops = _ops()
+    torch.manual_seed(8)
+    a, b = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
+    b[: n // 7] = a[: n // 7]  # exact ties -> sign 0
+    loss = torch.empty(1, device=DEV)
+    grad = torch.empty_like(a)
+    ops.l1_loss(a, b, loss, grad)
+    ref = float(O.l1_loss(a.double().cpu(), b.double().cpu()))
+    assert abs(float(loss) - ref) / ref < 1e-6
+    assert torch.equal(grad, torch.sign(a - b) / n)
+
+
+def test_preprocess_matches_reference_golden():
+    ops = _ops()
+    g = load_npz("preprocess.npz")
+    n, t, a = (torch.from_numpy(g[k]).to(DEV) for k in ("noisy_hwc", "gt_hwc", "aux_hwc"))
+    B, P = n.shape[0], n.shape[1]
+    no, to_, ao = (torch.empty(B, c, P, P, device=DEV) for c in (3, 3, 7))
+    ops.preprocess(n, t, a, no, to_, ao)
+    assert np.abs(no.cpu().numpy() - g["noisy"]).max() < 1e-6   # logf vs np.log: <= 1 ulp
+    assert np.abs(to_.cpu().numpy() - g["gt"]).max() < 1e-6
+    assert np.array_equal(ao.cpu().numpy(), g["aux"])           # clamp / nan_to_num are exact
+
+
+def test_crop_preprocess_matches_oracle_crop():
+    ops = _ops()
+    from pixel_heal_thyself_b200.data import synthetic_frames
+    fr = synthetic_frames(2, 96, 128, 11, DEV)
+    P = 32
+    centres = torch.tensor([[16, 16], [100, 50], [64, 80], [111, 79]], dtype=torch.int32, device=DEV)
+    img = torch.tensor([0, 1, 1, 0], dtype=torch.int32, device=DEV)
+    no, to_, ao = (torch.empty(4, c, P, P, device=DEV) for c in (3, 3, 7))
+    ops.crop_preprocess(fr["noisy"], fr["gt"], fr["aux"], centres, P, no, to_, ao, img)
+    rn, rg, ra = O.preprocess_batch(*(torch.from_numpy(np.stack([S.crop_patches(
+        fr[k][int(img[i])].cpu().numpy(), centres[i:i + 1].cpu().numpy(), P)[0] for i in range(4)]))
+        for k in ("noisy", "gt", "aux")))
+    assert (no.cpu() - rn).abs().max() < 1e-6 and (to_.cpu() - rg).abs().max() < 1e-6
+    assert torch.equal(ao.cpu(), ra)
+
+
+def test_adam_matches_torch_adam():
+    ops = _ops()
+    torch.manual_seed(9)
+    n = 100_003  # exercises the vector tail
+    p = torch.randn(n, device=DEV)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-4, betas=(0.9, 0.999), eps=1e-8)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn(n, device=DEV) * 10 ** random.Random(step).uniform(-4, 0)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam(p, g, m, v, lr=1e-4, step=step)
+    assert rel_err(p, ref.detach()) < 1e-6
+    # grad_scale == averaging over ranks
+    p2, m2, v2 = torch.ones(8, device=DEV), torch.zeros(8, device=DEV), torch.zeros(8, device=DEV)
+    p3, m3, v3 = torch.ones(8, device=DEV), torch.zeros(8, device=DEV), torch.zeros(8, device=DEV)
+    g = torch.arange(8, device=DEV, dtype=torch.float32) + 1
+    ops.adam(p2, g * 4, m2, v2, lr=1e-3, step=1, grad_scale=0.25)
+    ops.adam(p3, g, m3, v3, lr=1e-3, step=1)
+    assert torch.allclose(p2, p3)
+
+
+def test_pack_transpose_roundtrip():
+    ops = _ops()
+    torch.manual_seed(10)
+    w = torch.randn(32, 48, 3, 3, device=DEV)
+    fwd = torch.zeros(9, 32, 48, device=DEV)
+    ops.pack_weight(w, fwd, ksize=3, Ntot=32, Ktot=48)
+    assert torch.equal(fwd, w.permute(2, 3, 0, 1).reshape(9, 32, 48))
+    tr = torch.zeros(9, 48, 32, device=DEV)
+    ops.pack_weight(w, tr, ksize=3, Ntot=48, Ktot=32, transpose=1)
+    assert torch.equal(tr, w.flip(2, 3).permute(2, 3, 1, 0).reshape(9, 48, 32))
+    sl = torch.zeros(1, 16, 32, device=DEV)
+    w1 = torch.randn(32, 48, 1, 1, device=DEV)
+    ops.pack_weight(w1, sl, ksize=1, Ntot=16, Ktot=32, transpose=1, i_begin=32, i_count=16, scale=0.5)
+    assert torch.equal(sl[0], 0.5 * w1[:, 32:, 0, 0].t())
+    back = torch.empty_like(w)
+    ops.unpack_wgrad(back, fwd, ksize=3, Ntot=32, Ktot=48, scale=2.0)
+    assert torch.equal(back, 2 * w)
+
+
+def test_sampler_bit_exact_with_reference_golden():
+    ops = _ops()
+    g = load_npz("sampler.npz")
+    for key, ref in g.items():
+        parts = key.split("_")
+        h, w, p, n = int(parts[0][1:]), int(parts[1][1:]), int(parts[2][1:]), int(parts[3][1:])
+        seeds = torch.tensor([990819], dtype=torch.int64, device=DEV)
+        out = ops.sample_patches(seeds, (h, w), p, n)
+        assert np.array_equal(out[0].cpu().numpy(), ref), key
+
+
+def test_sampler_many_images_matches_oracle():
+    ops = _ops()
+    seeds = torch.tensor([0, 1, 2, 77, 2 ** 33 + 9, 990820], dtype=torch.int64, device=DEV)
+    out = ops.sample_patches(seeds, (200, 264), 32, 40).cpu().numpy()
+    for i, s in enumerate(seeds.tolist()):
+        ref = S.dart_throwing((200, 264), 32, 40, S.MT19937(s))
+        assert np.array_equal(out[i], ref), s
+    # Poisson-disk property at full size: all accepted points are distinct
+    big = ops.sample_patches(torch.tensor([5], dtype=torch.int64, device=DEV), (1024, 1024), 128, 400)[0].cpu().numpy()
+    assert len({tuple(p) for p in big}) == 400 and big.min() >= 0 and big.max() <= 1024 - 128 - 1
