@@ -28,3 +28,12 @@ def load_npz(name):
 def load_json(name):
     with open(os.path.join(GOLDEN, name)) as f:
         return json.load(f)
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_reference_math():
+    """torch references on the GPU must be true fp32 (no TF32) to serve as a 1e-5 checker."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
