@@ -391,8 +391,4 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   return PHT_OK;
 }
 
-// weight-gradient on tensor cores: not built yet -> CUDA-core split-K kernel
-int wgrad_tc(const pht_wgrad_args*, cudaStream_t, bool* handled) { *handled = false; return PHT_OK; }
-size_t wgrad_tc_workspace_bytes(const pht_wgrad_args*) { return 0; }
-
 }  // namespace pht

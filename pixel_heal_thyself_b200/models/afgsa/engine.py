@@ -63,6 +63,10 @@ class AfgsaEngine:
         # parameter gradients are final in net.flat_grad (parallel.GradBucketer.ready)
         self.grad_ready_hook = None
 
+    def _dbg(self, name, t):
+        if getattr(self, "debug_sink", None) is not None:
+            self.debug_sink[name] = t.detach().clone()
+
     def _ready(self, tag):
         if self.grad_ready_hook is not None:
             self.grad_ready_hook(tag)
@@ -279,15 +283,18 @@ class AfgsaEngine:
         ops.dec_tail_bwd_weight(d_out, D2, dw2, G["decoder.2.0.bias"], tail_ws)
         G["decoder.2.0.weight"].copy_(dw2.view(3, 3, 3, C).permute(0, 3, 1, 2))
         ops.dec_tail_bwd_data(d_out, pk["dec2"], D2, G0)                       # G0 = d(D2 pre-act)
+        self._dbg("dD2pre", G0); self._dbg("d_out", d_out); self._dbg("D2", D2); self._dbg("D1", D1p)
         conv3_wgrad(G0, D1p, "decoder.1.0")
         conv3_dgrad(G0, pk["dec1.T"])
         ops.pad_fold(GP, mode, mask=D1p[:, 1:-1, 1:-1, :], mslope=relu0, out2=G1)   # G1 = d(D1 pre-act)
+        self._dbg("dD1pre", G1)
         Xlast = g(f"Xp{self.num_sa}", (B, H + 2, W + 2, C), T)
         conv3_wgrad(G1, Xlast, "decoder.0.0")
         self._ready("decoder")
         conv3_dgrad(G1, pk["dec0.T"])
         if self.num_sa > 0:
             ops.pad_fold(GP, mode, mask=g(f"H2{self.num_sa - 1}", (B, H, W, C), T), mslope=relu0, out1=GX, out2=G0)
+            self._dbg("dXlast", GX); self._dbg("dH2pre_last", G0)
         else:
             ops.pad_fold(GP, mode, mask=Xlast[:, 1:-1, 1:-1, :], mslope=relu0, out2=G0)
 

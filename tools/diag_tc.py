@@ -72,6 +72,23 @@ def conv_case(B, H, W, Cs, N, ks, epi=False, pad_domain=False, seed=0):
     return run
 
 
+def wgrad_case(B, H, W, Cs, N, ks, seed=0):
+    torch.manual_seed(seed)
+    pad = ks // 2
+    srcs = [torch.randn(B, H + 2 * pad, W + 2 * pad, c, device=DEV).bfloat16() for c in Cs]
+    dy = torch.randn(B, H, W, N, device=DEV).bfloat16()
+    K = sum(Cs)
+    ws = torch.empty(64 * 1024 * 1024 // 4, device=DEV)
+
+    def run():
+        dw = torch.zeros(ks * ks, N, K, device=DEV)
+        db = torch.zeros(N, device=DEV)
+        ops.wgrad(dy, srcs, dw, ksize=ks, dbias=db, workspace=ws, src_offsets=[(pad, pad)] * len(Cs))
+        return [dw, db]
+
+    return run
+
+
 def main():
     print(torch.cuda.get_device_name(0))
     cases = [
@@ -84,6 +101,15 @@ def main():
         ("3x3 C256 N256 32x32 B2 epi", conv_case(2, 32, 32, [256], 256, 3, epi=True)),
         ("3x3 C256 N256 24x40 padded-domain", conv_case(1, 24, 40, [256], 256, 3, pad_domain=True)),
         ("1x1 C192 N768 16x16", conv_case(1, 16, 16, [192], 768, 1)),
+    ]
+    cases += [
+        ("wgrad 1x1 C64 N128 16x16", wgrad_case(1, 16, 16, [64], 128, 1)),
+        ("wgrad 1x1 C256 N256 32x32 B2", wgrad_case(2, 32, 32, [256], 256, 1)),
+        ("wgrad 3x3 C256 N256 24x40 B2", wgrad_case(2, 24, 40, [256], 256, 3)),
+        ("wgrad 1x1 C256+256 N256 24x40", wgrad_case(1, 24, 40, [256, 256], 256, 1)),
+        ("wgrad 1x1 C256 N512 16x48", wgrad_case(1, 16, 48, [256], 512, 1)),
+        ("wgrad 1x1 C192 N768 16x16", wgrad_case(2, 16, 16, [192], 768, 1)),
+        ("wgrad 1x1 C768 N256 8x8", wgrad_case(1, 8, 8, [768], 256, 1)),
     ]
     worst = 0.0
     for name, fn in cases:
@@ -110,6 +136,21 @@ def main():
             ms = e0.elapsed_time(e1) / 10
             fl = 2.0 * B * H * W * sum(Cs) * N * ks * ks
             print(f"  perf ks={ks} C={Cs} N={N} {B}x{H}x{W}: {ms:.3f} ms/launch (incl. 2 memsets) = {fl / ms / 1e9:.1f} TFLOP/s")
+        for (B, H, W, Cs, N, ks) in ((8, 128, 128, [256], 256, 3), (8, 128, 128, [256, 256], 256, 1),
+                                     (8, 128, 128, [256], 512, 1), (8, 128, 128, [768], 256, 1)):
+            fn = wgrad_case(B, H, W, Cs, N, ks)
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            fl = 2.0 * B * H * W * sum(Cs) * N * ks * ks
+            print(f"  perf wgrad ks={ks} C={Cs} N={N} {B}x{H}x{W}: {ms:.3f} ms (incl. colsum+memsets+reduce) = {fl / ms / 1e9:.1f} TFLOP/s")
 
 
 if __name__ == "__main__":
