@@ -235,28 +235,32 @@ __global__ void __launch_bounds__(256) wgrad_simple_kernel(WgradP P) {
   }
 }
 
-// column sums of dy (bias gradient): block = 32 channels x 8 pixel lanes
+// column sums of dy (bias gradient), HBM-bound: every pixel row of N channels is read once with 4-element
+// vector loads (tpp = N/4 consecutive threads cover one pixel -> fully coalesced), `rows` pixels per block
+// iteration, fp32 partials reduced through shared memory, one atomicAdd per channel per block.
 template <typename T>
-__global__ void colsum_kernel(View dy, int B, int Ho, int Wo, int N, int chunk, float* __restrict__ out) {
-  __shared__ float sm[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+__global__ void colsum_kernel(View dy, int B, int Ho, int Wo, int N, int tpp, int rows, int chunk, float* __restrict__ out) {
+  extern __shared__ float sm[];  // [rows][N]
+  const int col = (threadIdx.x % tpp) * 4, prow = threadIdx.x / tpp;
   const long long npx = (long long)B * Ho * Wo;
-  const long long pbeg = (long long)blockIdx.y * chunk, pend = pbeg + chunk < npx ? pbeg + chunk : npx;
-  float s = 0.f;
-  if (c < N)
-    for (long long p = pbeg + r; p < pend; p += 8) {
+  const long long pbeg = (long long)blockIdx.x * chunk, pend = pbeg + chunk < npx ? pbeg + chunk : npx;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (prow < rows)
+    for (long long p = pbeg + prow; p < pend; p += rows) {
       int x = (int)(p % Wo);
       long long q = p / Wo;
       int y = (int)(q % Ho);
       int b = (int)(q / Ho);
-      s += to_f<T>(((const T*)dy.ptr)[view_off(dy, b, y + dy.oy, x + dy.ox) + c]);
-    }
-  sm[r][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (r == 0 && c < N) {
-    float t = 0.f;
+      float v[4];
+      ld4<T>((const T*)dy.ptr + view_off(dy, b, y + dy.oy, x + dy.ox) + col, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+      for (int j = 0; j < 4; ++j) acc[j] += v[j];
+    }
+  if (prow < rows) *reinterpret_cast<float4*>(&sm[prow * N + col]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float t = 0.f;
+    for (int i = 0; i < rows; ++i) t += sm[i * N + c];
     atomicAdd(out + c, t);
   }
 }
@@ -369,15 +373,24 @@ int wgrad_simple(const pht_wgrad_args* a, cudaStream_t st) {
 
 int colsum(const pht_view& dy, int dtype, int B, int Ho, int Wo, int N, float* out, cudaStream_t st) {
   long long npx = (long long)B * Ho * Wo;
-  int splits = (int)((npx + 2047) / 2048);
-  if (splits > 1024) splits = 1024;
+  PHT_CHECK_ARG(N % 4 == 0 && N <= 4096, "colsum: N must be a multiple of 4 and <= 4096");
+  const int tpp = N / 4;                           // threads per pixel row
+  int rows = tpp >= 256 ? 1 : 256 / tpp;           // pixel rows per block iteration
+  int threads = tpp * rows;
+  if (threads > 1024) { rows = 1; threads = tpp; }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int splits = (int)((npx + 16 * rows - 1) / (16 * rows));
+  if (splits > 4 * sms) splits = 4 * sms;
+  if (splits < 1) splits = 1;
   int chunk = (int)((npx + splits - 1) / splits);
   splits = (int)((npx + chunk - 1) / chunk);
   PHT_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
-  dim3 grid(ceil_div(N, 32), splits);
   View v = make_view(dy);
-  if (dtype == PHT_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(v, B, Ho, Wo, N, chunk, out);
-  else colsum_kernel<bf16><<<grid, 256, 0, st>>>(v, B, Ho, Wo, N, chunk, out);
+  size_t smem = (size_t)rows * N * sizeof(float);
+  if (dtype == PHT_F32) colsum_kernel<float><<<splits, threads, smem, st>>>(v, B, Ho, Wo, N, tpp, rows, chunk, out);
+  else colsum_kernel<bf16><<<splits, threads, smem, st>>>(v, B, Ho, Wo, N, tpp, rows, chunk, out);
   count_launch(CNT_OTHER);
   PHT_LAUNCH_CHECK();
   return PHT_OK;

@@ -67,7 +67,9 @@ def _grad_errors(num_sa, B, H, W, mode, seed):
     sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
     torch.manual_seed(seed)
     x, aux, gt = torch.randn(B, 3, H, W) * 0.5, torch.rand(B, 7, H, W), torch.randn(B, 3, H, W) * 0.5
-    o_out, o_loss, o_grads = O.g_only_train_step(x, aux, gt, sd, mode, num_sa=num_sa)
+    # fp64 oracle = ground truth (a CPU fp32 run has its own, different, kink flips)
+    sd64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in sd.items()}
+    o_out, o_loss, o_grads = O.g_only_train_step(x.double(), aux.double(), gt.double(), sd64, mode, num_sa=num_sa)
     out = net(x.to(DEV), aux.to(DEV))
     loss = L1ReconstructionLoss()(out, gt.to(DEV))
     loss.backward()
@@ -76,8 +78,9 @@ def _grad_errors(num_sa, B, H, W, mode, seed):
     errs = {}
     for n, p in net.named_parameters():
         ref = o_grads[n]
-        errs[n] = (float((p.grad.cpu() - ref).abs().max() / (ref.abs().max() + 1e-30)),
-                   float((p.grad.cpu() - ref).norm() / (ref.norm() + 1e-30)))
+        got = p.grad.cpu().double()
+        errs[n] = (float((got - ref).abs().max() / (ref.abs().max() + 1e-300)),
+                   float((got - ref).norm() / (ref.norm() + 1e-300)))
     return errs
 
 

@@ -89,6 +89,34 @@ def wgrad_case(B, H, W, Cs, N, ks, seed=0):
     return run
 
 
+def attn_case(B, H, W, seed=0, bwd=False):
+    torch.manual_seed(seed)
+    C = 256
+    qk = torch.randn(B, H, W, 2 * C, device=DEV)
+    qk[..., :C] *= 0.125
+    qk = qk.bfloat16()
+    v = torch.randn(B, H, W, C, device=DEV).bfloat16()
+    resid = torch.randn(B, H, W, C, device=DEV).bfloat16()
+    rel_h, rel_w = torch.randn(14, 32, device=DEV), torch.randn(14, 32, device=DEV)
+    do = torch.randn(B, H, W, C, device=DEV).bfloat16()
+
+    def run():
+        out = torch.zeros(B, H + 2, W + 2, C, device=DEV, dtype=torch.bfloat16)
+        lse = torch.zeros(B, H, W, 4, device=DEV)
+        ops.attn_fwd(qk[..., :C], qk[..., C:], v, rel_h, rel_w, out[:, 1:-1, 1:-1, :], resid=resid, lse=lse)
+        res = [out, lse]
+        if bwd:
+            dq = torch.zeros(B, H, W, 2 * C, device=DEV, dtype=torch.bfloat16)
+            dk, dv = torch.zeros(B * H * W, C, device=DEV), torch.zeros(B * H * W, C, device=DEV)
+            drh, drw = torch.zeros(14, 32, device=DEV), torch.zeros(14, 32, device=DEV)
+            ws = torch.empty(max(ops.attn_bwd_workspace_bytes(v), 16) // 4, device=DEV)
+            ops.attn_bwd(qk[..., :C], qk[..., C:], v, rel_h, rel_w, lse, do, dq[..., :C], dk, dv, drh, drw, ws)
+            res += [dq, dk, dv, drh, drw]
+        return res
+
+    return run
+
+
 def main():
     print(torch.cuda.get_device_name(0))
     cases = [
@@ -111,6 +139,13 @@ def main():
         ("wgrad 1x1 C192 N768 16x16", wgrad_case(2, 16, 16, [192], 768, 1)),
         ("wgrad 1x1 C768 N256 8x8", wgrad_case(1, 8, 8, [768], 256, 1)),
     ]
+    cases += [
+        ("attn fwd 8x8", attn_case(1, 8, 8)),
+        ("attn fwd 16x24 B2", attn_case(2, 16, 24)),
+        ("attn fwd+bwd 32x32", attn_case(1, 32, 32, bwd=True)),
+    ]
+    if "--only-attn" in sys.argv:
+        cases = [c for c in cases if c[0].startswith("attn")]
     worst = 0.0
     for name, fn in cases:
         try:
@@ -136,6 +171,18 @@ def main():
             ms = e0.elapsed_time(e1) / 10
             fl = 2.0 * B * H * W * sum(Cs) * N * ks * ks
             print(f"  perf ks={ks} C={Cs} N={N} {B}x{H}x{W}: {ms:.3f} ms/launch (incl. 2 memsets) = {fl / ms / 1e9:.1f} TFLOP/s")
+        for bwd in (False, True):
+            fn = attn_case(8, 128, 128, bwd=bwd)
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            print(f"  perf attn {'fwd+bwd' if bwd else 'fwd'} 8x128x128: {e0.elapsed_time(e1) / 5:.3f} ms (incl. output memsets)")
         for (B, H, W, Cs, N, ks) in ((8, 128, 128, [256], 256, 3), (8, 128, 128, [256, 256], 256, 1),
                                      (8, 128, 128, [256], 512, 1), (8, 128, 128, [768], 256, 1)):
             fn = wgrad_case(B, H, W, Cs, N, ks)
