@@ -158,16 +158,18 @@ typedef struct pht_attn_args {
 int pht_attn_fwd(const pht_attn_args* args, void* stream);
 
 /* Recompute-based backward of the op above (autograd of model.py:474-516):
- * given d_out, recomputes P from q, k, lse and produces dq (view), dk / dv as
- * fp32 accumulators [B*H*W][C] (caller zeroes them; halo overlap is summed
- * with atomics), and d_rel_h / d_rel_w fp32 [win][d/2] (OVERWRITTEN).
- * workspace: pht_attn_bwd_workspace_bytes() for the per-block rel partials. */
+ * given d_out, recomputes P from q, k, lse and produces dq, dk, dv (views in
+ * the activations' dtype, OVERWRITTEN; the up-to-4 overlapping window
+ * contributions of a key pixel are summed inside the op) and d_rel_h / d_rel_w
+ * fp32 [win][d/2] (OVERWRITTEN).
+ * workspace: pht_attn_bwd_workspace_bytes() bytes (window-major dK/dV scratch or
+ * fp32 accumulators, plus the relative-position partial sums). */
 typedef struct pht_attn_bwd_args {
   pht_attn_args fwd;        /* q, k, v, rel_*, lse as in the forward; out/resid unused */
   pht_view d_out;
   pht_view dq;
-  float* dk_acc;
-  float* dv_acc;
+  pht_view dk;
+  pht_view dv;
   float* d_rel_h;
   float* d_rel_w;
   void* workspace;

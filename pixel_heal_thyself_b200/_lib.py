@@ -50,8 +50,8 @@ class AttnArgs(C.Structure):
 
 
 class AttnBwdArgs(C.Structure):
-    _fields_ = [("fwd", AttnArgs), ("d_out", PhtView), ("dq", PhtView), ("dk_acc", C.c_void_p),
-                ("dv_acc", C.c_void_p), ("d_rel_h", C.c_void_p), ("d_rel_w", C.c_void_p), ("workspace", C.c_void_p),
+    _fields_ = [("fwd", AttnArgs), ("d_out", PhtView), ("dq", PhtView), ("dk", PhtView),
+                ("dv", PhtView), ("d_rel_h", C.c_void_p), ("d_rel_w", C.c_void_p), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_size_t)]
 
 

@@ -7,6 +7,7 @@ namespace pht {
 
 int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled);       // attention_tc.cu
 int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled);   // attention_tc.cu
+size_t attn_bwd_tc_ws_bytes(const pht_attn_args& f);                            // attention_tc.cu
 
 struct AttnP {
   int B, H, W, heads, d, block, halo, win, nq, nk, nby, nbx;
@@ -259,28 +260,60 @@ int attn_fwd_simple(const pht_attn_args* a, cudaStream_t st) {
   return PHT_OK;
 }
 
+// fp32 accumulator [npx][C] -> strided NHWC view in the activation dtype
+template <typename T>
+__global__ void acc_to_view_kernel(const float* __restrict__ acc, View out, int B, int H, int W, int C) {
+  long long total = (long long)B * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int x = (int)(p % W);
+    long long r = p / W;
+    int y = (int)(r % H);
+    int b = (int)(r / H);
+    ((T*)out.ptr)[view_off(out, b, y, x) + c] = from_f<T>(acc[i]);
+  }
+}
+
+size_t attn_bwd_simple_ws_bytes(const pht_attn_args& f) {
+  size_t npx = (size_t)f.B * f.H * f.W, C = (size_t)f.heads * f.head_dim;
+  size_t nblk = (size_t)f.B * (f.H / f.block) * (f.W / f.block);
+  size_t win = f.block + 2 * f.halo;
+  return 2 * npx * C * sizeof(float) + nblk * f.heads * (2 * win * (f.head_dim / 2)) * sizeof(float);
+}
+
 int attn_bwd_simple(const pht_attn_bwd_args* a, cudaStream_t st) {
   AttnP P;
   int rc = fill_params(&a->fwd, &P);
   if (rc) return rc;
-  PHT_CHECK_ARG(a->d_out.ptr && a->dq.ptr && a->dk_acc && a->dv_acc && a->d_rel_h && a->d_rel_w && a->fwd.lse, "attn_bwd: null arg");
-  PHT_CHECK_ARG(a->workspace && a->workspace_bytes >= pht_attn_bwd_workspace_bytes(a), "attn_bwd: workspace too small");
+  PHT_CHECK_ARG(a->d_out.ptr && a->dq.ptr && a->dk.ptr && a->dv.ptr && a->d_rel_h && a->d_rel_w && a->fwd.lse, "attn_bwd: null arg");
+  PHT_CHECK_ARG(a->workspace && a->workspace_bytes >= attn_bwd_simple_ws_bytes(a->fwd), "attn_bwd: workspace too small");
   P.d_out = make_view(a->d_out); P.dq = make_view(a->dq);
-  P.dk_acc = a->dk_acc; P.dv_acc = a->dv_acc; P.rel_part = (float*)a->workspace;
+  const size_t npx = (size_t)P.B * P.H * P.W, C = (size_t)P.heads * P.d;
+  P.dk_acc = (float*)a->workspace;
+  P.dv_acc = P.dk_acc + npx * C;
+  P.rel_part = P.dv_acc + npx * C;
+  PHT_CUDA(cudaMemsetAsync(P.dk_acc, 0, 2 * npx * C * sizeof(float), st));
   size_t sm = smem_bytes(P, true);
   dim3 grid(P.B * P.nby * P.nbx, P.heads);
+  int cgrid = (int)((npx * C + 255) / 256);
+  if (cgrid > 148 * 16) cgrid = 148 * 16;
   if (a->fwd.dtype == PHT_F32) {
     PHT_CUDA(cudaFuncSetAttribute(attn_bwd_simple_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attn_bwd_simple_kernel<float><<<grid, 256, sm, st>>>(P);
+    acc_to_view_kernel<float><<<cgrid, 256, 0, st>>>(P.dk_acc, make_view(a->dk), P.B, P.H, P.W, (int)C);
+    acc_to_view_kernel<float><<<cgrid, 256, 0, st>>>(P.dv_acc, make_view(a->dv), P.B, P.H, P.W, (int)C);
   } else {
     PHT_CUDA(cudaFuncSetAttribute(attn_bwd_simple_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attn_bwd_simple_kernel<bf16><<<grid, 256, sm, st>>>(P);
+    acc_to_view_kernel<bf16><<<cgrid, 256, 0, st>>>(P.dk_acc, make_view(a->dk), P.B, P.H, P.W, (int)C);
+    acc_to_view_kernel<bf16><<<cgrid, 256, 0, st>>>(P.dv_acc, make_view(a->dv), P.B, P.H, P.W, (int)C);
   }
   PHT_LAUNCH_CHECK();
   int n = 2 * P.win * (P.d / 2);
   rel_reduce_kernel<<<ceil_div(n, 128), 128, 0, st>>>(P.rel_part, grid.x * grid.y, n, n / 2, a->d_rel_h, a->d_rel_w);
   count_launch(CNT_ATTN_SIMPLE);
-  count_launch(CNT_OTHER);
+  count_launch(CNT_OTHER, 3);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
@@ -305,11 +338,10 @@ int pht_attn_fwd(const pht_attn_args* a, void* stream) {
 }
 
 size_t pht_attn_bwd_workspace_bytes(const pht_attn_bwd_args* a) {
-  if (!a || a->fwd.block <= 0) return 0;
-  const pht_attn_args& f = a->fwd;
-  size_t nblk = (size_t)f.B * (f.H / f.block) * (f.W / f.block);
-  size_t win = f.block + 2 * f.halo;
-  return nblk * f.heads * (2 * win * (f.head_dim / 2)) * sizeof(float);
+  if (!a || a->fwd.block <= 0 || a->fwd.heads <= 0) return 0;
+  size_t s = attn_bwd_simple_ws_bytes(a->fwd);
+  size_t t = a->fwd.dtype == PHT_BF16 ? attn_bwd_tc_ws_bytes(a->fwd) : 0;
+  return s > t ? s : t;
 }
 
 int pht_attn_bwd(const pht_attn_bwd_args* a, void* stream) {

@@ -21,11 +21,6 @@ namespace pht {
 
 using namespace tc;
 
-int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {  // backward: CUDA-core kernel for now
-  *handled = false;
-  return PHT_OK;
-}
-
 constexpr int AT_THREADS = 192;
 constexpr int AT_NK = 196, AT_NKP = 208, AT_NS = 240;          // keys, keys padded to 16, S columns incl. rel rows
 constexpr int AT_Q_BYTES = 64 * 128;                           // 8 KB per head
@@ -360,6 +355,471 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   attn_fwd_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, P);
   PHT_LAUNCH_CHECK();
   count_launch(CNT_ATTN_TC);
+  *handled = true;
+  return PHT_OK;
+}
+
+
+// =================================================================================================
+// Backward (recompute), one (block, head) per iteration, everything on tcgen05:
+//   S' = Q K'^T, dP = dO V^T            (keys 0..111 in TMEM lanes +0, keys 112..223 in lanes +16: both 16-lane
+//                                         halves of every sub-partition hold one query row -> 128 busy threads)
+//   P = exp(S' - lse), delta = sum P.dP, dS = P.(dP - delta)   -> bf16 P / dS tiles in smem (128B swizzle)
+//   dV = P^T dO, dK = dS^T Q             (A operands MN-major: the [query x key] tiles are read transposed)
+//   dQ = dS_ext K_ext                    (K_ext rows 256..287 = relative-position rows, dS_ext cols 256..287 =
+//                                         row / column sums of dS over the 14x14 window => dS.(K + rel) exactly)
+//   d_rel += dS_ext[:, 256..287]^T Q     (one M=64 accumulator that lives in TMEM for the whole kernel)
+// dK / dV leave the SM window-major in bf16 (coalesced 128-byte rows, no atomics); a fold kernel sums the <= 4
+// overlapping windows of every pixel deterministically and writes the final NHWC gradients.
+// =================================================================================================
+constexpr int AB_K_ROWS = 288, AB_V_ROWS = 224;
+constexpr int AB_Q_BYTES = 8192, AB_K_BYTES = AB_K_ROWS * 128, AB_V_BYTES = AB_V_ROWS * 128;
+constexpr int AB_P_BYTES = 4 * 8192, AB_DS_BYTES = 5 * 8192;
+constexpr int AB_SMEM = 2 * AB_Q_BYTES + AB_K_BYTES + AB_V_BYTES + AB_P_BYTES + AB_DS_BYTES + 256 + 1024;
+constexpr int AB_COL_REL = 112, AB_COL_DP = 144, AB_COL_DV = 0, AB_COL_DK = 128, AB_COL_DQ = 256, AB_COL_RELACC = 448;
+constexpr int AB_REL_PART = 2 * 14 * 32;  // floats per CTA partial
+
+struct AbP {
+  int B, H, W, nbx, nby, nblocks;
+  View dq;
+  const float* rel_h;
+  const float* rel_w;
+  const float* lse;
+  bf16* dk_scratch;   // [nblocks][4][196][64]
+  bf16* dv_scratch;
+  float* rel_part;    // [gridDim.x][896]
+};
+
+__device__ __forceinline__ void st_row64_bf16(bf16* dst, const uint32_t* lo, const uint32_t* hi) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t* r = g < 4 ? lo + g * 8 : hi + (g - 4) * 8;
+    uint4 u;
+    __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    *reinterpret_cast<uint4*>(dst + g * 8) = u;
+  }
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AbP P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;
+  uint8_t* dOs = Qs + AB_Q_BYTES;
+  uint8_t* Ks = dOs + AB_Q_BYTES;
+  uint8_t* Vs = Ks + AB_K_BYTES;
+  uint8_t* Ps = Vs + AB_V_BYTES;
+  uint8_t* dSs = Ps + AB_P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dSs + AB_DS_BYTES);
+  uint64_t* in_full = bars + 0;
+  uint64_t* sdp_full = bars + 1;
+  uint64_t* ds_full = bars + 2;
+  uint64_t* out_full = bars + 3;
+  uint64_t* tmem_free = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time smem constants --------------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < (AB_K_ROWS - AT_NK) * 8; i += blockDim.x) {  // K rows 196..287
+    const int R = AT_NK + i / 8, ch = i % 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (R >= 256) {
+      const int rr = R - 256;  // 0..31: rows 0..13 = [rel_h | 0], rows 16..29 = [0 | rel_w]
+      if (rr < 14 && ch < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = P.rel_h[rr * 32 + ch * 8 + j];
+      } else if (rr >= 16 && rr < 30 && ch >= 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = P.rel_w[(rr - 16) * 32 + (ch - 4) * 8 + j];
+      }
+    }
+    uint4 u;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(Ks + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
+  }
+  for (int i = threadIdx.x; i < (AB_V_ROWS - AT_NK) * 8; i += blockDim.x)
+    *reinterpret_cast<uint4*>(Vs + (AT_NK + i / 8) * 128 + (i % 8) * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (AB_P_BYTES + AB_DS_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(Ps)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+    prefetch_tmap(&tmDO);
+    mbar_init(in_full, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_full, 128);
+    mbar_init(out_full, 1);
+    mbar_init(tmem_free, 128);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_blocks = (P.nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_it = 4 * my_blocks;  // (block, head) iterations
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
+        const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+        mbar_wait(out_full, (it & 1) ^ 1);  // all MMAs of the previous iteration have read the operand buffers
+        mbar_expect_tx(in_full, 2 * AB_Q_BYTES + 2 * AT_KV_BOX_BYTES);
+        tma_load_4d(Qs, &tmQ, in_full, head * 64, bx * 8, by * 8, b);
+        tma_load_4d(dOs, &tmDO, in_full, head * 64, bx * 8, by * 8, b);
+        tma_load_4d(Ks, &tmK, in_full, head * 64, bx * 8 - 3, by * 8 - 3, b);
+        tma_load_4d(Vs, &tmV, in_full, head * 64, bx * 8 - 3, by * 8 - 3, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t id_s = umma_idesc_bf16(64, 112, 0, 0);
+      constexpr uint32_t id_rel = umma_idesc_bf16(64, 32, 0, 0);
+      constexpr uint32_t id_dvk = umma_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t id_racc = umma_idesc_bf16(64, 64, 1, 1);
+      constexpr uint32_t id_dq = umma_idesc_bf16(64, 64, 0, 1);
+      const uint32_t q_a = smem_u32(Qs), do_a = smem_u32(dOs), k_a = smem_u32(Ks), v_a = smem_u32(Vs), p_a = smem_u32(Ps),
+                     ds_a = smem_u32(dSs);
+      for (int it = 0; it < n_it; ++it) {
+        mbar_wait(in_full, it & 1);
+        mbar_wait(tmem_free, (it & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t qd = umma_desc_k_sw128(q_a), dod = umma_desc_k_sw128(do_a);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {  // lane half hf handles keys [112*hf, 112*hf + 112)
+          const uint32_t d = tmem_base + ((uint32_t)(hf * 16) << 16);
+          const uint64_t kd = umma_desc_k_sw128(k_a + hf * 112 * 128);
+          const uint64_t kr = umma_desc_k_sw128(k_a + 256 * 128);
+          const uint64_t vd = umma_desc_k_sw128(v_a + hf * 112 * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, id_s, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d + AB_COL_REL, qd + 2 * k, kr + 2 * k, id_rel, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d + AB_COL_DP, dod + 2 * k, vd + 2 * k, id_s, k ? 1u : 0u);
+        }
+        umma_commit(sdp_full);
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t pa = umma_desc_mn_sw128(p_a + t2 * 16384 + k * 2048, 8192, 1024);
+            const uint64_t dsa = umma_desc_mn_sw128(ds_a + t2 * 16384 + k * 2048, 8192, 1024);
+            const uint64_t dob = umma_desc_mn_sw128(do_a + k * 2048, 8192, 1024);
+            const uint64_t qb = umma_desc_mn_sw128(q_a + k * 2048, 8192, 1024);
+            umma_bf16(tmem_base + AB_COL_DV + t2 * 64, pa, dob, id_dvk, k ? 1u : 0u);
+            umma_bf16(tmem_base + AB_COL_DK + t2 * 64, dsa, qb, id_dvk, k ? 1u : 0u);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ra = umma_desc_mn_sw128(ds_a + 4 * 8192 + k * 2048, 8192, 1024);
+          const uint64_t qb = umma_desc_mn_sw128(q_a + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base + AB_COL_RELACC, ra, qb, id_racc, (it | k) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 15; ++kk) {
+          const int tile = kk < 13 ? (kk >> 2) : 4, ks = kk < 13 ? (kk & 3) : kk - 13;
+          const int krow = kk < 13 ? kk * 16 : 256 + (kk - 13) * 16;
+          const uint64_t dsa = umma_desc_k_sw128(ds_a + tile * 8192) + 2 * ks;
+          const uint64_t kb = umma_desc_mn_sw128(k_a + krow * 128, 8192, 1024);
+          umma_bf16(tmem_base + AB_COL_DQ, dsa, kb, id_dq, kk ? 1u : 0u);
+        }
+        umma_commit(out_full);
+      }
+    }
+  } else {
+    // ================================ softmax / dS / read-out (warps 2..5) ================================
+    const int quad = warp & 3;
+    const int hf = lane >> 4;                    // key half handled by this thread
+    const int q = quad * 16 + (lane & 15);       // query row
+    const int qy = q >> 3, qx = q & 7;
+    const float LOG2E = 1.4426950408889634f;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int kvalid = hf ? 84 : 112;            // valid keys of this half: key = 112*hf + k' < 196
+    uint8_t* prow = Ps + q * 128;
+    uint8_t* dsrow = dSs + q * 128;
+
+    for (int it = 0; it < n_it; ++it) {
+      const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
+      const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+      const float l2 = P.lse[(((long long)b * P.H + by * 8 + qy) * P.W + bx * 8 + qx) * 4 + head] * LOG2E;
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      uint32_t rr[32];
+      tmem_ld32(lane_addr + AB_COL_REL, rr);
+      tmem_ld_wait();
+      float rh[8], rw[14];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rh[i] = __uint_as_float(hf ? rr[(8 + i) & 15] : rr[i]);
+#pragma unroll
+      for (int c = 0; c < 14; ++c) rw[c] = __uint_as_float(rr[16 + c]);
+      // ---- pass 1: P = exp(S' - lse) -> smem, delta = sum_j P dP ----
+      float delta = 0.f;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        uint32_t s[16], dp[16];
+        tmem_ld16(lane_addr + i * 16, s);
+        tmem_ld16(lane_addr + AB_COL_DP + i * 16, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float p[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int kp = i * 16 + g * 8 + j;
+            const float sv = __uint_as_float(s[g * 8 + j]) + rh[kp / 14] + rw[kp % 14];
+            p[j] = kp < kvalid ? ex2(fmaf(sv, LOG2E, -l2)) : 0.f;
+            delta = fmaf(p[j], __uint_as_float(dp[g * 8 + j]), delta);
+          }
+          uint4 u;
+          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
+          const int key0 = hf * 112 + i * 16 + g * 8;
+          *reinterpret_cast<uint4*>(prow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ (q & 7)) * 16)) = u;
+        }
+      }
+      delta += __shfl_xor_sync(0xffffffffu, delta, 16);
+      // ---- pass 2: dS = P (dP - delta) -> smem, window row / column sums for the relative-position terms ----
+      float rsum[8], csum[14];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rsum[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 14; ++c) csum[c] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        uint32_t dp[16];
+        tmem_ld16(lane_addr + AB_COL_DP + i * 16, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int key0 = hf * 112 + i * 16 + g * 8;
+          uint8_t* ppos = prow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ (q & 7)) * 16);
+          const uint4 pu = *reinterpret_cast<const uint4*>(ppos);
+          const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&pu);
+          float ds[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 pf = __bfloat1622float2(ph[j]);
+            ds[2 * j] = pf.x * (__uint_as_float(dp[g * 8 + 2 * j]) - delta);
+            ds[2 * j + 1] = pf.y * (__uint_as_float(dp[g * 8 + 2 * j + 1]) - delta);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int kp = i * 16 + g * 8 + j;
+            rsum[kp / 14] += ds[j];   // ds == 0 for invalid keys (P == 0)
+            csum[kp % 14] += ds[j];
+          }
+          uint4 u;
+          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(ds[2 * j], ds[2 * j + 1]);
+          *reinterpret_cast<uint4*>(dsrow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ (q & 7)) * 16)) = u;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 14; ++c) csum[c] += __shfl_xor_sync(0xffffffffu, csum[c], 16);
+      {
+        // dS_ext columns 256..271 = window-row sums (row r = 8*hf + i), 272..287 = window-column sums
+        uint4 u, w;
+        __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
+        __nv_bfloat162* wh = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a0 = (hf && 2 * j >= 6) ? 0.f : rsum[2 * j], a1 = (hf && 2 * j + 1 >= 6) ? 0.f : rsum[2 * j + 1];
+          uh[j] = __floats2bfloat162_rn(a0, a1);
+          const int c0 = hf * 8 + 2 * j;
+          const float b0 = c0 < 14 ? (hf ? csum[(8 + 2 * j) % 14] : csum[2 * j]) : 0.f;
+          const float b1 = c0 + 1 < 14 ? (hf ? csum[(9 + 2 * j) % 14] : csum[2 * j + 1]) : 0.f;
+          wh[j] = __floats2bfloat162_rn(b0, b1);
+        }
+        *reinterpret_cast<uint4*>(dsrow + 4 * 8192 + (((hf) ^ (q & 7)) * 16)) = u;
+        *reinterpret_cast<uint4*>(dsrow + 4 * 8192 + (((2 + hf) ^ (q & 7)) * 16)) = w;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+      // ---- read-out: dV, dK (window-major bf16 scratch), dQ ----
+      mbar_wait(out_full, it & 1);
+      tc_fence_after();
+      const long long srow = ((long long)blk * 4 + head) * AT_NK;
+#pragma unroll
+      for (int t2 = 0; t2 < 2; ++t2) {
+        const int key = t2 * 128 + quad * 32 + lane;
+        uint32_t a[32], c[32];
+        tmem_ld32(lane_addr + AB_COL_DV + t2 * 64, a);
+        tmem_ld32(lane_addr + AB_COL_DV + t2 * 64 + 32, c);
+        tmem_ld_wait();
+        if (key < AT_NK) st_row64_bf16(P.dv_scratch + (srow + key) * 64, a, c);
+        tmem_ld32(lane_addr + AB_COL_DK + t2 * 64, a);
+        tmem_ld32(lane_addr + AB_COL_DK + t2 * 64 + 32, c);
+        tmem_ld_wait();
+        if (key < AT_NK) st_row64_bf16(P.dk_scratch + (srow + key) * 64, a, c);
+      }
+      {
+        uint32_t a[32], c[32];
+        tmem_ld32(lane_addr + AB_COL_DQ, a);
+        tmem_ld32(lane_addr + AB_COL_DQ + 32, c);
+        tmem_ld_wait();
+        if (hf == 0) st_row64_bf16((bf16*)P.dq.ptr + view_off(P.dq, b, by * 8 + qy, bx * 8 + qx) + head * 64, a, c);
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_free);
+    }
+    // relative-position gradient accumulator of this CTA (complete: the last out_full covered its MMAs)
+    if (n_it > 0) {
+      uint32_t a[32], c[32];
+      tmem_ld32(lane_addr + AB_COL_RELACC, a);
+      tmem_ld32(lane_addr + AB_COL_RELACC + 32, c);
+      tmem_ld_wait();
+      if (hf == 0) {
+        float* part = P.rel_part + (long long)blockIdx.x * AB_REL_PART;
+        if (q < 14) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part[q * 32 + j] = __uint_as_float(a[j]);          // d rel_h[q][:]
+        } else if (q >= 16 && q < 30) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part[448 + (q - 16) * 32 + j] = __uint_as_float(c[j]);  // d rel_w[q-16][:]
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// sum the (up to 4) window-major contributions of every key pixel; one thread per (pixel, head, 8 channels)
+__global__ void attn_bwd_fold_kernel(const bf16* __restrict__ dks, const bf16* __restrict__ dvs, View dk, View dv, int B,
+                                     int H, int W, int nby, int nbx) {
+  long long total = (long long)B * H * W * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i & 7), head = (int)((i >> 3) & 3);
+    long long p = i >> 5;
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H), b = (int)(p / H);
+    float ak[8], av[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ak[j] = av[j] = 0.f;
+    const int by0 = y >> 3, bx0 = x >> 3;
+    for (int by = by0 - 1; by <= by0 + 1; ++by) {
+      const int wy = y - (by * 8 - 3);
+      if (by < 0 || by >= nby || wy < 0 || wy >= 14) continue;
+      for (int bx = bx0 - 1; bx <= bx0 + 1; ++bx) {
+        const int wx = x - (bx * 8 - 3);
+        if (bx < 0 || bx >= nbx || wx < 0 || wx >= 14) continue;
+        const long long off = (((((long long)b * nby + by) * nbx + bx) * 4 + head) * AT_NK + wy * 14 + wx) * 64 + cg * 8;
+        const uint4 uk = *reinterpret_cast<const uint4*>(dks + off);
+        const uint4 uv = *reinterpret_cast<const uint4*>(dvs + off);
+        const __nv_bfloat162* hk = reinterpret_cast<const __nv_bfloat162*>(&uk);
+        const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&uv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fk = __bfloat1622float2(hk[j]), fv = __bfloat1622float2(hv[j]);
+          ak[2 * j] += fk.x; ak[2 * j + 1] += fk.y;
+          av[2 * j] += fv.x; av[2 * j + 1] += fv.y;
+        }
+      }
+    }
+    uint4 ok, ov;
+    __nv_bfloat162* hk = reinterpret_cast<__nv_bfloat162*>(&ok);
+    __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hk[j] = __floats2bfloat162_rn(ak[2 * j], ak[2 * j + 1]);
+      hv[j] = __floats2bfloat162_rn(av[2 * j], av[2 * j + 1]);
+    }
+    *reinterpret_cast<uint4*>((bf16*)dk.ptr + view_off(dk, b, y, x) + head * 64 + cg * 8) = ok;
+    *reinterpret_cast<uint4*>((bf16*)dv.ptr + view_off(dv, b, y, x) + head * 64 + cg * 8) = ov;
+  }
+}
+
+__global__ void attn_bwd_rel_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ d_rel_h,
+                                           float* __restrict__ d_rel_w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= AB_REL_PART) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(long long)p * AB_REL_PART + i];
+  if (i < 448) d_rel_h[i] = s;
+  else d_rel_w[i - 448] = s;
+}
+
+static int at_grid(int nblocks) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return nblocks < sms ? nblocks : sms;
+}
+
+size_t attn_bwd_tc_ws_bytes(const pht_attn_args& f) {
+  if (f.heads != 4 || f.head_dim != 64 || f.block != 8 || f.halo != 3) return 0;
+  size_t nblk = (size_t)f.B * (f.H / 8) * (f.W / 8);
+  return 2 * nblk * 4 * AT_NK * 64 * sizeof(bf16) + (size_t)at_grid((int)nblk) * AB_REL_PART * sizeof(float) + 256;
+}
+
+int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
+  *handled = false;
+  const pht_attn_args& f = a->fwd;
+  if (f.dtype != PHT_BF16 || f.heads != 4 || f.head_dim != 64 || f.block != 8 || f.halo != 3) return PHT_OK;
+  if (f.H % 8 || f.W % 8 || !f.lse) return PHT_OK;
+  if (!at_view_ok(f.q, 256) || !at_view_ok(f.k, 256) || !at_view_ok(f.v, 256) || !at_view_ok(a->d_out, 256)) return PHT_OK;
+  if (!at_view_ok(a->dq, 256) || !at_view_ok(a->dk, 256) || !at_view_ok(a->dv, 256)) return PHT_OK;
+  if (!a->workspace || ((uintptr_t)a->workspace & 255) || a->workspace_bytes < attn_bwd_tc_ws_bytes(f)) return PHT_OK;
+  if (!get_encode_fn()) return PHT_OK;
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  int rc = at_tmap(&tmQ, f.q, f.B, 8, 8);
+  if (rc) return rc;
+  rc = at_tmap(&tmK, f.k, f.B, 14, 14);
+  if (rc) return rc;
+  rc = at_tmap(&tmV, f.v, f.B, 14, 14);
+  if (rc) return rc;
+  rc = at_tmap(&tmDO, a->d_out, f.B, 8, 8);
+  if (rc) return rc;
+  AbP P;
+  P.B = f.B; P.H = f.H; P.W = f.W; P.nbx = f.W / 8; P.nby = f.H / 8; P.nblocks = f.B * P.nbx * P.nby;
+  P.dq = make_view(a->dq);
+  P.rel_h = f.rel_h; P.rel_w = f.rel_w; P.lse = f.lse;
+  const size_t scratch = (size_t)P.nblocks * 4 * AT_NK * 64;
+  P.dk_scratch = (bf16*)a->workspace;
+  P.dv_scratch = P.dk_scratch + scratch;
+  P.rel_part = (float*)(P.dv_scratch + scratch);
+  static bool attr = false;
+  if (!attr) {
+    PHT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    attr = true;
+  }
+  const int grid = at_grid(P.nblocks);
+  attn_bwd_tc_kernel<<<grid, AT_THREADS, AB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, P);
+  PHT_LAUNCH_CHECK();
+  long long items = (long long)f.B * f.H * f.W * 32;
+  int fgrid = (int)((items + 255) / 256);
+  if (fgrid > 148 * 16) fgrid = 148 * 16;
+  attn_bwd_fold_kernel<<<fgrid, 256, 0, st>>>(P.dk_scratch, P.dv_scratch, make_view(a->dk), make_view(a->dv), f.B, f.H, f.W,
+                                             P.nby, P.nbx);
+  attn_bwd_rel_reduce_kernel<<<(AB_REL_PART + 127) / 128, 128, 0, st>>>(P.rel_part, grid, a->d_rel_h, a->d_rel_w);
+  PHT_LAUNCH_CHECK();
+  count_launch(CNT_ATTN_TC);
+  count_launch(CNT_OTHER, 2);
   *handled = true;
   return PHT_OK;
 }

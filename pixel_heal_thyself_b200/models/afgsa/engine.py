@@ -259,8 +259,6 @@ class AfgsaEngine:
         dQK = g("dQK", (B, H, W, 2 * C), T)
         dV = g("dV", (B, H, W, C), T)
         dcat = g("dcat", (B, H, W, 768), T)
-        dk_acc = g("dk_acc", (npx, C), torch.float32)
-        dv_acc = g("dv_acc", (npx, C), torch.float32)
         wtmp = g("wtmp", (9 * C * 768,), torch.float32)
         btmp = g("btmp", (768,), torch.float32)
         attn_ws = g("attn_ws", (max(ops.attn_bwd_workspace_bytes(dQK[..., :C], self.heads, self.block, self.halo), 16) // 4,),
@@ -314,13 +312,9 @@ class AfgsaEngine:
             conv3_dgrad(G1, pk[f"b{i}.ff0.T"])
             ops.pad_fold(GP, mode, resid=GX, out1=G2)                                      # G2 = dX1 = dO
             # attention
-            dk_acc.zero_()
-            dv_acc.zero_()
             ops.attn_bwd(QK[..., :C], QK[..., C:], V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], lse, G2,
-                         dQK[..., :C], dk_acc, dv_acc, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,
+                         dQK[..., :C], dQK[..., C:], dV, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,
                          heads=self.heads, block=self.block, halo=self.halo)
-            ops.cast2d(dk_acc, dQK.view(npx, 2 * C)[:, C:])
-            ops.cast2d(dv_acc, dV.view(npx, C))
             wqk = wtmp[: 2 * C * C].view(1, 2 * C, C)
             ops.wgrad(dQK, [M], wqk, workspace=wg_ws)
             ops.unpack_wgrad(G[pre + "attention.q_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=0, scale=self.scale)

@@ -140,18 +140,20 @@ def attn_fwd(q, k, v, rel_h, rel_w, out, *, heads=4, block=8, halo=3, resid=None
 
 def attn_bwd_workspace_bytes(q, heads=4, block=8, halo=3) -> int:
     a = L.AttnBwdArgs()
+    a.fwd.dtype = L.DTYPES[q.dtype]
     a.fwd.B, a.fwd.H, a.fwd.W = q.shape[0], q.shape[1], q.shape[2]
     a.fwd.heads, a.fwd.head_dim, a.fwd.block, a.fwd.halo = heads, q.shape[3] // heads, block, halo
     return int(lib.pht_attn_bwd_workspace_bytes(C.byref(a)))
 
 
-def attn_bwd(q, k, v, rel_h, rel_w, lse, d_out, dq, dk_acc, dv_acc, d_rel_h, d_rel_w, workspace, *, heads=4, block=8,
+def attn_bwd(q, k, v, rel_h, rel_w, lse, d_out, dq, dk, dv, d_rel_h, d_rel_w, workspace, *, heads=4, block=8,
              halo=3):
-    L.require_cuda(q, k, v, d_out, dq, dk_acc, dv_acc)
+    """dq / dk / dv: [B,H,W,C] views (activation dtype), overwritten with the final gradients."""
+    L.require_cuda(q, k, v, d_out, dq, dk, dv)
     a = L.AttnBwdArgs()
     a.fwd = _attn_args(q, k, v, rel_h, rel_w, heads, block, halo, None, None, lse)
     a.d_out, a.dq = L.view(d_out), L.view(dq)
-    a.dk_acc, a.dv_acc = dk_acc.data_ptr(), dv_acc.data_ptr()
+    a.dk, a.dv = L.view(dk), L.view(dv)
     a.d_rel_h, a.d_rel_w = d_rel_h.data_ptr(), d_rel_w.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     L.check(lib.pht_attn_bwd(C.byref(a), L.stream_ptr()), "pht_attn_bwd")

@@ -235,15 +235,15 @@ def test_attention_forward_backward_matches_oracle(dtype, B, C, H, W):
         ops.attn_fwd(qd, kd, vd, rhd, rwd, out2, resid=resid)
         assert rel_err(out2 - resid, out) < 1e-5
     dq = torch.empty_like(qd)
-    dk = torch.zeros(B * H * W, C, device=DEV)
-    dv = torch.zeros(B * H * W, C, device=DEV)
+    dk = torch.zeros(B, H, W, C, dtype=dtype, device=DEV)
+    dv = torch.zeros(B, H, W, C, dtype=dtype, device=DEV)
     drh, drw = torch.empty_like(rhd), torch.empty_like(rwd)
     ws = torch.empty(max(ops.attn_bwd_workspace_bytes(qd), 16) // 4, device=DEV)
     ops.attn_bwd(qd, kd, vd, rhd, rwd, lse, g(do), dq, dk, dv, drh, drw, ws)
     t = 2e-5 if dtype == torch.float32 else 3e-2
     assert rel_err(nchw(dq).cpu(), qr.grad) < t
-    assert rel_err(dk.view(B, H, W, C).permute(0, 3, 1, 2).cpu(), kr.grad) < t
-    assert rel_err(dv.view(B, H, W, C).permute(0, 3, 1, 2).cpu(), vr.grad) < t
+    assert rel_err(nchw(dk).cpu(), kr.grad) < t
+    assert rel_err(nchw(dv).cpu(), vr.grad) < t
     assert rel_err(drh.cpu(), rh.grad) < t
     assert rel_err(drw.cpu(), rw.grad) < t
 

@@ -107,7 +107,8 @@ def attn_case(B, H, W, seed=0, bwd=False):
         res = [out, lse]
         if bwd:
             dq = torch.zeros(B, H, W, 2 * C, device=DEV, dtype=torch.bfloat16)
-            dk, dv = torch.zeros(B * H * W, C, device=DEV), torch.zeros(B * H * W, C, device=DEV)
+            dk = torch.zeros(B, H, W, C, device=DEV, dtype=torch.bfloat16)
+            dv = torch.zeros_like(dk)
             drh, drw = torch.zeros(14, 32, device=DEV), torch.zeros(14, 32, device=DEV)
             ws = torch.empty(max(ops.attn_bwd_workspace_bytes(v), 16) // 4, device=DEV)
             ops.attn_bwd(qk[..., :C], qk[..., C:], v, rel_h, rel_w, lse, do, dq[..., :C], dk, dv, drh, drw, ws)
