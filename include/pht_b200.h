@@ -243,6 +243,23 @@ typedef struct pht_pack_args {
 int pht_pack_weight(const pht_pack_args* a, void* stream);
 int pht_unpack_wgrad(const pht_pack_args* a, void* stream);
 
+/* All weight (re)packs of a step in ONE launch.  `jobs` is a HOST array of n descriptors (same meaning as
+ * pht_pack_weight; jobs[i].dtype is the dtype of jobs[i].packed).  `table_dev` is caller-owned device scratch of
+ * pht_pack_table_bytes(n) bytes; upload != 0 (re)writes the device copy of the descriptor table (needed the first
+ * time and whenever a pointer or shape in `jobs` changed), upload == 0 reuses it. */
+size_t pht_pack_table_bytes(int32_t n);
+int pht_pack_weights_batched(const pht_pack_args* jobs, int32_t n, void* table_dev, size_t table_bytes, int32_t upload,
+                             void* stream);
+
+/* Decoder tail on the tensor-core path (model.py:707-714, 732): the 256->3 zero-padded 3x3 conv runs as a 64-wide
+ * pht_conv_gemm with fp32 output y [B*H*W][ldy]; this adds bias and the residual and transposes to NCHW:
+ *   out_nchw[b,co,y,x] = y[p][co] + bias[co] + x_nchw[b,co,y,x]. */
+int pht_tail_finish(const float* y, int32_t ldy, const float* bias, const float* x_nchw, float* out_nchw, int32_t B,
+                    int32_t H, int32_t W, void* stream);
+/* Backward side: a[p][t*3+co] = dout[p - tap_t][co] (bf16 [B*H*W][64], columns 27..63 zero) so that
+ * d(decoder.1 output) = a @ Wt and d(decoder.2 weight) = h^T a are plain GEMMs; dbias[co] = sum_p dout[p][co]. */
+int pht_tail_im2col_bwd(const float* dout_nchw, void* a_bf16, float* dbias, int32_t B, int32_t H, int32_t W, void* stream);
+
 /* dtype conversion of a contiguous array (fp32 <-> bf16), n elements. */
 int pht_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream);
 /* same for a rows x cols matrix with leading dimensions (elements) src_ld / dst_ld */

@@ -85,6 +85,10 @@ SYMBOLS = {
     "pht_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "pht_pack_weight": (C.c_int, [C.POINTER(PackArgs), _vp]),
     "pht_unpack_wgrad": (C.c_int, [C.POINTER(PackArgs), _vp]),
+    "pht_pack_table_bytes": (_sz, [_i32]),
+    "pht_pack_weights_batched": (C.c_int, [C.POINTER(PackArgs), _i32, _vp, _sz, _i32, _vp]),
+    "pht_tail_finish": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "pht_tail_im2col_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pht_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "pht_cast2d": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
     "pht_sample_patches": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

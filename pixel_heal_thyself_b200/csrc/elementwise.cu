@@ -3,6 +3,8 @@
 // All are vectorised (16-byte accesses along the channel dim), coalesced and
 // use warp-shuffle reductions; grids are sized in multiples of the SM count
 // where a grid-stride loop is used.
+#include <vector>
+
 #include "common.cuh"
 
 namespace pht {
@@ -456,6 +458,84 @@ __global__ void unpack_wgrad_kernel(float* __restrict__ wg, const float* __restr
   }
 }
 
+// all weight (re)packs of a step in ONE launch: blockIdx.y selects the descriptor (table lives in device memory)
+struct PackJob {
+  const float* w;
+  void* dst;
+  PackP p;
+  int dtype;
+  int pad_;
+};
+__global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  const PackP a = j.p;
+  long long total = (long long)a.O * a.I * a.ks * a.ks;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int kx = (int)(idx % a.ks);
+    long long r = idx / a.ks;
+    int ky = (int)(r % a.ks); r /= a.ks;
+    int i = (int)(r % a.I);
+    int o = (int)(r / a.I);
+    if (i < a.i_begin || i >= a.i_begin + a.i_count) continue;
+    const float v = j.w[idx] * a.scale;
+    const long long di = packed_index(a, o, i - a.i_begin, ky, kx);
+    if (j.dtype == PHT_F32) ((float*)j.dst)[di] = v;
+    else ((bf16*)j.dst)[di] = __float2bfloat16_rn(v);
+  }
+}
+
+// decoder tail on the GEMM path: out = y[..., 0:3] + bias + x  (y = fp32 [B,H,W,64] conv result, NHWC -> NCHW)
+__global__ void tail_finish_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ bias,
+                                   const float* __restrict__ x, float* __restrict__ out, int B, int H, int W) {
+  long long total = (long long)B * 3 * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int px = (int)(i % W);
+    long long r = i / W;
+    int py = (int)(r % H); r /= H;
+    int co = (int)(r % 3);
+    int b = (int)(r / 3);
+    out[i] = y[(((long long)b * H + py) * W + px) * ldy + co] + bias[co] + x[i];
+  }
+}
+// a[p][t*3+co] = dout[p - tap_t][co] (zero outside the image), columns 27..63 zero; dbias[co] = sum_p dout[p][co]
+__global__ void tail_im2col_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ a, float* __restrict__ dbias, int B,
+                                       int H, int W) {
+  __shared__ float sb[3];
+  if (threadIdx.x < 3) sb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long npx = (long long)B * H * W;
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npx * 8; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);          // 8-column group of the 64-wide row
+    const long long p = i >> 3;
+    const int px = (int)(p % W);
+    long long r = p / W;
+    const int py = (int)(r % H), b = (int)(r / H);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = g * 8 + j;
+      v[j] = 0.f;
+      if (col < 27) {
+        const int t = col / 3, co = col % 3;
+        const int yy = py - (t / 3 - 1), xx = px - (t % 3 - 1);
+        if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) v[j] = dout[(((long long)b * 3 + co) * H + yy) * W + xx];
+      }
+    }
+    if (g == 1) {  // columns 12..14 are the centre tap (t = 4): dout[p][0..2]
+      acc[0] += v[4]; acc[1] += v[5]; acc[2] += v[6];
+    }
+    Vec<bf16>::st(a + p * 64 + g * 8, v);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s = warp_sum(acc[c]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sb[c], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) atomicAdd(dbias + threadIdx.x, sb[threadIdx.x]);
+}
+
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ s, long long sld, D* __restrict__ d, long long dld, long long rows,
                             long long cols) {
@@ -688,6 +768,55 @@ int pht_pack_weight(const pht_pack_args* a, void* stream) {
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
+size_t pht_pack_table_bytes(int32_t n) { return (size_t)(n > 0 ? n : 0) * sizeof(PackJob); }
+
+int pht_pack_weights_batched(const pht_pack_args* jobs, int32_t n, void* table_dev, size_t table_bytes, int32_t upload,
+                             void* stream) {
+  PHT_CHECK_ARG(jobs && n > 0 && table_dev && table_bytes >= pht_pack_table_bytes(n), "pack_batched: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long max_total = 0;
+  static thread_local std::vector<PackJob> host;
+  host.resize(n);
+  for (int i = 0; i < n; ++i) {
+    PackP p;
+    int rc = check_pack(&jobs[i], &p);
+    if (rc) return rc;
+    PHT_CHECK_ARG(jobs[i].dtype == PHT_F32 || jobs[i].dtype == PHT_BF16, "pack_batched: bad dtype");
+    host[i].w = jobs[i].w; host[i].dst = jobs[i].packed; host[i].p = p; host[i].dtype = jobs[i].dtype; host[i].pad_ = 0;
+    long long total = (long long)p.O * p.I * p.ks * p.ks;
+    if (total > max_total) max_total = total;
+  }
+  if (upload) PHT_CUDA(cudaMemcpyAsync(table_dev, host.data(), (size_t)n * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+  int gx = (int)((max_total + 255) / 256);
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, n);
+  pack_weights_batched_kernel<<<grid, 256, 0, st>>>((const PackJob*)table_dev);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_tail_finish(const float* y, int32_t ldy, const float* bias, const float* x_nchw, float* out_nchw, int32_t B, int32_t H,
+                    int32_t W, void* stream) {
+  PHT_CHECK_ARG(y && bias && x_nchw && out_nchw && ldy >= 3, "tail_finish: bad args");
+  long long n = (long long)B * 3 * H * W;
+  tail_finish_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, bias, x_nchw, out_nchw, B, H, W);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_tail_im2col_bwd(const float* dout_nchw, void* a_bf16, float* dbias, int32_t B, int32_t H, int32_t W, void* stream) {
+  PHT_CHECK_ARG(dout_nchw && a_bf16 && dbias, "tail_im2col_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  PHT_CUDA(cudaMemsetAsync(dbias, 0, 3 * sizeof(float), st));
+  long long n = (long long)B * H * W * 8;
+  tail_im2col_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dout_nchw, (bf16*)a_bf16, dbias, B, H, W);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
 int pht_unpack_wgrad(const pht_pack_args* a, void* stream) {
   PackP p;
   int rc = check_pack(a, &p);

@@ -11,8 +11,9 @@
 //               TMEM accumulator buffers (2 x BN fp32 columns), tcgen05.commit releases the smem stage / publishes the
 //               accumulator.
 //   warps 2..5  epilogue: tcgen05.ld the accumulator (each thread owns one output pixel = one TMEM lane), fused
-//               bias / residual / (leaky)ReLU / activation-derivative mask, bf16 pack, 16-byte stores.  Runs
-//               concurrently with the MMAs of the next tile (double-buffered TMEM).
+//               bias / residual / (leaky)ReLU / activation-derivative mask, bf16 pack into a 128B-swizzled staging
+//               tile [128 px][64 ch] and one TMA tensor store per 64-channel chunk (full-line writes, ragged tiles
+//               clipped by the tensor map).  Runs concurrently with the MMAs of the next tile (double-buffered TMEM).
 #include "tc_common.cuh"
 
 namespace pht {
@@ -23,6 +24,7 @@ constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;  // 128 output 
 constexpr int BK = 64;                                            // bf16 elements per 128-byte swizzle row
 constexpr int TC_THREADS = 192;
 constexpr int MAX_VEC_N = 1024;
+constexpr int STG_BYTES = TILE_M * 128;  // epilogue staging tile: 128 pixels x 64 bf16
 
 struct TcGemmP {
   int B, Ho, Wo, N, ks, n_src;
@@ -33,6 +35,7 @@ struct TcGemmP {
   const float* slope;
   const float* mslope;
   View resid, mask, out1, out2;
+  int out1_f32;  // out1 is fp32 (direct stores; used by the 64-wide decoder-tail GEMM only)
 };
 
 template <int BN> struct TcCfg {
@@ -41,7 +44,7 @@ template <int BN> struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN == 256 ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // power of two for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 3 * MAX_VEC_N * 4 + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 3 * MAX_VEC_N * 4 + 256 + 1024;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -64,13 +67,15 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW, const TcGemmP P) {
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const TcGemmP P) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stage bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* s_bias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // 1024-aligned (stage sizes are multiples of 1024)
+  float* s_bias = reinterpret_cast<float*>(stg + STG_BYTES);
   float* s_slope = s_bias + MAX_VEC_N;
   float* s_mslope = s_slope + MAX_VEC_N;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_mslope + MAX_VEC_N);
@@ -174,11 +179,29 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // accumulator row == pixel index inside the tile
     const int py = row / TILE_W, px = row % TILE_W;
+    const bool issuer = (warp == 2 && lane == 0);
+    uint8_t* srow = stg + row * 128;
+    auto stage_and_store = [&](const float* v, const CUtensorMap* tm, int c_glob, int x0, int y0, int b) {
+      // staging tile free? (the previous TMA store has finished READING it)
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) * 16)) = pack8(v + g * 8);
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(stg)), "r"(c_glob), "r"(x0), "r"(y0), "r"(b)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
       const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
-      const int x = tx * TILE_W + px, y = ty * TILE_H + py, n0 = nt * BN;
+      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+      const int x = x0 + px, y = y0 + py, n0 = nt * BN;
       const bool valid = x < P.Wo && y < P.Ho;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -187,58 +210,79 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
       const bf16* rp = nullptr;
       const bf16* mp = nullptr;
-      bf16* o1 = nullptr;
-      bf16* o2 = nullptr;
       if (valid) {
         if (P.flags & (PHT_EPI_RESID_PRE | PHT_EPI_RESID_POST))
           rp = (const bf16*)P.resid.ptr + view_off(P.resid, b, y + P.resid.oy, x + P.resid.ox) + n0;
         if (P.flags & PHT_EPI_MASK) mp = (const bf16*)P.mask.ptr + view_off(P.mask, b, y + P.mask.oy, x + P.mask.ox) + n0;
-        if (P.out1.ptr) o1 = (bf16*)P.out1.ptr + view_off(P.out1, b, y + P.out1.oy, x + P.out1.ox) + n0;
-        if (P.out2.ptr) o2 = (bf16*)P.out2.ptr + view_off(P.out2, b, y + P.out2.oy, x + P.out2.ox) + n0;
       }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_addr + c0, r);   // warp-collective: executed by all lanes, valid or not
-        tmem_ld_wait();
-        if (valid) {
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        float v[64];
+        {
+          uint32_t r[32];
+          tmem_ld32(t_addr + c0, r);       // warp-collective: executed by all lanes, valid or not
+          tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float v[8], rs[8];
-            const int c = c0 + g * 8;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          tmem_ld32(t_addr + c0 + 32, r);
+          tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]) + s_bias[n0 + c + j];
-            if (rp) {
-              unpack8(*reinterpret_cast<const uint4*>(rp + c), rs);
-              if (P.flags & PHT_EPI_RESID_PRE) {
+          for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r[j]);
+        }
+        if (c0 + 64 >= BN) {               // accumulator fully in registers: release it to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+        }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += rs[j];
-              }
-            }
-            if (P.slope) {
+        for (int j = 0; j < 64; ++j) v[j] += s_bias[n0 + c0 + j];
+        if (rp && (P.flags & PHT_EPI_RESID_PRE)) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * s_slope[n0 + c + j];
-            }
-            if (o1) *reinterpret_cast<uint4*>(o1 + c) = pack8(v);
-            if (o2) {
-              if (P.flags & PHT_EPI_RESID_POST) {
+          for (int g = 0; g < 8; ++g) {
+            float rs[8];
+            unpack8(*reinterpret_cast<const uint4*>(rp + c0 + g * 8), rs);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += rs[j];
-              }
-              if (mp) {
-                float mk[8];
-                unpack8(*reinterpret_cast<const uint4*>(mp + c), mk);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] *= (mk[j] > 0.f ? 1.f : s_mslope[n0 + c + j]);
-              }
-              *reinterpret_cast<uint4*>(o2 + c) = pack8(v);
-            }
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += rs[j];
           }
         }
+        if (P.slope) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * s_slope[n0 + c0 + j];
+        }
+        if (P.out1.ptr) {
+          if (P.out1_f32) {
+            if (valid) {
+              float* o = (float*)P.out1.ptr + view_off(P.out1, b, y + P.out1.oy, x + P.out1.ox) + n0 + c0;
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          } else {
+            stage_and_store(v, &tmO1, n0 + c0, x0 + P.out1.ox, y0 + P.out1.oy, b);
+          }
+        }
+        if (P.out2.ptr) {
+          if (rp && (P.flags & PHT_EPI_RESID_POST)) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float rs[8];
+              unpack8(*reinterpret_cast<const uint4*>(rp + c0 + g * 8), rs);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += rs[j];
+            }
+          }
+          if (mp) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              float mk[8];
+              unpack8(*reinterpret_cast<const uint4*>(mp + c0 + g * 8), mk);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] *= (mk[j] > 0.f ? 1.f : s_mslope[n0 + c0 + g * 8 + j]);
+            }
+          }
+          stage_and_store(v, &tmO2, n0 + c0, x0 + P.out2.ox, y0 + P.out2.oy, b);
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);  // 128 arrivals release the accumulator buffer
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all tensor stores complete before exit
   }
 
   tc_fence_before();
@@ -316,7 +360,7 @@ static int make_src_tmap(CUtensorMap* tm, const pht_view& v, int B) {
 
 template <int BN>
 static int launch_tc(const pht_conv_gemm_args* a, const TcGemmP& P, const CUtensorMap* tmA, const CUtensorMap& tmW,
-                     cudaStream_t st) {
+                     const CUtensorMap* tmO, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -327,7 +371,7 @@ static int launch_tc(const pht_conv_gemm_args* a, const TcGemmP& P, const CUtens
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
-  conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA[0], tmA[1], tmA[2], tmW, P);
+  conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA[0], tmA[1], tmA[2], tmW, tmO[0], tmO[1], P);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
@@ -344,8 +388,13 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   }
   if ((a->flags & (PHT_EPI_RESID_PRE | PHT_EPI_RESID_POST)) && !view_vec8_ok(a->resid)) return PHT_OK;
   if ((a->flags & PHT_EPI_MASK) && !view_vec8_ok(a->mask)) return PHT_OK;
-  if (a->out1.ptr && !view_vec8_ok(a->out1)) return PHT_OK;
-  if (a->out2.ptr && !view_vec8_ok(a->out2)) return PHT_OK;
+  const bool out1_f32 = a->out1.ptr && a->out1.dtype == PHT_F32;
+  if (out1_f32) {
+    if (((uintptr_t)a->out1.ptr & 15) || a->out1.sx % 4 || a->out1.sy % 4 || a->out1.sb % 4) return PHT_OK;
+  } else if (a->out1.ptr && (!view_tma_ok(a->out1) || a->out1.C < a->N)) {
+    return PHT_OK;
+  }
+  if (a->out2.ptr && (!view_tma_ok(a->out2) || a->out2.C < a->N)) return PHT_OK;
   if (((uintptr_t)a->w & 15) != 0) return PHT_OK;
   if (!get_encode_fn()) return PHT_OK;
 
@@ -381,10 +430,21 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   P.mask = (a->flags & PHT_EPI_MASK) ? make_view(a->mask) : null_view();
   P.out1 = a->out1.ptr ? make_view(a->out1) : null_view();
   P.out2 = a->out2.ptr ? make_view(a->out2) : null_view();
+  P.out1_f32 = out1_f32 ? 1 : 0;
+  CUtensorMap tmO[2];
+  tmO[0] = tmO[1] = tmW;
+  if (a->out1.ptr && !out1_f32) {
+    int rc1 = make_src_tmap(&tmO[0], a->out1, a->B);
+    if (rc1) return rc1;
+  }
+  if (a->out2.ptr) {
+    int rc2 = make_src_tmap(&tmO[1], a->out2, a->B);
+    if (rc2) return rc2;
+  }
   int rc;
-  if (BN == 256) rc = launch_tc<256>(a, P, tmA, tmW, st);
-  else if (BN == 128) rc = launch_tc<128>(a, P, tmA, tmW, st);
-  else rc = launch_tc<64>(a, P, tmA, tmW, st);
+  if (BN == 256) rc = launch_tc<256>(a, P, tmA, tmW, tmO, st);
+  else if (BN == 128) rc = launch_tc<128>(a, P, tmA, tmW, tmO, st);
+  else rc = launch_tc<64>(a, P, tmA, tmW, tmO, st);
   if (rc) return rc;
   count_launch(CNT_GEMM_TC);
   *handled = true;

@@ -237,6 +237,55 @@ def pack_weight(w, packed, **kw):
     L.check(lib.pht_pack_weight(C.byref(a), L.stream_ptr()), "pht_pack_weight")
 
 
+class PackPlan:
+    """A cached batch of weight-pack descriptors executed by ONE kernel launch (pht_pack_weights_batched)."""
+
+    def __init__(self):
+        self.jobs = []          # (w, packed, kwargs)
+        self._arr = None
+        self._table = None
+        self._sig = None
+
+    def add(self, w, packed, **kw):
+        self.jobs.append((w, packed, kw))
+
+    def run(self):
+        if not self.jobs:
+            return
+        sig = tuple((w.data_ptr(), p.data_ptr(), p.dtype) for w, p, _ in self.jobs)
+        upload = 0
+        if sig != self._sig:
+            n = len(self.jobs)
+            arr = (L.PackArgs * n)()
+            for i, (w, p, kw) in enumerate(self.jobs):
+                L.require_cuda(w, p)
+                assert w.is_contiguous() and w.dtype == torch.float32
+                arr[i] = _pack_args(w, p, **kw)
+            nbytes = int(lib.pht_pack_table_bytes(n))
+            self._table = torch.empty(nbytes, dtype=torch.uint8, device=self.jobs[0][0].device)
+            self._arr, self._sig, upload = arr, sig, 1
+        L.check(lib.pht_pack_weights_batched(self._arr, len(self.jobs), self._table.data_ptr(), self._table.numel(), upload,
+                                             L.stream_ptr()), "pht_pack_weights_batched")
+
+
+def tail_finish(y, bias, x_nchw, out_nchw):
+    """y fp32 [B,H,W,ldy] (channels 0..2 = conv result) -> out_nchw = y[..., :3] + bias + x_nchw."""
+    L.require_cuda(y, bias, x_nchw, out_nchw)
+    B, H, W, ldy = y.shape
+    assert y.is_contiguous() and y.dtype == torch.float32
+    L.check(lib.pht_tail_finish(y.data_ptr(), ldy, bias.data_ptr(), x_nchw.data_ptr(), out_nchw.data_ptr(), B, H, W,
+                                L.stream_ptr()), "pht_tail_finish")
+
+
+def tail_im2col_bwd(dout_nchw, a, dbias):
+    """dout fp32 [B,3,H,W] -> a bf16 [B,H,W,64] (27 shifted copies), dbias fp32 [3]."""
+    L.require_cuda(dout_nchw, a, dbias)
+    B, _, H, W = dout_nchw.shape
+    assert a.is_contiguous() and a.dtype == torch.bfloat16 and a.shape[-1] == 64
+    L.check(lib.pht_tail_im2col_bwd(dout_nchw.data_ptr(), a.data_ptr(), dbias.data_ptr(), B, H, W, L.stream_ptr()),
+            "pht_tail_im2col_bwd")
+
+
 def unpack_wgrad(w_grad, packed, **kw):
     L.require_cuda(w_grad, packed)
     assert w_grad.is_contiguous() and w_grad.dtype == torch.float32 and packed.dtype == torch.float32
