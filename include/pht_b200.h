@@ -222,6 +222,8 @@ int pht_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
  * kernels' [tap][N][K] layout.
  *   pack:    dst[t][n_off+o][k_off+i] = scale * w[o][i][ky][kx]   (transpose=0)
  *            dst[t'][n_off+i][k_off+o] = scale * w[o][i][ky][kx], t' = flipped tap (transpose=1, dgrad)
+ *            dst[n_off+i][k_off + t*O + o] = scale * w[o][i][ky][kx]  (transpose=2: taps x outputs folded into K,
+ *                                             no flip; the decoder tail's data-/weight-gradient GEMMs)
  *   embed:   the ksize x ksize kernel is centred inside a `grid` x `grid` tap
  *            grid whose taps are folded into K (used for the im2col5 encoders):
  *            dst[n_off+o][((ky+e)*grid + kx+e)*I + i], e = (grid-ksize)/2.

@@ -429,6 +429,7 @@ __device__ __forceinline__ long long packed_index(const PackP& a, int o, int i, 
     return (long long)(a.n_off + o) * a.Ktot + k;
   }
   int t = ky * a.ks + kx, T = a.ks * a.ks;
+  if (a.transpose == 2) return (long long)(a.n_off + i) * a.Ktot + a.k_off + t * a.O + o;  // taps x outputs folded into K
   if (!a.transpose) return ((long long)t * a.Ntot + a.n_off + o) * a.Ktot + a.k_off + i;
   return ((long long)(T - 1 - t) * a.Ntot + a.n_off + i) * a.Ktot + a.k_off + o;
 }
@@ -750,6 +751,8 @@ static int check_pack(const pht_pack_args* a, PackP* p) {
   if (a->grid > 0) {
     PHT_CHECK_ARG(a->grid >= a->ksize && !a->transpose, "pack: bad embed");
     PHT_CHECK_ARG(a->k_off + a->grid * a->grid * Ic <= a->Ktot && a->n_off + a->O <= a->Ntot, "pack: embed out of range");
+  } else if (a->transpose == 2) {
+    PHT_CHECK_ARG(a->n_off + Ic <= a->Ntot && a->k_off + a->ksize * a->ksize * a->O <= a->Ktot, "pack: out of range (T2)");
   } else if (!a->transpose) {
     PHT_CHECK_ARG(a->n_off + a->O <= a->Ntot && a->k_off + Ic <= a->Ktot, "pack: out of range");
   } else {
@@ -821,7 +824,6 @@ int pht_unpack_wgrad(const pht_pack_args* a, void* stream) {
   PackP p;
   int rc = check_pack(a, &p);
   if (rc) return rc;
-  PHT_CHECK_ARG(!a->transpose, "unpack: transpose unsupported");
   long long total = (long long)p.O * p.I * p.ks * p.ks;
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((float*)a->w, (const float*)a->packed, p);
   count_launch(CNT_OTHER);

@@ -226,7 +226,8 @@ static WgPlan wg_plan(const pht_wgrad_args* a, size_t ws_limit_bytes) {
   p.ptiles_total = a->B * p.ptiles_x * p.ptiles_y;
   int base_jobs = p.T * p.n_ntiles * p.n_ktiles;
   int sms = sm_count();
-  int splits = (sms + base_jobs - 1) / base_jobs;
+  // one CTA per SM (192 KB of smem): never spill a few jobs into a second wave
+  int splits = base_jobs >= sms ? 1 : sms / base_jobs;
   if (splits > p.ptiles_total) splits = p.ptiles_total;
   size_t per_split_bytes = (size_t)p.T * a->N * p.Ktot * sizeof(float);
   if (ws_limit_bytes > 0) {

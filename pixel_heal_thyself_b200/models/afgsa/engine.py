@@ -57,6 +57,7 @@ class AfgsaEngine:
         self._packed: dict[str, torch.Tensor] = {}
         self._consts: dict[str, torch.Tensor] = {}
         self._packed_key = None
+        self._pack_plans = {}
         self._saved_gen = {}
         self._gen = 0
         # data-parallel hook: called with "decoder" / "block<i>" / "encoders" as soon as that group's
@@ -102,17 +103,35 @@ class AfgsaEngine:
     # ------------------------------------------------------------------ weights
     def pack_weights(self, backward: bool):
         """(Re)pack the fp32 OIHW master weights into the kernels' [tap][N][K]
-        layout (and the flipped/transposed copies the data-gradients use)."""
+        layout (and the flipped/transposed copies the data-gradients use): every
+        pack of the step is one descriptor of ONE batched launch."""
+        key = (backward, self.dtype, str(self.device), self.net.flat_param.data_ptr())
+        plan = self._pack_plans.get(key)
+        if plan is None:
+            plan = self._pack_plans[key] = self._build_pack_plan(backward)
+        plan.run()
+
+    def _pk32(self, name, shape):
+        t = self._packed.get(name)
+        if t is None or t.dtype != torch.float32 or t.device != self.device or tuple(t.shape) != tuple(shape):
+            t = self._packed[name] = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        return t
+
+    def _build_pack_plan(self, backward: bool):
         net, C = self.net, self.C
         P = dict(net.named_parameters())
-        pw = ops.pack_weight
-        # encoders: 1x1 / 3x3 / 5x5 kernels embedded in the 5x5 im2col K axis
+        plan = ops.PackPlan()
+        pw = plan.add
+        tc_tail = self.dtype == torch.bfloat16
+        # encoders: 1x1 / 3x3 / 5x5 kernels embedded in the 5x5 im2col K axis; biases concatenated to [768]
         for tag, names, cin in (("encN", ("conv1", "conv3", "conv5"), net.input_channels),
                                 ("encA", ("conv_a1", "conv_a3", "conv_a5"), net.aux_input_channels)):
             kpad = ENC_KPAD.get(cin, ((25 * cin + 63) // 64) * 64)
             wp = self._pk(tag, (1, 768, kpad))
+            bp = self._pk32(tag + ".bias", (768,))
             for j, (nm, ks) in enumerate(zip(names, (1, 3, 5))):
                 pw(P[f"{nm}.0.weight"], wp, ksize=ks, Ntot=768, Ktot=kpad, n_off=256 * j, grid=5)
+                pw(P[f"{nm}.0.bias"].view(256, 1), bp, ksize=1, Ntot=768, Ktot=1, n_off=256 * j)
         for nm, I in (("conv_map", 768), ("conv_aenc1", 768), ("conv_aenc2", C)):
             pw(P[f"{nm}.0.weight"], self._pk(nm, (1, C, I)), ksize=1, Ntot=C, Ktot=I)
             if backward:
@@ -144,10 +163,17 @@ class AfgsaEngine:
             pw(w, self._pk(f"dec{j}", (9, C, C)), ksize=3, Ntot=C, Ktot=C)
             if backward:
                 pw(w, self._pk(f"dec{j}.T", (9, C, C)), ksize=3, Ntot=C, Ktot=C, transpose=1)
-        # decoder tail weights stay fp32: [3][9][C]
-        self._packed["dec2"] = P["decoder.2.0.weight"].detach().permute(0, 2, 3, 1).reshape(3, 9, C).contiguous()
-        self._packed["encN.bias"] = torch.cat([P[f"{n}.0.bias"].detach() for n in ("conv1", "conv3", "conv5")])
-        self._packed["encA.bias"] = torch.cat([P[f"{n}.0.bias"].detach() for n in ("conv_a1", "conv_a3", "conv_a5")])
+        w2 = P["decoder.2.0.weight"]
+        if tc_tail:
+            # decoder tail on the tensor cores: 3 output channels padded to a 64-wide N tile (rows 3..63 stay zero);
+            # backward operand [C][27 -> 64]: k = tap*3 + co
+            pw(w2, self._pk("dec2g", (9, 64, C)), ksize=3, Ntot=64, Ktot=C)
+            if backward:
+                pw(w2, self._pk("dec2g.T", (1, C, 64)), ksize=3, Ntot=C, Ktot=64, transpose=2)
+        else:
+            # fp32 parity path: CUDA-core tail kernels read [3][9][C] = dst[co][t*C + c]
+            pw(w2, self._pk32("dec2", (3, 9, C)), ksize=3, Ntot=3, Ktot=9 * C, grid=3)
+        return plan
 
     def _maybe_pack(self, backward: bool):
         key = (self.net.weights_version(), backward or (self._packed_key is not None and self._packed_key[1]),
@@ -227,7 +253,13 @@ class AfgsaEngine:
         ops.conv_gemm([D1p], pk["dec1"], C, ksize=3, src_offsets=[(1, 1)], bias=P["decoder.1.0.bias"], slope=relu,
                       out1=D2)
         out = torch.empty_like(x)
-        ops.dec_tail_fwd(D2, pk["dec2"], P["decoder.2.0.bias"], x, out)
+        if T == torch.bfloat16:
+            # 256->3 zero-padded conv as a 64-wide tensor-core GEMM (TMA zero-fills the border), then bias+residual+NCHW
+            Y = g("tailY", (B, H, W, 64), torch.float32)
+            ops.conv_gemm([D2], pk["dec2g"], 64, ksize=3, out1=Y)
+            ops.tail_finish(Y, P["decoder.2.0.bias"], x, out)
+        else:
+            ops.dec_tail_fwd(D2, pk["dec2"], P["decoder.2.0.bias"], x, out)
         if save:
             self._gen += 1
             self._saved_gen[(B, H, W)] = self._gen
@@ -277,10 +309,18 @@ class AfgsaEngine:
 
         # ---- decoder -------------------------------------------------------------------------
         D1p, D2 = g("D1p", (B, H + 2, W + 2, C), T), g("D2", (B, H, W, C), T)
-        dw2 = wtmp[: 27 * C].view(3, 9, C)
-        ops.dec_tail_bwd_weight(d_out, D2, dw2, G["decoder.2.0.bias"], tail_ws)
-        G["decoder.2.0.weight"].copy_(dw2.view(3, 3, 3, C).permute(0, 3, 1, 2))
-        ops.dec_tail_bwd_data(d_out, pk["dec2"], D2, G0)                       # G0 = d(D2 pre-act)
+        if T == torch.bfloat16:
+            tailA = g("tailA", (B, H, W, 64), T)               # a[p][t*3+co] = d_out[p - tap_t][co]
+            ops.tail_im2col_bwd(d_out, tailA, G["decoder.2.0.bias"])
+            dw2 = wtmp[: 64 * C].view(1, C, 64)                # dw2[c][t*3+co] = sum_p D2[p][c] a[p][t*3+co]
+            ops.wgrad(D2, [tailA], dw2, workspace=wg_ws)
+            ops.unpack_wgrad(G["decoder.2.0.weight"], dw2, ksize=3, Ntot=C, Ktot=64, transpose=2)
+            ops.conv_gemm([tailA], pk["dec2g.T"], C, mask=D2, mslope=relu0, out2=G0)   # G0 = d(D2 pre-act)
+        else:
+            dw2 = wtmp[: 27 * C].view(3, 9, C)
+            ops.dec_tail_bwd_weight(d_out, D2, dw2, G["decoder.2.0.bias"], tail_ws)
+            ops.unpack_wgrad(G["decoder.2.0.weight"], dw2, ksize=3, Ntot=3, Ktot=9 * C, grid=3)
+            ops.dec_tail_bwd_data(d_out, pk["dec2"], D2, G0)                       # G0 = d(D2 pre-act)
         self._dbg("dD2pre", G0); self._dbg("d_out", d_out); self._dbg("D2", D2); self._dbg("D1", D1p)
         conv3_wgrad(G0, D1p, "decoder.1.0")
         conv3_dgrad(G0, pk["dec1.T"])
@@ -366,4 +406,4 @@ class AfgsaEngine:
         ops.wgrad(dcat, [col], w, dbias=btmp, workspace=wg_ws)
         for j, (nm, ks) in enumerate(zip(names, (1, 3, 5))):
             ops.unpack_wgrad(G[f"{nm}.0.weight"], w, ksize=ks, Ntot=768, Ktot=kpad, n_off=256 * j, grid=5)
-            G[f"{nm}.0.bias"].copy_(btmp[256 * j: 256 * (j + 1)])
+            ops.unpack_wgrad(G[f"{nm}.0.bias"].view(256, 1), btmp, ksize=1, Ntot=768, Ktot=1, n_off=256 * j)
