@@ -287,6 +287,8 @@ void pht_get_counters(uint64_t* counters8);
 void pht_reset_counters(void);
 /* 1 = never use tcgen05 paths (debug / A-B testing) */
 void pht_set_force_simple(int on);
+/* tuning / A-B knobs: "tc_cfg" = 0 auto, 1 prefer the deep-ring conv_gemm config, 2 force the wide-epilogue one */
+int pht_set_option(const char* name, int value);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,7 @@ SYMBOLS = {
     "pht_get_counters": (None, [C.POINTER(C.c_uint64)]),
     "pht_reset_counters": (None, []),
     "pht_set_force_simple": (None, [C.c_int]),
+    "pht_set_option": (C.c_int, [C.c_char_p, C.c_int]),
 }
 
 
@@ -116,6 +117,12 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
+
+# A/B tuning knobs from the environment, e.g. PHT_OPTIONS="tc_cfg=1" (see pht_set_option in include/pht_b200.h)
+for _kv in filter(None, os.environ.get("PHT_OPTIONS", "").split(",")):
+    _k, _v = _kv.split("=")
+    if lib.pht_set_option(_k.strip().encode(), int(_v)) != 0:
+        raise ValueError(f"PHT_OPTIONS: unknown option {_k!r}")
 
 
 def check(rc: int, what: str) -> None:

@@ -14,6 +14,8 @@
 //               bias / residual / (leaky)ReLU / activation-derivative mask, bf16 pack into a 128B-swizzled staging
 //               tile [128 px][64 ch] and one TMA tensor store per 64-channel chunk (full-line writes, ragged tiles
 //               clipped by the tensor map).  Runs concurrently with the MMAs of the next tile (double-buffered TMEM).
+#include <atomic>
+
 #include "tc_common.cuh"
 
 namespace pht {
@@ -22,9 +24,9 @@ using namespace tc;
 
 constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;  // 128 output pixels per tile
 constexpr int BK = 64;                                            // bf16 elements per 128-byte swizzle row
-constexpr int TC_THREADS = 192;
-constexpr int MAX_VEC_N = 1024;
-constexpr int STG_BYTES = TILE_M * 128;  // epilogue staging tile: 128 pixels x 64 bf16
+constexpr int TC_THREADS = 224;                                   // 7 warps: TMA, MMA, 4 x epilogue, aux TMA
+constexpr int MAX_VEC_N = 768;
+constexpr int STG_BYTES = TILE_M * 128;  // one epilogue tile: 128 pixels x 64 bf16, 128B-swizzled rows
 
 struct TcGemmP {
   int B, Ho, Wo, N, ks, n_src;
@@ -34,17 +36,24 @@ struct TcGemmP {
   const float* bias;
   const float* slope;
   const float* mslope;
-  View resid, mask, out1, out2;
-  int out1_f32;  // out1 is fp32 (direct stores; used by the 64-wide decoder-tail GEMM only)
+  View out1;          // only used when out1_f32
+  int has_out1, has_out2, has_resid, has_mask;
+  int out1_f32;       // out1 is fp32 (direct stores; used by the 64-wide decoder-tail GEMM only)
+  int residOy, residOx, maskOy, maskOx, out1Oy, out1Ox, out2Oy, out2Ox;
 };
 
-template <int BN> struct TcCfg {
+// WIDE = false ("deep"): 4-stage operand ring, one output staging tile, no epilogue inputs: K-heavy 3x3 convolutions.
+// WIDE = true  ("wide"): 3-stage ring, two output staging tiles and a 2-slot ring of TMA-prefetched epilogue input
+//                        tiles (residual / activation mask): the HBM-bound 1x1 GEMMs and every fused epilogue.
+template <int BN, bool WIDE> struct TcCfg {
   static constexpr int A_BYTES = TILE_M * BK * 2;                  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;                      // 32 KB @ BN=256
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = BN == 256 ? (WIDE ? 3 : 4) : (BN == 128 ? 4 : 6);
+  static constexpr int NSTG = WIDE ? 2 : 1;
+  static constexpr int AUX_SLOTS = WIDE ? 2 : 0;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // power of two for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 3 * MAX_VEC_N * 4 + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (NSTG + AUX_SLOTS) * STG_BYTES + 3 * MAX_VEC_N * 4 + 256 + 1024;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -63,19 +72,28 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return u;
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 
-template <int BN>
+template <int BN, bool WIDE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const TcGemmP P) {
-  using Cfg = TcCfg<BN>;
+                    const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmM, const TcGemmP P) {
+  using Cfg = TcCfg<BN, WIDE>;
+  constexpr int NCHUNK = BN / 64;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stage bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint8_t* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // 1024-aligned (stage sizes are multiples of 1024)
-  float* s_bias = reinterpret_cast<float*>(stg + STG_BYTES);
+  uint8_t* aux = stg + Cfg::NSTG * STG_BYTES;
+  float* s_bias = reinterpret_cast<float*>(aux + Cfg::AUX_SLOTS * STG_BYTES);
   float* s_slope = s_bias + MAX_VEC_N;
   float* s_mslope = s_slope + MAX_VEC_N;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_mslope + MAX_VEC_N);
@@ -83,7 +101,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* empty_bar = bars + Cfg::STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* afull_bar = tempty_bar + 2;           // [2] epilogue-input slot filled (TMA tx)
+  uint64_t* aempty_bar = afull_bar + 2;           // [2] epilogue-input slot consumed (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -104,6 +124,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 128);
+      mbar_init(&afull_bar[a], 1);
+      mbar_init(&aempty_bar[a], 128);
     }
     mbar_fence_init();
   }
@@ -114,6 +136,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const int T = P.ks * P.ks, half = P.ks / 2;
+  const int n_kinds = P.has_resid + P.has_mask;   // epilogue-input tiles per 64-channel chunk
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -174,27 +197,75 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
       }
     }
+  } else if (warp == 6) {
+    // ================================ epilogue-input TMA producer ================================
+    // streams the residual / mask tiles in exactly the order the epilogue consumes them:
+    // for tile: for 64-channel chunk: [resid], [mask]
+    if (WIDE && lane == 0 && n_kinds > 0) {
+      prefetch_tmap(&tmR);
+      prefetch_tmap(&tmM);
+      int j = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
+        const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * BN;
+        for (int c = 0; c < NCHUNK; ++c) {
+          for (int kind = P.has_resid ? 0 : 1; kind < (P.has_mask ? 2 : 1); ++kind, ++j) {
+            const int slot = j & 1;
+            mbar_wait(&aempty_bar[slot], ((j >> 1) & 1) ^ 1);
+            mbar_expect_tx(&afull_bar[slot], STG_BYTES);
+            if (kind == 0) tma_load_4d(aux + slot * STG_BYTES, &tmR, &afull_bar[slot], n0 + c * 64, x0 + P.residOx, y0 + P.residOy, b);
+            else tma_load_4d(aux + slot * STG_BYTES, &tmM, &afull_bar[slot], n0 + c * 64, x0 + P.maskOx, y0 + P.maskOy, b);
+          }
+        }
+      }
+    }
   } else {
     // ================================ epilogue (warps 2..5) ================================
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // accumulator row == pixel index inside the tile
     const int py = row / TILE_W, px = row % TILE_W;
     const bool issuer = (warp == 2 && lane == 0);
-    uint8_t* srow = stg + row * 128;
+    const int rsw = row & 7;
+    int n_store = 0;                       // output tiles stored so far (selects the staging buffer)
+    int j_aux = 0;                         // epilogue-input tiles consumed so far
     auto stage_and_store = [&](const float* v, const CUtensorMap* tm, int c_glob, int x0, int y0, int b) {
-      // staging tile free? (the previous TMA store has finished READING it)
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) * 16)) = pack8(v + g * 8);
-      fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (issuer) {
-        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                     ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(stg)), "r"(c_glob), "r"(x0), "r"(y0), "r"(b)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      uint8_t* buf = stg + (Cfg::NSTG == 2 ? (n_store & 1) : 0) * STG_BYTES;
+      if (Cfg::NSTG == 1) {
+        // single staging tile: wait until the previous TMA store has finished READING it
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      uint8_t* srow = buf + row * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(srow + ((g ^ rsw) * 16)) = pack8(v + g * 8);
+      fence_proxy_async();
+      // two staging tiles: the store issued one round ago read the OTHER tile; once it has finished reading, that
+      // tile is free for the next round (everyone learns it at the barrier below)
+      if (Cfg::NSTG == 2 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) tma_store_4d(tm, buf, c_glob, x0, y0, b);
+      ++n_store;
+    };
+    // v[64] (op)= the epilogue-input tile that is next in the stream; releases its slot
+    auto aux_apply = [&](float* v, int c_abs, bool is_mask) {
+      const int slot = j_aux & 1;
+      mbar_wait(&afull_bar[slot], (j_aux >> 1) & 1);
+      const uint8_t* arow = aux + slot * STG_BYTES + row * 128;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float t[8];
+        unpack8(*reinterpret_cast<const uint4*>(arow + ((g ^ rsw) * 16)), t);
+        if (is_mask) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[g * 8 + j] *= (t[j] > 0.f ? 1.f : s_mslope[c_abs + g * 8 + j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+        }
+      }
+      mbar_arrive(&aempty_bar[slot]);
+      ++j_aux;
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
@@ -208,13 +279,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      const bf16* rp = nullptr;
-      const bf16* mp = nullptr;
-      if (valid) {
-        if (P.flags & (PHT_EPI_RESID_PRE | PHT_EPI_RESID_POST))
-          rp = (const bf16*)P.resid.ptr + view_off(P.resid, b, y + P.resid.oy, x + P.resid.ox) + n0;
-        if (P.flags & PHT_EPI_MASK) mp = (const bf16*)P.mask.ptr + view_off(P.mask, b, y + P.mask.oy, x + P.mask.ox) + n0;
-      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 64) {
         float v[64];
@@ -235,20 +299,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] += s_bias[n0 + c0 + j];
-        if (rp && (P.flags & PHT_EPI_RESID_PRE)) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float rs[8];
-            unpack8(*reinterpret_cast<const uint4*>(rp + c0 + g * 8), rs);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] += rs[j];
-          }
-        }
+        if (WIDE && (P.flags & PHT_EPI_RESID_PRE)) aux_apply(v, n0 + c0, false);
         if (P.slope) {
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * s_slope[n0 + c0 + j];
         }
-        if (P.out1.ptr) {
+        if (P.has_out1) {
           if (P.out1_f32) {
             if (valid) {
               float* o = (float*)P.out1.ptr + view_off(P.out1, b, y + P.out1.oy, x + P.out1.ox) + n0 + c0;
@@ -256,29 +312,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               for (int j = 0; j < 64; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else {
-            stage_and_store(v, &tmO1, n0 + c0, x0 + P.out1.ox, y0 + P.out1.oy, b);
+            stage_and_store(v, &tmO1, n0 + c0, x0 + P.out1Ox, y0 + P.out1Oy, b);
           }
         }
-        if (P.out2.ptr) {
-          if (rp && (P.flags & PHT_EPI_RESID_POST)) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float rs[8];
-              unpack8(*reinterpret_cast<const uint4*>(rp + c0 + g * 8), rs);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] += rs[j];
-            }
-          }
-          if (mp) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float mk[8];
-              unpack8(*reinterpret_cast<const uint4*>(mp + c0 + g * 8), mk);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] *= (mk[j] > 0.f ? 1.f : s_mslope[n0 + c0 + g * 8 + j]);
-            }
-          }
-          stage_and_store(v, &tmO2, n0 + c0, x0 + P.out2.ox, y0 + P.out2.oy, b);
+        if (P.has_out2) {   // (the host clears RESID_POST / MASK when there is no out2)
+          if (WIDE && (P.flags & PHT_EPI_RESID_POST)) aux_apply(v, n0 + c0, false);
+          if (WIDE && (P.flags & PHT_EPI_MASK)) aux_apply(v, n0 + c0, true);
+          stage_and_store(v, &tmO2, n0 + c0, x0 + P.out2Ox, y0 + P.out2Oy, b);
         }
       }
     }
@@ -347,9 +387,6 @@ static bool view_tma_ok(const pht_view& v) {
   if (v.sx <= 0 || v.sy <= 0 || v.sb <= 0) return false;
   return true;
 }
-static bool view_vec8_ok(const pht_view& v) {
-  return v.ptr && v.dtype == PHT_BF16 && ((uintptr_t)v.ptr & 15) == 0 && v.sx % 8 == 0 && v.sy % 8 == 0 && v.sb % 8 == 0;
-}
 
 static int make_src_tmap(CUtensorMap* tm, const pht_view& v, int B) {
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)B};
@@ -358,23 +395,29 @@ static int make_src_tmap(CUtensorMap* tm, const pht_view& v, int B) {
   return make_tmap_bf16(tm, v.ptr, 4, dims, strides, box);
 }
 
-template <int BN>
-static int launch_tc(const pht_conv_gemm_args* a, const TcGemmP& P, const CUtensorMap* tmA, const CUtensorMap& tmW,
-                     const CUtensorMap* tmO, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+struct TcMaps {
+  CUtensorMap A[3], W, O[2], R, M;
+};
+
+template <int BN, bool WIDE>
+static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
+  using Cfg = TcCfg<BN, WIDE>;
   static bool attr_set = false;
   if (!attr_set) {
-    PHT_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PHT_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
-  conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA[0], tmA[1], tmA[2], tmW, tmO[0], tmO[1], P);
+  conv_gemm_tc_kernel<BN, WIDE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.A[0], m.A[1], m.A[2], m.W, m.O[0], m.O[1], m.R, m.M, P);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
+
+static std::atomic<int> g_tc_cfg{0};  // 0 = auto, 1 = force "deep" where legal, 2 = force "wide"
+void set_tc_cfg(int v) { g_tc_cfg.store(v, std::memory_order_relaxed); }
 
 int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   *handled = false;
@@ -386,8 +429,11 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
     if (!view_tma_ok(a->src[s])) return PHT_OK;
     ktot += a->src[s].C;
   }
-  if ((a->flags & (PHT_EPI_RESID_PRE | PHT_EPI_RESID_POST)) && !view_vec8_ok(a->resid)) return PHT_OK;
-  if ((a->flags & PHT_EPI_MASK) && !view_vec8_ok(a->mask)) return PHT_OK;
+  unsigned flags = a->flags;
+  if (!a->out2.ptr) flags &= ~(PHT_EPI_RESID_POST | PHT_EPI_MASK);   // they only shape out2
+  const bool has_resid = (flags & (PHT_EPI_RESID_PRE | PHT_EPI_RESID_POST)) != 0, has_mask = (flags & PHT_EPI_MASK) != 0;
+  if (has_resid && (!view_tma_ok(a->resid) || a->resid.C < a->N)) return PHT_OK;
+  if (has_mask && (!view_tma_ok(a->mask) || a->mask.C < a->N)) return PHT_OK;
   const bool out1_f32 = a->out1.ptr && a->out1.dtype == PHT_F32;
   if (out1_f32) {
     if (((uintptr_t)a->out1.ptr & 15) || a->out1.sx % 4 || a->out1.sy % 4 || a->out1.sb % 4) return PHT_OK;
@@ -399,18 +445,18 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   if (!get_encode_fn()) return PHT_OK;
 
   TcGemmP P;
-  P.B = a->B; P.Ho = a->Ho; P.Wo = a->Wo; P.N = a->N; P.ks = a->ksize; P.n_src = a->n_src; P.flags = a->flags;
-  CUtensorMap tmA[3], tmW;
+  P.B = a->B; P.Ho = a->Ho; P.Wo = a->Wo; P.N = a->N; P.ks = a->ksize; P.n_src = a->n_src; P.flags = flags;
+  TcMaps m;
   int k = 0;
   for (int s = 0; s < 3; ++s) {
     if (s < a->n_src) {
       P.srcC[s] = a->src[s].C; P.srcOy[s] = a->src[s].oy; P.srcOx[s] = a->src[s].ox; P.koff[s] = k;
       k += a->src[s].C;
-      int rc = make_src_tmap(&tmA[s], a->src[s], a->B);
+      int rc = make_src_tmap(&m.A[s], a->src[s], a->B);
       if (rc) return rc;
     } else {
       P.srcC[s] = 0; P.srcOy[s] = P.srcOx[s] = 0; P.koff[s] = 0;
-      tmA[s] = tmA[0];
+      m.A[s] = m.A[0];
     }
   }
   const int T = a->ksize * a->ksize;
@@ -418,7 +464,7 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)a->N, (uint64_t)T};
     uint64_t strides[2] = {(uint64_t)ktot * 2, (uint64_t)ktot * a->N * 2};
     uint32_t box[3] = {BK, (uint32_t)BN, 1};
-    int rc = make_tmap_bf16(&tmW, const_cast<void*>(a->w), 3, dims, strides, box);
+    int rc = make_tmap_bf16(&m.W, const_cast<void*>(a->w), 3, dims, strides, box);
     if (rc) return rc;
   }
   P.tiles_x = ceil_div(a->Wo, TILE_W);
@@ -426,25 +472,27 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   P.n_tiles = a->N / BN;
   P.num_tiles = a->B * P.tiles_x * P.tiles_y * P.n_tiles;
   P.bias = a->bias; P.slope = a->slope; P.mslope = a->mslope;
-  P.resid = (a->flags & (PHT_EPI_RESID_PRE | PHT_EPI_RESID_POST)) ? make_view(a->resid) : null_view();
-  P.mask = (a->flags & PHT_EPI_MASK) ? make_view(a->mask) : null_view();
   P.out1 = a->out1.ptr ? make_view(a->out1) : null_view();
-  P.out2 = a->out2.ptr ? make_view(a->out2) : null_view();
+  P.has_out1 = a->out1.ptr ? 1 : 0; P.has_out2 = a->out2.ptr ? 1 : 0;
+  P.has_resid = has_resid ? 1 : 0; P.has_mask = has_mask ? 1 : 0;
   P.out1_f32 = out1_f32 ? 1 : 0;
-  CUtensorMap tmO[2];
-  tmO[0] = tmO[1] = tmW;
-  if (a->out1.ptr && !out1_f32) {
-    int rc1 = make_src_tmap(&tmO[0], a->out1, a->B);
-    if (rc1) return rc1;
-  }
-  if (a->out2.ptr) {
-    int rc2 = make_src_tmap(&tmO[1], a->out2, a->B);
-    if (rc2) return rc2;
-  }
-  int rc;
-  if (BN == 256) rc = launch_tc<256>(a, P, tmA, tmW, tmO, st);
-  else if (BN == 128) rc = launch_tc<128>(a, P, tmA, tmW, tmO, st);
-  else rc = launch_tc<64>(a, P, tmA, tmW, tmO, st);
+  P.residOy = a->resid.oy; P.residOx = a->resid.ox; P.maskOy = a->mask.oy; P.maskOx = a->mask.ox;
+  P.out1Oy = a->out1.oy; P.out1Ox = a->out1.ox; P.out2Oy = a->out2.oy; P.out2Ox = a->out2.ox;
+  m.O[0] = m.O[1] = m.R = m.M = m.W;
+  int rc = PHT_OK;
+  if (a->out1.ptr && !out1_f32) rc = make_src_tmap(&m.O[0], a->out1, a->B);
+  if (!rc && a->out2.ptr) rc = make_src_tmap(&m.O[1], a->out2, a->B);
+  if (!rc && has_resid) rc = make_src_tmap(&m.R, a->resid, a->B);
+  if (!rc && has_mask) rc = make_src_tmap(&m.M, a->mask, a->B);
+  if (rc) return rc;
+  // "wide" whenever the epilogue streams inputs (mandatory) or the GEMM is HBM-bound (1x1) or writes two outputs
+  const int force = g_tc_cfg.load(std::memory_order_relaxed);
+  bool wide = has_resid || has_mask || a->ksize == 1 || (a->out1.ptr && a->out2.ptr);
+  if (force == 2) wide = true;
+  if (force == 1 && !has_resid && !has_mask) wide = false;
+  if (BN == 256) rc = wide ? launch_tc<256, true>(P, m, st) : launch_tc<256, false>(P, m, st);
+  else if (BN == 128) rc = wide ? launch_tc<128, true>(P, m, st) : launch_tc<128, false>(P, m, st);
+  else rc = wide ? launch_tc<64, true>(P, m, st) : launch_tc<64, false>(P, m, st);
   if (rc) return rc;
   count_launch(CNT_GEMM_TC);
   *handled = true;

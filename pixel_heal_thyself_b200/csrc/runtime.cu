@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int slot, uint64_t n) { g_counters[slot & 7].fetch_add(n, std::memory_order_relaxed); }
+void set_tc_cfg(int v);  // igemm_tc.cu
 bool force_simple() { return g_force_simple.load(std::memory_order_relaxed) != 0; }
 
 }  // namespace pht
@@ -31,6 +32,11 @@ void pht_get_counters(uint64_t* c) {
 }
 void pht_reset_counters(void) {
   for (int i = 0; i < 8; ++i) pht::g_counters[i].store(0, std::memory_order_relaxed);
+}
+int pht_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "tc_cfg")) { pht::set_tc_cfg(value); return PHT_OK; }
+  pht::set_error("pht_set_option: unknown option");
+  return PHT_ERR_INVALID;
 }
 void pht_set_force_simple(int on) { pht::g_force_simple.store(on ? 1 : 0, std::memory_order_relaxed); }
 
