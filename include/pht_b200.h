@@ -59,6 +59,13 @@ typedef struct pht_view {
 #define PHT_EPI_RESID_PRE  1u  /* v += resid before the activation            */
 #define PHT_EPI_RESID_POST 2u  /* out2 = v + resid                            */
 #define PHT_EPI_MASK       4u  /* out2 *= (mask > 0 ? 1 : mslope[n])          */
+/* Backward of REPLICATE padding fused into a data-gradient: the output domain (Ho, Wo) = (H+2, W+2) is the padded
+ * domain; before the epilogue runs, the value of every border pixel is added to the interior pixel it was replicated
+ * from (== pht_pad_fold with PHT_PAD_REPLICATE).  resid / mask are views of the INTERIOR (H x W; padded pixel (y, x)
+ * reads view pixel (y-1, x-1)); out1 / out2 are views of PADDED buffers (H+2 x W+2): their interior holds the result,
+ * their 1-pixel frame receives don't-care values.  bf16 tensor-core path only (ksize 3, N <= 256, H % 8 == 0,
+ * W % 8 == 0); otherwise PHT_ERR_UNSUPPORTED. */
+#define PHT_EPI_PADFOLD    8u
 
 /* Implicit-GEMM convolution over pixels with virtual concat:
  *   acc[p, n] = sum_t sum_s sum_k src[s](p + tap_t)[k] * w[t][n][koff_s + k]

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libpht_b200.so")
 
 PHT_F32, PHT_BF16 = 0, 1
 PAD_REPLICATE, PAD_REFLECT = 0, 1
-EPI_RESID_PRE, EPI_RESID_POST, EPI_MASK = 1, 2, 4
+EPI_RESID_PRE, EPI_RESID_POST, EPI_MASK, EPI_PADFOLD = 1, 2, 4, 8
 ABI_VERSION = 1
 
 PAD_MODES = {"replicate": PAD_REPLICATE, "reflect": PAD_REFLECT}

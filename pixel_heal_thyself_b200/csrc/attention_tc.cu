@@ -28,11 +28,13 @@ constexpr int AT_K_BYTES = AT_NS * 128;                        // 30720
 constexpr int AT_V_BYTES = AT_NKP * 128;                       // 26624
 constexpr int AT_P_BYTES = 4 * 64 * 128;                       // 4 K-tiles of 64 keys
 constexpr int AT_KV_BOX_BYTES = AT_NK * 128;                   // 25088 written by one TMA box
-constexpr int AT_SMEM = 2 * (AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES + AT_P_BYTES) + 256 + 1024;
+constexpr int AT_RO_BYTES = 2 * AT_Q_BYTES;                    // residual-in / output staging: 2 heads x [64 px][64 ch]
+constexpr int AT_SMEM = 2 * (AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES + AT_P_BYTES) + 2 * AT_RO_BYTES + 256 + 1024;
+static_assert(AT_SMEM <= 232448, "attn_fwd_tc: shared memory budget");
 
 struct AtP {
   int B, H, W, nbx, nby, nblocks;
-  View resid, out;
+  int has_resid, residOy, residOx, outOy, outOx;
   const float* rel_h;
   const float* rel_w;
   float* lse;
@@ -46,14 +48,18 @@ __device__ __forceinline__ float ex2(float x) {
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const AtP P) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmR,
+                   const __grid_constant__ CUtensorMap tmO, const AtP P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Qs = smem;                                   // [2][64 x 128B]
   uint8_t* Ks = Qs + 2 * AT_Q_BYTES;                    // [2][240 x 128B]
   uint8_t* Vs = Ks + 2 * AT_K_BYTES;                    // [2][208 x 128B]
   uint8_t* Ps = Vs + 2 * AT_V_BYTES;                    // [2][4][64 x 128B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * AT_P_BYTES);
+  uint8_t* Rs = Ps + 2 * AT_P_BYTES;                    // [2][64 x 128B] residual tiles (TMA in)
+  uint8_t* Os = Rs + AT_RO_BYTES;                       // [2][64 x 128B] output staging (TMA out)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Os + AT_RO_BYTES);
+  uint64_t* r_full = bars + 10;
   uint64_t* qk_full = bars + 0;
   uint64_t* qk_empty = bars + 1;
   uint64_t* v_full = bars + 2;
@@ -61,7 +67,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* p_full = bars + 4;
   uint64_t* s_full = bars + 5;     // [2]
   uint64_t* tmem_free = bars + 7;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // one-time smem constants: zero pad rows of K / V, relative-position rows of K (swizzled like a TMA box)
@@ -100,6 +106,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(v_full, 1);
     mbar_init(pv_done, 1);
     mbar_init(p_full, 128);
+    mbar_init(r_full, 1);
     for (int r = 0; r < 2; ++r) {
       mbar_init(&s_full[r], 1);
       mbar_init(&tmem_free[r], 128);
@@ -191,16 +198,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float prev_m = 0.f, prev_sum = 1.f;
     int prev_blk = 0, prev_pair = 0;
 
+    const bool issuer = (warp == 2 && lane == 0);
+    // residual tiles of iteration `it` (both heads of the pair) -> Rs, signalled on r_full
+    auto load_resid = [&](int it) {
+      const int blk = blockIdx.x + (it >> 1) * gridDim.x, pair = it & 1;
+      const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+      mbar_expect_tx(r_full, AT_RO_BYTES);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        tma_load_4d(Rs + h * AT_Q_BYTES, &tmR, r_full, (pair * 2 + h) * 64, bx * 8 + P.residOx, by * 8 + P.residOy, b);
+    };
+    if (issuer && P.has_resid && n_it > 0) load_resid(0);
+
     auto epilogue = [&](int it, float m, float sum, int blk, int pair) {
       const int r = it & 1;
       mbar_wait(pv_done, it & 1);
       tc_fence_after();
+      if (P.has_resid) mbar_wait(r_full, it & 1);
+      // the previous iteration's TMA store has finished reading the staging tile
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
       const int y = by * 8 + qy, x = bx * 8 + qx, head = pair * 2 + hp;
       const float inv = 1.f / sum;
       const uint32_t t_addr = tmem_base + r * 256 + ((uint32_t)(quad * 32) << 16);
-      bf16* op = (bf16*)P.out.ptr + view_off(P.out, b, y, x) + head * 64;
-      const bf16* rp = P.resid.ptr ? (const bf16*)P.resid.ptr + view_off(P.resid, b, y, x) + head * 64 : nullptr;
+      const uint8_t* rrow = Rs + hp * AT_Q_BYTES + q * 128;
+      uint8_t* orow = Os + hp * AT_Q_BYTES + q * 128;
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t o[32];
@@ -211,8 +234,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(o[g * 8 + j]) * inv;
-          if (rp) {
-            uint4 ru = *reinterpret_cast<const uint4*>(rp + c0 + g * 8);
+          const int ch = ((c0 >> 3) + g) ^ (q & 7);      // 128B-swizzled 16-byte chunk of this row
+          if (P.has_resid) {
+            uint4 ru = *reinterpret_cast<const uint4*>(rrow + ch * 16);
             const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&ru);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -225,12 +249,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          *reinterpret_cast<uint4*>(op + c0 + g * 8) = u;
+          *reinterpret_cast<uint4*>(orow + ch * 16) = u;
         }
       }
       if (P.lse) P.lse[(((long long)b * P.H + y) * P.W + x) * 4 + head] = m + logf(sum);
+      fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&tmem_free[r]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // staging complete, residual tile consumed
+      if (issuer) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Os + h * AT_Q_BYTES)), "r"((pair * 2 + h) * 64),
+                         "r"(bx * 8 + P.outOx), "r"(by * 8 + P.outOy), "r"(b)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (P.has_resid && it + 1 < n_it) load_resid(it + 1);
+      }
     };
 
     for (int it = 0; it < n_it; ++it) {
@@ -300,6 +337,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       prev_m = m; prev_sum = sum; prev_blk = blk; prev_pair = pair;
     }
     if (n_it > 0) epilogue(n_it - 1, prev_m, prev_sum, prev_blk, prev_pair);
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before exit
   }
 
   tc_fence_before();
@@ -331,17 +369,24 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   if (!at_view_ok(a->q, 256) || !at_view_ok(a->k, 256) || !at_view_ok(a->v, 256) || !at_view_ok(a->out, 256)) return PHT_OK;
   if (a->resid.ptr && !at_view_ok(a->resid, 256)) return PHT_OK;
   if (!get_encode_fn()) return PHT_OK;
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmR, tmO;
   int rc = at_tmap(&tmQ, a->q, a->B, 8, 8);
   if (rc) return rc;
   rc = at_tmap(&tmK, a->k, a->B, 14, 14);
   if (rc) return rc;
   rc = at_tmap(&tmV, a->v, a->B, 14, 14);
   if (rc) return rc;
+  rc = at_tmap(&tmO, a->out, a->B, 8, 8);
+  if (rc) return rc;
+  tmR = tmO;
+  if (a->resid.ptr) {
+    rc = at_tmap(&tmR, a->resid, a->B, 8, 8);
+    if (rc) return rc;
+  }
   AtP P;
   P.B = a->B; P.H = a->H; P.W = a->W; P.nbx = a->W / 8; P.nby = a->H / 8; P.nblocks = a->B * P.nbx * P.nby;
-  P.resid = a->resid.ptr ? make_view(a->resid) : null_view();
-  P.out = make_view(a->out);
+  P.has_resid = a->resid.ptr ? 1 : 0;
+  P.residOy = a->resid.oy; P.residOx = a->resid.ox; P.outOy = a->out.oy; P.outOx = a->out.ox;
   P.rel_h = a->rel_h; P.rel_w = a->rel_w; P.lse = a->lse;
   static bool attr = false;
   if (!attr) {
@@ -352,7 +397,7 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.nblocks < sms ? P.nblocks : sms;
-  attn_fwd_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, P);
+  attn_fwd_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, tmR, tmO, P);
   PHT_LAUNCH_CHECK();
   count_launch(CNT_ATTN_TC);
   *handled = true;

@@ -265,43 +265,46 @@ __global__ void colsum_kernel(View dy, int B, int Ho, int Wo, int N, int tpp, in
   }
 }
 
-// bf16 fast path of the column sum for pixel-contiguous views (offset = p * sx): 16-byte loads, 4 loads in flight per
-// thread, each thread owns one fixed 8-channel group (tpp = N/8 threads cover a pixel), block partials through shared
-// memory, one atomicAdd per channel per block.
-__global__ void __launch_bounds__(256) colsum_bf16_flat_kernel(const bf16* __restrict__ dy, long long sx, long long npx, int N,
-                                                               int tpp, int rows, long long chunk, float* __restrict__ out) {
+// bf16 fast path of the column sum for any strided NHWC view: 16-byte loads, 4 loads in flight per thread, each
+// thread owns one fixed 8-channel group (tpp = N/8 threads cover a pixel), blocks stride over image rows (no per-pixel
+// division), block partials through shared memory, one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256) colsum_bf16_rows_kernel(const bf16* __restrict__ dy, long long sb, long long sy,
+                                                               long long sx, int Ho, int Wo, int nrows, int N, int tpp,
+                                                               int rows, float* __restrict__ out) {
   extern __shared__ float sm[];  // [rows][N]
   const int cg = threadIdx.x % tpp, prow = threadIdx.x / tpp;
-  const long long pbeg = (long long)blockIdx.x * chunk, pend = pbeg + chunk < npx ? pbeg + chunk : npx;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (prow < rows) {
-    const bf16* base = dy + cg * 8;
-    long long p = pbeg + prow;
-    for (; p + 3LL * rows < pend; p += 4LL * rows) {
-      uint4 u[4];
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+      const int b = r / Ho, y = r - b * Ho;
+      const bf16* base = dy + b * sb + y * sy + cg * 8;
+      int x = prow;
+      for (; x + 3 * rows < Wo; x += 4 * rows) {
+        uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (p + (long long)k * rows) * sx));
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(base + (long long)(x + k * rows) * sx));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+        for (int k = 0; k < 4; ++k) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __bfloat1622float2(h[j]);
+            acc[2 * j] += f.x;
+            acc[2 * j + 1] += f.y;
+          }
+        }
+      }
+      for (; x < Wo; x += rows) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (long long)x * sx));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float2 f = __bfloat1622float2(h[j]);
           acc[2 * j] += f.x;
           acc[2 * j + 1] += f.y;
         }
-      }
-    }
-    for (; p < pend; p += rows) {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * sx));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(h[j]);
-        acc[2 * j] += f.x;
-        acc[2 * j + 1] += f.y;
       }
     }
 #pragma unroll
@@ -437,16 +440,14 @@ int colsum(const pht_view& dy, int dtype, int B, int Ho, int Wo, int N, float* o
   int chunk = (int)((npx + splits - 1) / splits);
   splits = (int)((npx + chunk - 1) / chunk);
   PHT_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
-  if (dtype == PHT_BF16 && N % 8 == 0 && N / 8 <= 256 && dy.sx % 8 == 0 && ((uintptr_t)dy.ptr & 15) == 0 && dy.oy == 0 &&
-      dy.ox == 0 && dy.sy == (long long)Wo * dy.sx && (B == 1 || dy.sb == (long long)Ho * dy.sy)) {
+  if (dtype == PHT_BF16 && N % 8 == 0 && N / 8 <= 256 && dy.sx % 8 == 0 && dy.sy % 8 == 0 && dy.sb % 8 == 0 &&
+      ((uintptr_t)dy.ptr & 15) == 0) {
     const int tpp8 = N / 8, rows8 = 256 / tpp8;
-    int blocks = (int)((npx + 32LL * rows8 - 1) / (32LL * rows8));
-    if (blocks > 8 * sms) blocks = 8 * sms;
-    if (blocks < 1) blocks = 1;
-    long long chunk8 = (npx + blocks - 1) / blocks;
-    blocks = (int)((npx + chunk8 - 1) / chunk8);
-    colsum_bf16_flat_kernel<<<blocks, 256, (size_t)rows8 * N * sizeof(float), st>>>((const bf16*)dy.ptr, dy.sx, npx, N, tpp8,
-                                                                                     rows8, chunk8, out);
+    const int nrows = B * Ho;
+    int blocks = nrows < 8 * sms ? nrows : 8 * sms;
+    const bf16* base = (const bf16*)dy.ptr + (long long)dy.oy * dy.sy + (long long)dy.ox * dy.sx;
+    colsum_bf16_rows_kernel<<<blocks, 256, (size_t)rows8 * N * sizeof(float), st>>>(base, dy.sb, dy.sy, dy.sx, Ho, Wo, nrows, N,
+                                                                                     tpp8, rows8, out);
     count_launch(CNT_OTHER);
     PHT_LAUNCH_CHECK();
     return PHT_OK;
@@ -480,6 +481,10 @@ int pht_conv_gemm(const pht_conv_gemm_args* a, void* stream) {
     if (rc) return rc;
     if (handled) return PHT_OK;
   }
+  if (a->flags & PHT_EPI_PADFOLD) {
+    set_error("conv_gemm: PHT_EPI_PADFOLD needs the bf16 tensor-core path (ksize 3, H and W multiples of 8, TMA-able views)");
+    return PHT_ERR_UNSUPPORTED;
+  }
   return conv_gemm_simple(a, st);
 }
 
@@ -494,15 +499,15 @@ int pht_wgrad(const pht_wgrad_args* a, void* stream) {
   PHT_CHECK_ARG(a->ksize == 1 || a->ksize == 3 || a->ksize == 5, "wgrad: ksize must be 1, 3 or 5");
   PHT_CHECK_ARG(a->n_src >= 1 && a->n_src <= 3, "wgrad: n_src must be 1..3");
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == PHT_BF16 && !force_simple()) {
+    bool handled = false;
+    int rc = wgrad_tc(a, st, &handled);   // also produces dbias (fused column sums)
+    if (rc) return rc;
+    if (handled) return PHT_OK;
+  }
   if (a->dbias) {
     int rc = colsum(a->dy, a->dtype, a->B, a->Ho, a->Wo, a->N, a->dbias, st);
     if (rc) return rc;
-  }
-  if (a->dtype == PHT_BF16 && !force_simple()) {
-    bool handled = false;
-    int rc = wgrad_tc(a, st, &handled);
-    if (rc) return rc;
-    if (handled) return PHT_OK;
   }
   return wgrad_simple(a, st);
 }

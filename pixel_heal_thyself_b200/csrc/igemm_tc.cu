@@ -25,7 +25,7 @@ using namespace tc;
 constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;  // 128 output pixels per tile
 constexpr int BK = 64;                                            // bf16 elements per 128-byte swizzle row
 constexpr int TC_THREADS = 224;                                   // 7 warps: TMA, MMA, 4 x epilogue, aux TMA
-constexpr int MAX_VEC_N = 768;
+constexpr int MAX_VEC_N = 768;                                     // largest N (bias / slope vectors)
 constexpr int STG_BYTES = TILE_M * 128;  // one epilogue tile: 128 pixels x 64 bf16, 128B-swizzled rows
 
 struct TcGemmP {
@@ -42,19 +42,27 @@ struct TcGemmP {
   int residOy, residOx, maskOy, maskOx, out1Oy, out1Ox, out2Oy, out2Ox;
 };
 
-// WIDE = false ("deep"): 4-stage operand ring, one output staging tile, no epilogue inputs: K-heavy 3x3 convolutions.
-// WIDE = true  ("wide"): 3-stage ring, two output staging tiles and a 2-slot ring of TMA-prefetched epilogue input
-//                        tiles (residual / activation mask): the HBM-bound 1x1 GEMMs and every fused epilogue.
-template <int BN, bool WIDE> struct TcCfg {
+// MODE 0 "deep":     4-stage operand ring, one output staging tile, no epilogue inputs: K-heavy 3x3 convolutions.
+// MODE 1 "wide":     3-stage ring, two output staging tiles and a 2-slot ring of TMA-prefetched epilogue input tiles
+//                    (residual / activation mask): the HBM-bound 1x1 GEMMs.
+// MODE 2 "deep+aux": 4-stage ring, one staging tile, one epilogue-input slot: 3x3 convolutions with a fused
+//                    residual / mask / second output / padding fold (their long K loop hides the serial epilogue);
+//                    slope vectors are read through the L1 instead of shared memory to fit in 227 KB.
+template <int BN, int MODE> struct TcCfg {
   static constexpr int A_BYTES = TILE_M * BK * 2;                  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;                      // 32 KB @ BN=256
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? (WIDE ? 3 : 4) : (BN == 128 ? 4 : 6);
-  static constexpr int NSTG = WIDE ? 2 : 1;
-  static constexpr int AUX_SLOTS = WIDE ? 2 : 0;
+  static constexpr int STAGES = BN == 256 ? (MODE == 1 ? 3 : 4) : (BN == 128 ? 4 : 6);
+  static constexpr int NSTG = MODE == 1 ? 2 : 1;
+  static constexpr int AUX_SLOTS = MODE == 1 ? 2 : (MODE == 2 ? 1 : 0);
+  static constexpr bool VEC_SMEM = MODE != 2;                      // slope / mslope staged in shared memory
+  static constexpr int VEC_N = VEC_SMEM ? MAX_VEC_N : 256;         // largest N this config accepts
+  static constexpr int VEC_BYTES = (VEC_SMEM ? 3 : 1) * VEC_N * 4;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // power of two for BN in {64,128,256}
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (NSTG + AUX_SLOTS) * STG_BYTES + 3 * MAX_VEC_N * 4 + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (NSTG + AUX_SLOTS) * STG_BYTES + VEC_BYTES + 256 + 1024;
 };
+static_assert(TcCfg<256, 0>::SMEM_BYTES <= 232448 && TcCfg<256, 1>::SMEM_BYTES <= 232448 && TcCfg<256, 2>::SMEM_BYTES <= 232448,
+              "conv_gemm_tc: shared memory budget");
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -79,14 +87,15 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <int BN, bool WIDE>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmM, const TcGemmP P) {
-  using Cfg = TcCfg<BN, WIDE>;
+  using Cfg = TcCfg<BN, MODE>;
   constexpr int NCHUNK = BN / 64;
+  constexpr bool AUX = Cfg::AUX_SLOTS > 0;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stage bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,9 +103,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint8_t* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // 1024-aligned (stage sizes are multiples of 1024)
   uint8_t* aux = stg + Cfg::NSTG * STG_BYTES;
   float* s_bias = reinterpret_cast<float*>(aux + Cfg::AUX_SLOTS * STG_BYTES);
-  float* s_slope = s_bias + MAX_VEC_N;
+  float* s_slope = s_bias + MAX_VEC_N;      // only when Cfg::VEC_SMEM
   float* s_mslope = s_slope + MAX_VEC_N;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mslope + MAX_VEC_N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_bias) + Cfg::VEC_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]
   uint64_t* empty_bar = bars + Cfg::STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;   // [2]
@@ -109,8 +118,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
     s_bias[i] = P.bias ? P.bias[i] : 0.f;
-    s_slope[i] = P.slope ? P.slope[i] : 1.f;
-    s_mslope[i] = P.mslope ? P.mslope[i] : 0.f;
+    if (Cfg::VEC_SMEM) {
+      s_slope[i] = P.slope ? P.slope[i] : 1.f;
+      s_mslope[i] = P.mslope ? P.mslope[i] : 0.f;
+    }
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
@@ -201,7 +212,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ================================ epilogue-input TMA producer ================================
     // streams the residual / mask tiles in exactly the order the epilogue consumes them:
     // for tile: for 64-channel chunk: [resid], [mask]
-    if (WIDE && lane == 0 && n_kinds > 0) {
+    if (AUX && lane == 0 && n_kinds > 0) {
+      constexpr int NS = AUX ? Cfg::AUX_SLOTS : 1;
+      const int fo = (P.flags & PHT_EPI_PADFOLD) ? 1 : 0;   // residual / mask live on the interior domain
       prefetch_tmap(&tmR);
       prefetch_tmap(&tmM);
       int j = 0;
@@ -211,11 +224,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * BN;
         for (int c = 0; c < NCHUNK; ++c) {
           for (int kind = P.has_resid ? 0 : 1; kind < (P.has_mask ? 2 : 1); ++kind, ++j) {
-            const int slot = j & 1;
-            mbar_wait(&aempty_bar[slot], ((j >> 1) & 1) ^ 1);
+            const int slot = j % NS;
+            mbar_wait(&aempty_bar[slot], ((j / NS) & 1) ^ 1);
             mbar_expect_tx(&afull_bar[slot], STG_BYTES);
-            if (kind == 0) tma_load_4d(aux + slot * STG_BYTES, &tmR, &afull_bar[slot], n0 + c * 64, x0 + P.residOx, y0 + P.residOy, b);
-            else tma_load_4d(aux + slot * STG_BYTES, &tmM, &afull_bar[slot], n0 + c * 64, x0 + P.maskOx, y0 + P.maskOy, b);
+            if (kind == 0) tma_load_4d(aux + slot * STG_BYTES, &tmR, &afull_bar[slot], n0 + c * 64, x0 - fo + P.residOx, y0 - fo + P.residOy, b);
+            else tma_load_4d(aux + slot * STG_BYTES, &tmM, &afull_bar[slot], n0 + c * 64, x0 - fo + P.maskOx, y0 - fo + P.maskOy, b);
           }
         }
       }
@@ -249,8 +262,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     };
     // v[64] (op)= the epilogue-input tile that is next in the stream; releases its slot
     auto aux_apply = [&](float* v, int c_abs, bool is_mask) {
-      const int slot = j_aux & 1;
-      mbar_wait(&afull_bar[slot], (j_aux >> 1) & 1);
+      constexpr int NS = AUX ? Cfg::AUX_SLOTS : 1;
+      const int slot = j_aux % NS;
+      mbar_wait(&afull_bar[slot], (j_aux / NS) & 1);
       const uint8_t* arow = aux + slot * STG_BYTES + row * 128;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -258,7 +272,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         unpack8(*reinterpret_cast<const uint4*>(arow + ((g ^ rsw) * 16)), t);
         if (is_mask) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[g * 8 + j] *= (t[j] > 0.f ? 1.f : s_mslope[c_abs + g * 8 + j]);
+          for (int j = 0; j < 8; ++j)
+            v[g * 8 + j] *= (t[j] > 0.f ? 1.f : (Cfg::VEC_SMEM ? s_mslope[c_abs + g * 8 + j]
+                                                               : (P.mslope ? __ldg(P.mslope + c_abs + g * 8 + j) : 0.f)));
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
@@ -299,10 +315,38 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] += s_bias[n0 + c0 + j];
-        if (WIDE && (P.flags & PHT_EPI_RESID_PRE)) aux_apply(v, n0 + c0, false);
+        if (MODE == 2 && (P.flags & PHT_EPI_PADFOLD)) {
+          // backward of replicate padding, fused: the tile lives on the padded domain; every border pixel's value is
+          // added to the interior pixel it was replicated from (always inside the same tile, see the host check)
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          uint8_t* srow = stg + row * 128;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(srow + ((g ^ rsw) * 16)) = pack8(v + g * 8);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int ey = y == 1 ? -1 : (y == P.Ho - 2 ? 1 : 0), ex = x == 1 ? -1 : (x == P.Wo - 2 ? 1 : 0);
+          const bool interior = y >= 1 && y <= P.Ho - 2 && x >= 1 && x <= P.Wo - 2;
+          if (interior && (ey | ex)) {
+            auto add_row = [&](int r2) {
+              const uint8_t* nrow = stg + r2 * 128;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                float t[8];
+                unpack8(*reinterpret_cast<const uint4*>(nrow + ((g ^ (r2 & 7)) * 16)), t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+              }
+            };
+            if (ey) add_row(row + ey * TILE_W);
+            if (ex) add_row(row + ex);
+            if (ey && ex) add_row(row + ey * TILE_W + ex);
+          }
+        }
+        if (AUX && (P.flags & PHT_EPI_RESID_PRE)) aux_apply(v, n0 + c0, false);
         if (P.slope) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * s_slope[n0 + c0 + j];
+          for (int j = 0; j < 64; ++j)
+            v[j] = v[j] > 0.f ? v[j] : v[j] * (Cfg::VEC_SMEM ? s_slope[n0 + c0 + j] : __ldg(P.slope + n0 + c0 + j));
         }
         if (P.has_out1) {
           if (P.out1_f32) {
@@ -316,8 +360,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           }
         }
         if (P.has_out2) {   // (the host clears RESID_POST / MASK when there is no out2)
-          if (WIDE && (P.flags & PHT_EPI_RESID_POST)) aux_apply(v, n0 + c0, false);
-          if (WIDE && (P.flags & PHT_EPI_MASK)) aux_apply(v, n0 + c0, true);
+          if (AUX && (P.flags & PHT_EPI_RESID_POST)) aux_apply(v, n0 + c0, false);
+          if (AUX && (P.flags & PHT_EPI_MASK)) aux_apply(v, n0 + c0, true);
           stage_and_store(v, &tmO2, n0 + c0, x0 + P.out2Ox, y0 + P.out2Oy, b);
         }
       }
@@ -399,19 +443,19 @@ struct TcMaps {
   CUtensorMap A[3], W, O[2], R, M;
 };
 
-template <int BN, bool WIDE>
+template <int BN, int MODE>
 static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
-  using Cfg = TcCfg<BN, WIDE>;
+  using Cfg = TcCfg<BN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    PHT_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    PHT_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
-  conv_gemm_tc_kernel<BN, WIDE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.A[0], m.A[1], m.A[2], m.W, m.O[0], m.O[1], m.R, m.M, P);
+  conv_gemm_tc_kernel<BN, MODE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.A[0], m.A[1], m.A[2], m.W, m.O[0], m.O[1], m.R, m.M, P);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
@@ -434,6 +478,10 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   const bool has_resid = (flags & (PHT_EPI_RESID_PRE | PHT_EPI_RESID_POST)) != 0, has_mask = (flags & PHT_EPI_MASK) != 0;
   if (has_resid && (!view_tma_ok(a->resid) || a->resid.C < a->N)) return PHT_OK;
   if (has_mask && (!view_tma_ok(a->mask) || a->mask.C < a->N)) return PHT_OK;
+  const bool padfold = (flags & PHT_EPI_PADFOLD) != 0;
+  if (padfold && (a->ksize != 3 || (a->Ho - 2) % TILE_H || (a->Wo - 2) % 8 || a->Ho < 10 || a->Wo < 10 ||
+                  (a->out1.ptr && a->out1.dtype != PHT_BF16)))
+    return PHT_OK;
   const bool out1_f32 = a->out1.ptr && a->out1.dtype == PHT_F32;
   if (out1_f32) {
     if (((uintptr_t)a->out1.ptr & 15) || a->out1.sx % 4 || a->out1.sy % 4 || a->out1.sb % 4) return PHT_OK;
@@ -485,14 +533,21 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   if (!rc && has_resid) rc = make_src_tmap(&m.R, a->resid, a->B);
   if (!rc && has_mask) rc = make_src_tmap(&m.M, a->mask, a->B);
   if (rc) return rc;
-  // "wide" whenever the epilogue streams inputs (mandatory) or the GEMM is HBM-bound (1x1) or writes two outputs
+  // 1x1 GEMMs are HBM-bound: wide epilogue.  3x3: deep ring; with a fused epilogue (inputs, second output, fold) the
+  // deep+aux variant.
   const int force = g_tc_cfg.load(std::memory_order_relaxed);
-  bool wide = has_resid || has_mask || a->ksize == 1 || (a->out1.ptr && a->out2.ptr);
-  if (force == 2) wide = true;
-  if (force == 1 && !has_resid && !has_mask) wide = false;
-  if (BN == 256) rc = wide ? launch_tc<256, true>(P, m, st) : launch_tc<256, false>(P, m, st);
-  else if (BN == 128) rc = wide ? launch_tc<128, true>(P, m, st) : launch_tc<128, false>(P, m, st);
-  else rc = wide ? launch_tc<64, true>(P, m, st) : launch_tc<64, false>(P, m, st);
+  const bool fused = has_resid || has_mask || (a->out1.ptr && a->out2.ptr) || padfold;
+  int mode = a->ksize == 1 ? 1 : (fused ? 2 : 0);
+  if (mode == 2 && a->N > TcCfg<256, 2>::VEC_N) {
+    if (padfold) return PHT_OK;   // (the dispatcher reports PHT_ERR_UNSUPPORTED)
+    mode = 1;
+  }
+  if (force == 2 && !padfold) mode = 1;
+  if (force == 1 && !fused) mode = 0;
+  if (force == 3 && a->ksize == 1 && a->N <= TcCfg<256, 2>::VEC_N) mode = fused ? 2 : 0;
+  if (BN == 256) rc = mode == 0 ? launch_tc<256, 0>(P, m, st) : (mode == 1 ? launch_tc<256, 1>(P, m, st) : launch_tc<256, 2>(P, m, st));
+  else if (BN == 128) rc = mode == 0 ? launch_tc<128, 0>(P, m, st) : (mode == 1 ? launch_tc<128, 1>(P, m, st) : launch_tc<128, 2>(P, m, st));
+  else rc = mode == 0 ? launch_tc<64, 0>(P, m, st) : (mode == 1 ? launch_tc<64, 1>(P, m, st) : launch_tc<64, 2>(P, m, st));
   if (rc) return rc;
   count_launch(CNT_GEMM_TC);
   *handled = true;

@@ -3,6 +3,8 @@
 // i.e. a GEMM with M = dy channels, N = source channels, K = pixels.  Both operands are "MN-major" (the channel
 // dim is contiguous in the NHWC buffers, the pixel dim is the K row), which tcgen05 consumes directly from the
 // 128B-swizzled TMA boxes [64 ch x (4 x 16) pixels] -- no transposes are ever materialised.
+// The bias gradient (column sums of dy) is fused: in the jobs of the centre tap / first k-tile the four otherwise idle
+// epilogue warps sum the dy tiles straight out of the TMA stages while the tensor core consumes them.
 //
 // One CTA = one job (tap t, n-tile of 128*MH channels, k-tile of <= 256 source channels, pixel split): it streams its
 // pixel range through a 3/4-stage TMA ring, accumulates in TMEM (MH accumulators of 128 x 256 fp32) and writes the
@@ -29,7 +31,8 @@ struct WgP {
   int dyOy, dyOx;
   int srcOy[3], srcOx[3];
   WgKTile kt[WG_MAX_KT];
-  float* ws;  // [splits][T][N][Ktot]
+  float* ws;       // [splits][T][N][Ktot]
+  float* bias_ws;  // [splits][N] partial column sums of dy, or nullptr
 };
 
 template <int MH> struct WgCfg {
@@ -67,13 +70,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   const int pt_beg = split * P.ptiles_per_split;
   const int pt_end = min(pt_beg + P.ptiles_per_split, P.ptiles_total);
   const int npt = pt_end - pt_beg;
+  // this job also produces the bias-gradient partial of its (split, n-tile): centre tap, first k-tile
+  const bool do_bias = P.bias_ws != nullptr && kti == 0 && t == (P.T >> 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmDy);
     prefetch_tmap(&tmS0);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], do_bias ? 5 : 1);   // tensor core (commit) + the 4 column-sum warps
     }
     mbar_init(done_bar, 1);
     mbar_fence_init();
@@ -134,6 +139,44 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   } else {
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
+    if (do_bias) {
+      // column sums of the dy tiles: warp w of the 4 owns channel box (w, w+4, ..) of 64 channels, lane = channel pair;
+      // a warp reads one whole 128-byte pixel row per instruction (conflict-free under the 128B swizzle)
+      const int ew = warp - 2;
+      float bs[MH][2];
+#pragma unroll
+      for (int h = 0; h < MH; ++h) bs[h][0] = bs[h][1] = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < npt; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint8_t* a_base = smem + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int h = 0; h < MH; ++h) {
+          const uint8_t* box = a_base + (h * 4 + ew) * WG_BOX_BYTES;   // boxes ew and ew+4 (MH = 2): 4 warps x MH boxes
+          if (h * 4 + ew < 2 * MH) {
+#pragma unroll 8
+            for (int r = 0; r < WG_PIX; ++r) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(box + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+              bs[h][0] += __uint_as_float(u << 16);
+              bs[h][1] += __uint_as_float(u & 0xffff0000u);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int h = 0; h < MH; ++h) {
+        const int bidx = h * 4 + ew;
+        if (bidx < 2 * MH) {
+          float* dst = P.bias_ws + (size_t)split * P.N + n0 + bidx * 64 + lane * 2;
+          dst[0] = bs[h][0];
+          dst[1] = bs[h][1];
+        }
+      }
+    }
     if (npt > 0) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
@@ -167,8 +210,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   }
 }
 
-__global__ void wgrad_reduce_splits_kernel(const float4* __restrict__ ws, float4* __restrict__ dw, long long n4, int splits) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+// fixed-order (deterministic) sum of the split partials; the LAST block reduces the bias partials [splits][N]
+__global__ void wgrad_reduce_splits_kernel(const float4* __restrict__ ws, float4* __restrict__ dw, long long n4, int splits,
+                                           const float* __restrict__ bias_ws, float* __restrict__ dbias, int N) {
+  if (bias_ws != nullptr && blockIdx.x == gridDim.x - 1) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      float a = 0.f;
+      for (int s = 0; s < splits; ++s) a += bias_ws[(long long)s * N + n];
+      dbias[n] = a;
+    }
+    return;
+  }
+  const long long nblk = bias_ws != nullptr ? gridDim.x - 1 : gridDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += nblk * blockDim.x) {
     float4 a = ws[i];
     for (int s = 1; s < splits; ++s) {
       float4 b = ws[(long long)s * n4 + i];
@@ -229,7 +283,7 @@ static WgPlan wg_plan(const pht_wgrad_args* a, size_t ws_limit_bytes) {
   // one CTA per SM (192 KB of smem): never spill a few jobs into a second wave
   int splits = base_jobs >= sms ? 1 : sms / base_jobs;
   if (splits > p.ptiles_total) splits = p.ptiles_total;
-  size_t per_split_bytes = (size_t)p.T * a->N * p.Ktot * sizeof(float);
+  size_t per_split_bytes = ((size_t)p.T * a->N * p.Ktot + a->N) * sizeof(float);   // + one bias partial row
   if (ws_limit_bytes > 0) {
     size_t max_splits = ws_limit_bytes / per_split_bytes;
     if (max_splits < 1) return p;
@@ -245,7 +299,7 @@ static WgPlan wg_plan(const pht_wgrad_args* a, size_t ws_limit_bytes) {
 size_t wgrad_tc_workspace_bytes(const pht_wgrad_args* a) {
   WgPlan p = wg_plan(a, 0);
   if (!p.ok) return 0;
-  return (size_t)p.splits * p.T * a->N * p.Ktot * sizeof(float);
+  return (size_t)p.splits * ((size_t)p.T * a->N * p.Ktot + a->N) * sizeof(float);
 }
 
 static int wg_tmap(CUtensorMap* tm, const pht_view& v, int B) {
@@ -267,6 +321,7 @@ int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled) {
   P.dyOy = a->dy.oy; P.dyOx = a->dy.ox;
   for (int i = 0; i < WG_MAX_KT; ++i) P.kt[i] = p.kt[i < p.n_ktiles ? i : 0];
   P.ws = (float*)a->workspace;
+  P.bias_ws = a->dbias ? P.ws + (size_t)p.splits * p.T * a->N * p.Ktot : nullptr;
   CUtensorMap tmDy, tmS[3];
   int rc = wg_tmap(&tmDy, a->dy, a->B);
   if (rc) return rc;
@@ -301,7 +356,8 @@ int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled) {
   int grid = (int)((n4 + 255) / 256);
   int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
-  wgrad_reduce_splits_kernel<<<grid, 256, 0, st>>>((const float4*)a->workspace, (float4*)a->dw, n4, p.splits);
+  wgrad_reduce_splits_kernel<<<grid + (P.bias_ws ? 1 : 0), 256, 0, st>>>((const float4*)a->workspace, (float4*)a->dw, n4, p.splits,
+                                                                       P.bias_ws, a->dbias, a->N);
   PHT_LAUNCH_CHECK();
   count_launch(CNT_WGRAD_TC);
   count_launch(CNT_OTHER);

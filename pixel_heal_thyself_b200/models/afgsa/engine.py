@@ -286,8 +286,14 @@ class AfgsaEngine:
         slopeA = self._const("slopeA", [0.0] * 256 + [LEAKY] * 512)
         npx = B * H * W
 
-        G0, G1, G2, GX, GA = (g(n, (B, H, W, C), T) for n in ("G0", "G1", "G2", "GX", "GA"))
-        GP = g("GP", (B, H + 2, W + 2, C), T)
+        # gradient ping-pong buffers live in padded frames: the fused data-gradient (PHT_EPI_PADFOLD) stores whole
+        # padded-domain tiles (frame = don't care), everything else addresses the interior views
+        Gpad = {n: g(n + "p", (B, H + 2, W + 2, C), T) for n in ("G0", "G1", "G2", "GX")}
+        G0, G1, G2, GX = (Gpad[n][:, 1:-1, 1:-1, :] for n in ("G0", "G1", "G2", "GX"))
+        pad_of = {id(G0): Gpad["G0"], id(G1): Gpad["G1"], id(G2): Gpad["G2"], id(GX): Gpad["GX"]}
+        GA = g("GA", (B, H, W, C), T)
+        fused_fold = T == torch.bfloat16 and net.padding_mode == "replicate" and not getattr(self, "no_fused_fold", False)
+        GP = None if fused_fold else g("GP", (B, H + 2, W + 2, C), T)
         dQK = g("dQK", (B, H, W, 2 * C), T)
         dV = g("dV", (B, H, W, C), T)
         dcat = g("dcat", (B, H, W, 768), T)
@@ -304,8 +310,19 @@ class AfgsaEngine:
             ops.wgrad(dy, [src_pad], w, ksize=3, dbias=G[name + ".bias"], workspace=wg_ws, src_offsets=[(1, 1)])
             ops.unpack_wgrad(G[name + ".weight"], w, ksize=3, Ntot=C, Ktot=C)
 
-        def conv3_dgrad(dy, wT):
-            ops.conv_gemm([dy], wT, C, ksize=3, out_domain=pdom, src_offsets=[(-1, -1)], out1=GP)
+        def conv3_dgrad(dy, wT, *, resid=None, mask=None, out1=None, out2=None):
+            """d(input of a padded 3x3 conv): data-gradient over the padded domain, border folded back into the
+            interior, then out1 = fold (+ resid), out2 = out1 * relu'(mask)."""
+            if fused_fold:   # one launch: the fold, residual and mask run in the GEMM epilogue
+                ops.conv_gemm([dy], wT, C, ksize=3, out_domain=pdom, src_offsets=[(-1, -1)], padfold=True,
+                              resid=resid, resid_mode="pre" if resid is not None else None,
+                              mask=mask, mslope=relu0 if mask is not None else None,
+                              out1=None if out1 is None else pad_of[id(out1)],
+                              out2=None if out2 is None else pad_of[id(out2)])
+            else:
+                ops.conv_gemm([dy], wT, C, ksize=3, out_domain=pdom, src_offsets=[(-1, -1)], out1=GP)
+                ops.pad_fold(GP, mode, resid=resid, mask=mask, mslope=relu0 if mask is not None else None,
+                             out1=out1, out2=out2)
 
         # ---- decoder -------------------------------------------------------------------------
         D1p, D2 = g("D1p", (B, H + 2, W + 2, C), T), g("D2", (B, H, W, C), T)
@@ -323,18 +340,16 @@ class AfgsaEngine:
             ops.dec_tail_bwd_data(d_out, pk["dec2"], D2, G0)                       # G0 = d(D2 pre-act)
         self._dbg("dD2pre", G0); self._dbg("d_out", d_out); self._dbg("D2", D2); self._dbg("D1", D1p)
         conv3_wgrad(G0, D1p, "decoder.1.0")
-        conv3_dgrad(G0, pk["dec1.T"])
-        ops.pad_fold(GP, mode, mask=D1p[:, 1:-1, 1:-1, :], mslope=relu0, out2=G1)   # G1 = d(D1 pre-act)
+        conv3_dgrad(G0, pk["dec1.T"], mask=D1p[:, 1:-1, 1:-1, :], out2=G1)          # G1 = d(D1 pre-act)
         self._dbg("dD1pre", G1)
         Xlast = g(f"Xp{self.num_sa}", (B, H + 2, W + 2, C), T)
         conv3_wgrad(G1, Xlast, "decoder.0.0")
         self._ready("decoder")
-        conv3_dgrad(G1, pk["dec0.T"])
         if self.num_sa > 0:
-            ops.pad_fold(GP, mode, mask=g(f"H2{self.num_sa - 1}", (B, H, W, C), T), mslope=relu0, out1=GX, out2=G0)
+            conv3_dgrad(G1, pk["dec0.T"], mask=g(f"H2{self.num_sa - 1}", (B, H, W, C), T), out1=GX, out2=G0)
             self._dbg("dXlast", GX); self._dbg("dH2pre_last", G0)
         else:
-            ops.pad_fold(GP, mode, mask=Xlast[:, 1:-1, 1:-1, :], mslope=relu0, out2=G0)
+            conv3_dgrad(G1, pk["dec0.T"], mask=Xlast[:, 1:-1, 1:-1, :], out2=G0)
 
         Af, A1 = g("A", (B, H, W, C), T), g("A1", (B, H, W, C), T)
         # ---- transformer blocks, last to first ------------------------------------------------
@@ -346,11 +361,9 @@ class AfgsaEngine:
             X = g(f"Xp{i}", (B, H + 2, W + 2, C), T)[:, 1:-1, 1:-1, :]
             # GX = d(block output) raw, G0 = d(H2 pre-act)
             conv3_wgrad(G0, H1p, pre + "feed_forward.1.0")
-            conv3_dgrad(G0, pk[f"b{i}.ff1.T"])
-            ops.pad_fold(GP, mode, mask=H1p[:, 1:-1, 1:-1, :], mslope=relu0, out2=G1)     # G1 = d(H1 pre-act)
+            conv3_dgrad(G0, pk[f"b{i}.ff1.T"], mask=H1p[:, 1:-1, 1:-1, :], out2=G1)       # G1 = d(H1 pre-act)
             conv3_wgrad(G1, X1p, pre + "feed_forward.0.0")
-            conv3_dgrad(G1, pk[f"b{i}.ff0.T"])
-            ops.pad_fold(GP, mode, resid=GX, out1=G2)                                      # G2 = dX1 = dO
+            conv3_dgrad(G1, pk[f"b{i}.ff0.T"], resid=GX, out1=G2)                          # G2 = dX1 = dO
             # attention
             ops.attn_bwd(QK[..., :C], QK[..., C:], V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], lse, G2,
                          dQK[..., :C], dQK[..., C:], dV, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,

@@ -26,11 +26,12 @@ def set_launch_profiler(sink, flt=None):
 
 
 def conv_gemm(srcs, w, N, *, ksize=1, out_domain=None, bias=None, slope=None, resid=None, resid_mode=None, mask=None,
-              mslope=None, out1=None, out2=None, src_offsets=None):
+              mslope=None, out1=None, out2=None, src_offsets=None, padfold=False):
     """pht_conv_gemm.  srcs: list of [B,H,W,C] tensors (virtual concat along C).
     out_domain: (B, Ho, Wo), default = shape of the first output.
     src_offsets: list of (oy, ox) per source (default 0,0).
-    resid_mode: None | "pre" | "post"."""
+    resid_mode: None | "pre" | "post".
+    padfold: out_domain is the padded domain, resid/mask/outputs are interior views (PHT_EPI_PADFOLD)."""
     a = L.ConvGemmArgs()
     ref = out1 if out1 is not None else out2
     L.require_cuda(*srcs, w, ref)
@@ -51,6 +52,8 @@ def conv_gemm(srcs, w, N, *, ksize=1, out_domain=None, bias=None, slope=None, re
     if mask is not None:
         a.mask = L.view(mask)
         flags |= L.EPI_MASK
+    if padfold:
+        flags |= L.EPI_PADFOLD
     a.flags = flags
     a.out1, a.out2 = L.view(out1), L.view(out2)
     if _profile_sink is not None:

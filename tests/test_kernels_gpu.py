@@ -120,6 +120,56 @@ def test_padded_conv_forward_and_backward(dtype, mode):
     assert rel_err(db, dpre.float().sum((0, 2, 3))) < 1e-4
 
 
+@pytest.mark.parametrize("B,C,N,H,W", [(2, 64, 64, 16, 24), (1, 256, 256, 32, 32), (2, 128, 64, 8, 40)])
+def test_fused_replicate_padfold_dgrad(B, C, N, H, W):
+    """PHT_EPI_PADFOLD: data-gradient of a replicate-padded 3x3 conv with the padding backward, the residual add and
+    the ReLU mask fused into the GEMM epilogue == autograd of F.pad(replicate) + conv2d, and == the unfused
+    conv_gemm + pht_pad_fold pair.  (W = 24 / 40 exercise the half-filled last 16-pixel tile column.)"""
+    ops = _ops()
+    from pixel_heal_thyself_b200._lib import PAD_MODES
+    torch.manual_seed(5)
+    dt = torch.bfloat16
+    w = torch.randn(N, C, 3, 3, device=DEV) / (9 * C) ** 0.5
+    dy = torch.randn(B, N, H, W, device=DEV).to(dt)
+    resid = torch.randn(B, C, H, W, device=DEV).to(dt)
+    mask = torch.randn(B, C, H, W, device=DEV).to(dt)
+    wq = pack(w, dt).float().view(3, 3, N, C).permute(2, 3, 0, 1).contiguous()
+    xr = torch.zeros(B, C, H, W, device=DEV, requires_grad=True)
+    F.conv2d(F.pad(xr, (1, 1, 1, 1), mode="replicate"), wq).backward(dy.float())
+    ref1 = xr.grad + resid.float()
+    ref2 = ref1 * (mask.float() > 0)
+    wT = pack(w, dt, transpose=1)
+    o1p = torch.zeros(B, H + 2, W + 2, C, dtype=dt, device=DEV)   # outputs are padded frames, results in the interior
+    o2p = torch.zeros(B, H + 2, W + 2, C, dtype=dt, device=DEV)
+    o1, o2 = o1p[:, 1:-1, 1:-1, :], o2p[:, 1:-1, 1:-1, :]
+    ops.conv_gemm([nhwc(dy)], wT, C, ksize=3, out_domain=(B, H + 2, W + 2), src_offsets=[(-1, -1)], padfold=True,
+                  resid=nhwc(resid), resid_mode="pre", mask=nhwc(mask), mslope=torch.zeros(C, device=DEV), out1=o1p, out2=o2p)
+    assert rel_err(nchw(o1), ref1) < 2.5e-2
+    assert rel_err(nchw(o2), ref2) < 2.5e-2
+    # against the unfused pair (same bf16 rounding points up to the border values)
+    gp = torch.empty(B, H + 2, W + 2, C, dtype=dt, device=DEV)
+    ops.conv_gemm([nhwc(dy)], wT, C, ksize=3, out_domain=(B, H + 2, W + 2), src_offsets=[(-1, -1)], out1=gp)
+    u1 = torch.empty_like(o1)
+    u2 = torch.empty_like(o2)
+    ops.pad_fold(gp, PAD_MODES["replicate"], resid=nhwc(resid), mask=nhwc(mask), mslope=torch.zeros(C, device=DEV),
+                 out1=u1, out2=u2)
+    assert rel_err(o1.contiguous(), u1) < 1e-2 and rel_err(o2.contiguous(), u2) < 1e-2
+    # single output, mask only (the decoder / feed-forward uses)
+    o3p = torch.zeros(B, H + 2, W + 2, C, dtype=dt, device=DEV)
+    ops.conv_gemm([nhwc(dy)], wT, C, ksize=3, out_domain=(B, H + 2, W + 2), src_offsets=[(-1, -1)], padfold=True,
+                  mask=nhwc(mask), mslope=torch.zeros(C, device=DEV), out2=o3p)
+    assert rel_err(nchw(o3p[:, 1:-1, 1:-1, :]), xr.grad * (mask.float() > 0)) < 2.5e-2
+
+
+def test_padfold_flag_is_refused_off_the_tensor_core_path():
+    ops = _ops()
+    x = torch.randn(1, 10, 10, 64, device=DEV)
+    w = torch.randn(9, 64, 64, device=DEV)
+    out = torch.empty(1, 8, 8, 64, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.conv_gemm([x], w, 64, ksize=3, out_domain=(1, 10, 10), padfold=True, out1=out)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_gemm_virtual_concat_and_epilogues(dtype):
     ops = _ops()
