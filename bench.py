@@ -36,6 +36,20 @@ TRAIN_FLOP_PER_PX = 58_639_872      # fwd + dgrad + wgrad, BASELINE.md section 4
 CONV3_FLOP_PER_PX = 2 * 9 * 256 * 256
 
 
+def _traffic():
+    """Measured DRAM bytes per launch of the roofline kernel (ncu --set full capture, profiles/traffic.json):
+    launch-weighted mean over the two variants of the 3x3 256->256 conv_gemm that run in a step."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    n = t["launches_per_step"]
+    mean = (t["conv3x3_deep_bytes"] * n["deep"] + t["conv3x3_fused_bytes"] * n["fused"]) / (n["deep"] + n["fused"])
+    return mean, {"deep": t["conv3x3_deep_bytes"], "fused_epilogue": t["conv3x3_fused_bytes"], "unit": "bytes/launch",
+                  "source": "profiles/r1_ncu_full_conv3x3.txt"}
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -262,7 +276,8 @@ def run_ours(args):
         "launch_counters": counters,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm 3x3 256->256 (forward + data-grad launches)",
                      "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": (ach / peaks["tf_sustained"]) if ach else None, "traffic": None,
+                     "frac": (ach / peaks["tf_sustained"]) if ach else None, "traffic": _traffic()[0],
+                     "traffic_detail": _traffic()[1],
                      "peak_source": f"{peaks['src']} sustained bf16", "launches_timed": len(conv_ms),
                      "avg_launch_ms": conv_avg_ms, "algorithmic_flop_per_launch": conv_flop,
                      "share_of_step": (sum(conv_ms) / ms) if conv_ms else None},

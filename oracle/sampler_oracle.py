@@ -145,3 +145,92 @@ def crop_patches(frame_nhwc: np.ndarray, centres: np.ndarray, patch_size: int) -
     for i, (px, py) in enumerate(centres):
         out[i] = frame_nhwc[py - half:py + half, px - half:px + half, :]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# importance sampling (preprocessing.py:119-168, 223-322)
+# ---------------------------------------------------------------------------------------------------------------
+def _reflect_index(i: np.ndarray, n: int) -> np.ndarray:
+    """scipy.ndimage mode='reflect' (half-sample symmetric: d c b a | a b c d | d c b a)."""
+    i = np.where(i < 0, -i - 1, i)
+    return np.where(i >= n, 2 * n - 1 - i, i)
+
+
+def uniform_filter1d(a: np.ndarray, size: int, axis: int) -> np.ndarray:
+    """scipy.ndimage.uniform_filter1d (scipy 1.15.2 pinned by the reference's uv.lock; third-party, restated):
+    out[i] = mean(a[i - size//2 : i - size//2 + size]) with 'reflect' borders, accumulated in double, result in
+    the input dtype."""
+    n = a.shape[axis]
+    idx = np.arange(n)[:, None] - size // 2 + np.arange(size)[None, :]           # [n, size]
+    g = np.take(a.astype(np.float64), _reflect_index(idx, n).reshape(-1), axis=axis)
+    shape = list(a.shape)
+    shape[axis:axis + 1] = [n, size]
+    return (g.reshape(shape).sum(axis=axis + 1) / size).astype(a.dtype)
+
+
+def uniform_filter_pp1(buffer: np.ndarray, patch_size: int) -> np.ndarray:
+    """ndimage.uniform_filter(buffer, size=(P, P, 1)): separable, axis 0 then axis 1, intermediate in buffer.dtype."""
+    return uniform_filter1d(uniform_filter1d(buffer, patch_size, 0), patch_size, 1)
+
+
+def variance_map(buffer: np.ndarray, patch_size: int, relative: bool) -> np.ndarray:
+    """get_variance_map, preprocessing.py:119-140 (float32 arithmetic like the reference's arrays)."""
+    mean = uniform_filter_pp1(buffer, patch_size)
+    square_mean = uniform_filter_pp1(buffer ** 2, patch_size)
+    variance = np.maximum(square_mean - mean ** 2, 0)
+    if relative:
+        variance = variance / np.maximum(mean ** 2, 1e-4)
+    variance = variance.max(axis=2)
+    variance = np.minimum(variance ** (1.0 / 2.2), 1.0)
+    return variance / np.maximum(variance.max(), 1e-4)
+
+
+def importance_map(noisy: np.ndarray, normal: np.ndarray, patch_size: int) -> np.ndarray:
+    """get_importance_map as called by importance_sampling (preprocessing.py:143-168, 293-300):
+    relative variance of the noisy radiance + variance of the normals, weights 1, normalised by the maximum."""
+    imp = variance_map(noisy, patch_size, True) * 1.0
+    imp += variance_map(normal, patch_size, False) * 1.0
+    return imp / np.max(imp)
+
+
+def region_list(shape, step):
+    """get_region_list, preprocessing.py:223-238: serpentine scan of step x step regions as (x0, x1, y0, y1)."""
+    regions = []
+    for y in range(0, shape[0], step):
+        xs = list(range(0, shape[1], step))
+        if (y // step) % 2 == 1:
+            xs.reverse()
+        regions.extend((x, x + step, y, y + step) for x in xs)
+    return regions
+
+
+def prune_patches(shape, centres: np.ndarray, patch_size: int, imp: np.ndarray, rng) -> np.ndarray:
+    """prune_patches + split_patches, preprocessing.py:241-281: error-diffusion thinning.  Region bounds are
+    inclusive on both sides; the arithmetic is numpy float32 scalar arithmetic (NEP 50, numpy 2.2.4 pinned): the error
+    accumulator is float32 and rng.random() is rounded to float32 for the comparison."""
+    remain = [tuple(int(v) for v in p) for p in centres]
+    kept = []
+    error = np.float32(0.0)
+    for (x0, x1, y0, y1) in region_list(shape, 4 * patch_size):
+        current = [p for p in remain if x0 <= p[0] <= x1 and y0 <= p[1] <= y1]
+        remain = [p for p in remain if not (x0 <= p[0] <= x1 and y0 <= p[1] <= y1)]
+        for (x, y) in current:
+            v = np.float32(imp[y, x])
+            if np.float32(v - error) > np.float32(rng.random()):
+                kept.append((x, y))
+                error = np.float32(error + np.float32(np.float32(1.0) - v))
+            else:
+                error = np.float32(error + np.float32(np.float32(0.0) - v))
+    return np.array(kept, dtype=np.int64).reshape(-1, 2)
+
+
+def importance_sampling(noisy: np.ndarray, normal: np.ndarray, patch_size: int, num_patches: int, rng,
+                        imp: np.ndarray | None = None) -> np.ndarray:
+    """importance_sampling, preprocessing.py:284-322 -> kept patch CENTRES [x, y] in processing order.
+    ``rng`` needs randint and random (MT19937 above or random.Random); the map can be passed in precomputed."""
+    if imp is None:
+        imp = importance_map(noisy, normal, patch_size)
+    corners = dart_throwing(noisy.shape[:2], patch_size, num_patches, rng)
+    pad = patch_size // 2
+    pruned = np.maximum(0, prune_patches(noisy.shape[:2], corners + pad, patch_size, imp, rng) - pad)
+    return pruned + pad

@@ -51,7 +51,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmR,
                    const __grid_constant__ CUtensorMap tmO, const AtP P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
   uint8_t* Qs = smem;                                   // [2][64 x 128B]
   uint8_t* Ks = Qs + 2 * AT_Q_BYTES;                    // [2][240 x 128B]
   uint8_t* Vs = Ks + 2 * AT_K_BYTES;                    // [2][208 x 128B]
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AbP P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
   uint8_t* Qs = smem;
   uint8_t* dOs = Qs + AB_Q_BYTES;
   uint8_t* Ks = dOs + AB_Q_BYTES;

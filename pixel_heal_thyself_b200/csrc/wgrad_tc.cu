@@ -50,7 +50,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmS1, const __grid_constant__ CUtensorMap tmS2, const WgP P) {
   using Cfg = WgCfg<MH>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::STAGES;
@@ -150,17 +150,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
       uint32_t phase = 0;
       for (int i = 0; i < npt; ++i) {
         mbar_wait(&full_bar[stage], phase);
-        const uint8_t* a_base = smem + stage * Cfg::STAGE_BYTES;
+        const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
 #pragma unroll
         for (int h = 0; h < MH; ++h) {
-          const uint8_t* box = a_base + (h * 4 + ew) * WG_BOX_BYTES;   // boxes ew and ew+4 (MH = 2): 4 warps x MH boxes
+          const uint32_t box = a_base + (h * 4 + ew) * WG_BOX_BYTES + ((lane & 3) << 2);   // 4 warps x MH boxes
           if (h * 4 + ew < 2 * MH) {
-#pragma unroll 8
-            for (int r = 0; r < WG_PIX; ++r) {
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(box + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
-              bs[h][0] += __uint_as_float(u << 16);
-              bs[h][1] += __uint_as_float(u & 0xffff0000u);
+            float e0 = 0.f, e1 = 0.f, o0 = 0.f, o1 = 0.f;   // two independent add chains per channel
+#pragma unroll
+            for (int r = 0; r < WG_PIX; r += 2) {
+              uint32_t u, w;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u) : "r"(box + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(box + (r + 1) * 128 + (((lane >> 2) ^ ((r + 1) & 7)) << 4)));
+              e0 += __uint_as_float(u << 16);
+              e1 += __uint_as_float(u & 0xffff0000u);
+              o0 += __uint_as_float(w << 16);
+              o1 += __uint_as_float(w & 0xffff0000u);
             }
+            bs[h][0] += e0 + o0;
+            bs[h][1] += e1 + o1;
           }
         }
         __syncwarp();
