@@ -284,6 +284,25 @@ int pht_cast2d(const void* src, int32_t src_dtype, int64_t src_ld, void* dst, in
 int pht_sample_patches(const int64_t* seeds, int32_t n_img, int32_t Hf, int32_t Wf, int32_t P, int32_t n,
                        int32_t max_iter, int32_t* out, void* stream);
 
+/* Importance map of the patch sampler (get_importance_map as called by importance_sampling,
+ * preprocessing.py:119-168, 293-300): relative variance of the noisy radiance + variance of the normals over a
+ * P x P box (scipy.ndimage.uniform_filter semantics: 'reflect' borders, window [i-P/2, i-P/2+P), double accumulation,
+ * float32 after each separable pass), channel max, gamma 1/2.2, each map and the sum normalised by its maximum.
+ * noisy_f [n_img][Hf][Wf][3], aux_f [n_img][Hf][Wf][7] (normal = channels 0..2) are the raw frames (the cleaning of
+ * preprocess_data, :97-103, is applied on the fly); imp fp32 [n_img][Hf][Wf] is OVERWRITTEN.
+ * workspace: pht_importance_map_ws_bytes() bytes. */
+size_t pht_importance_map_ws_bytes(int32_t n_img, int32_t Hf, int32_t Wf);
+int pht_importance_map(const float* noisy_f, const float* aux_f, int32_t n_img, int32_t Hf, int32_t Wf, int32_t P,
+                       float* imp, void* workspace, size_t workspace_bytes, void* stream);
+
+/* importance_sampling(data, P, n, random.Random(seed)) of preprocessing.py:284-322, bit-exact given the map:
+ * pht_sample_patches' dart throwing followed, on the same RNG stream, by prune_patches (:259-281: serpentine
+ * 4P-regions with inclusive bounds, float32 error diffusion against random.random()).
+ * out_centres int32 [n_img][n][2] = kept patch CENTRES (x, y) in the reference's order, -1 padded;
+ * out_counts int32 [n_img] = number kept (-1 if dart throwing failed). */
+int pht_importance_sample(const int64_t* seeds, int32_t n_img, int32_t Hf, int32_t Wf, int32_t P, int32_t n,
+                          int32_t max_iter, const float* imp, int32_t* out_centres, int32_t* out_counts, void* stream);
+
 /* Introspection */
 int pht_abi_version(void);
 const char* pht_last_error(void);

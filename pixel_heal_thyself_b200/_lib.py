@@ -92,6 +92,9 @@ SYMBOLS = {
     "pht_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "pht_cast2d": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
     "pht_sample_patches": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "pht_importance_map_ws_bytes": (_sz, [_i32, _i32, _i32]),
+    "pht_importance_map": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "pht_importance_sample": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "pht_abi_version": (C.c_int, []),
     "pht_last_error": (C.c_char_p, []),
     "pht_get_counters": (None, [C.POINTER(C.c_uint64)]),

@@ -93,26 +93,14 @@ __device__ __forceinline__ int mt_randbelow(Mt& g, int n, int lane) {
   return (int)r;
 }
 
-__global__ void __launch_bounds__(32) sample_patches_kernel(const long long* __restrict__ seeds, int Hf, int Wf, int P,
-                                                            int n, int max_iter, int* __restrict__ out) {
-  extern __shared__ uint32_t smem_u[];
-  uint32_t* mt = smem_u;
-  int* px = (int*)(mt + MT_N);
-  int* py = px + n;
-  const int lane = threadIdx.x;
-  const int img = blockIdx.x;
-  Mt g;
-  g.mt = mt;
-  long long s = seeds[img];
-  mt_seed(g, (unsigned long long)(s < 0 ? -s : s), lane);
-
+// dart throwing with the warp-uniform RNG; px/py in shared memory.  Returns false if the radius shrank > 1e5 times.
+__device__ bool dart_throw(Mt& g, int lane, int Hf, int Wf, int P, int n, int max_iter, int* px, int* py) {
   // preprocessing.py:187-192 in IEEE double, same operation order
   double radius = sqrt(((double)((long long)Hf * Wf) / (double)n) / 3.141592653589793);
   double min_sq = (2.0 * radius) * (2.0 * radius);
   const int x_span = Wf - P - 1 + 1, y_span = Hf - P - 1 + 1;  // randint(0, max) -> randbelow(max + 1)
   int shrinks = 0;
-  bool failed = false;
-  for (int idx = 0; idx < n && !failed; ++idx) {
+  for (int idx = 0; idx < n; ++idx) {
     bool done = false;
     while (!done) {
       for (int it = 0; it < max_iter; ++it) {
@@ -139,14 +127,99 @@ __global__ void __launch_bounds__(32) sample_patches_kernel(const long long* __r
       if (!done) {
         radius *= 0.96;
         min_sq = (2.0 * radius) * (2.0 * radius);
-        if (++shrinks > 100000) { failed = true; break; }
+        if (++shrinks > 100000) return false;
       }
     }
   }
+  return true;
+}
+
+__global__ void __launch_bounds__(32) sample_patches_kernel(const long long* __restrict__ seeds, int Hf, int Wf, int P,
+                                                            int n, int max_iter, int* __restrict__ out) {
+  extern __shared__ uint32_t smem_u[];
+  uint32_t* mt = smem_u;
+  int* px = (int*)(mt + MT_N);
+  int* py = px + n;
+  const int lane = threadIdx.x;
+  const int img = blockIdx.x;
+  Mt g;
+  g.mt = mt;
+  long long s = seeds[img];
+  mt_seed(g, (unsigned long long)(s < 0 ? -s : s), lane);
+  const bool ok = dart_throw(g, lane, Hf, Wf, P, n, max_iter, px, py);
   for (int i = lane; i < n; i += 32) {
-    out[((long long)img * n + i) * 2 + 0] = failed ? -1 : px[i];
-    out[((long long)img * n + i) * 2 + 1] = failed ? -1 : py[i];
+    out[((long long)img * n + i) * 2 + 0] = ok ? px[i] : -1;
+    out[((long long)img * n + i) * 2 + 1] = ok ? py[i] : -1;
   }
+}
+
+// random.random(): 53-bit double from two draws (CPython _random.c: (a >> 5, b >> 6))
+__device__ __forceinline__ double mt_random(Mt& g, int lane) {
+  const uint32_t a = mt_u32(g, lane) >> 5, b = mt_u32(g, lane) >> 6;
+  return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+
+// importance_sampling (preprocessing.py:284-322): dart throwing, then prune_patches (:259-281) on the SAME RNG stream:
+// regions of 4P x 4P pixels in serpentine order (:223-238), a patch belongs to the first region whose INCLUSIVE bounds
+// contain its centre (:241-256); error diffusion in numpy-float32 scalar arithmetic (NEP 50), rng.random() rounded to
+// float32 for the comparison.  Everything is warp-uniform (the RNG state is shared), the loop is serial like the reference.
+__global__ void __launch_bounds__(32) importance_sample_kernel(const long long* __restrict__ seeds, int Hf, int Wf, int P,
+                                                               int n, int max_iter, const float* __restrict__ imp,
+                                                               int* __restrict__ out, int* __restrict__ counts) {
+  extern __shared__ uint32_t smem_u[];
+  uint32_t* mt = smem_u;
+  int* px = (int*)(mt + MT_N);
+  int* py = px + n;
+  float* iv = (float*)(py + n);
+  int* state = (int*)(iv + n);    // 0 = not yet visited, 1 = visited
+  const int lane = threadIdx.x;
+  const int img = blockIdx.x;
+  Mt g;
+  g.mt = mt;
+  long long s = seeds[img];
+  mt_seed(g, (unsigned long long)(s < 0 ? -s : s), lane);
+  const bool ok = dart_throw(g, lane, Hf, Wf, P, n, max_iter, px, py);
+  int* o = out + (long long)img * n * 2;
+  for (int i = lane; i < 2 * n; i += 32) o[i] = -1;
+  if (!ok) {
+    if (lane == 0) counts[img] = -1;
+    return;
+  }
+  const int pad = P / 2;
+  for (int i = lane; i < n; i += 32) {
+    px[i] += pad;                 // centres (importance_sampling: patches + pad)
+    py[i] += pad;
+    iv[i] = imp[((long long)img * Hf + py[i]) * Wf + px[i]];
+    state[i] = 0;
+  }
+  __syncwarp();
+  const int step = 4 * P;
+  int count = 0;
+  float error = 0.f;
+  for (int ry = 0, row = 0; ry < Hf; ry += step, ++row) {
+    const int ncol = (Wf + step - 1) / step;
+    for (int k = 0; k < ncol; ++k) {
+      const int rx = ((row & 1) ? (ncol - 1 - k) : k) * step;
+      for (int i = 0; i < n; ++i) {
+        if (state[i]) continue;
+        const int x = px[i], y = py[i];
+        if (!(rx <= x && x <= rx + step && ry <= y && y <= ry + step)) continue;
+        __syncwarp();
+        if (lane == 0) state[i] = 1;
+        const float v = iv[i];
+        const float u = (float)mt_random(g, lane);
+        if (__fsub_rn(v, error) > u) {
+          if (lane == 0) { o[count * 2] = x; o[count * 2 + 1] = y; }
+          ++count;
+          error = __fadd_rn(error, __fsub_rn(1.0f, v));
+        } else {
+          error = __fadd_rn(error, __fsub_rn(0.0f, v));
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) counts[img] = count;
 }
 
 }  // namespace pht
@@ -161,6 +234,21 @@ extern "C" int pht_sample_patches(const int64_t* seeds, int32_t n_img, int32_t H
   size_t smem = MT_N * sizeof(uint32_t) + 2 * (size_t)n * sizeof(int);
   PHT_CUDA(cudaFuncSetAttribute(sample_patches_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sample_patches_kernel<<<n_img, 32, smem, (cudaStream_t)stream>>>((const long long*)seeds, Hf, Wf, P, n, max_iter, out);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+extern "C" int pht_importance_sample(const int64_t* seeds, int32_t n_img, int32_t Hf, int32_t Wf, int32_t P, int32_t n,
+                                     int32_t max_iter, const float* imp, int32_t* out_centres, int32_t* out_counts,
+                                     void* stream) {
+  PHT_CHECK_ARG(seeds && imp && out_centres && out_counts && n_img > 0 && n > 0 && max_iter > 0, "importance_sample: bad args");
+  PHT_CHECK_ARG(Wf - P - 1 >= 0 && Hf - P - 1 >= 0, "importance_sample: patch larger than frame");
+  PHT_CHECK_ARG(n <= 8192, "importance_sample: at most 8192 patches per image");
+  size_t smem = MT_N * sizeof(uint32_t) + 4 * (size_t)n * sizeof(int);
+  PHT_CUDA(cudaFuncSetAttribute(importance_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  importance_sample_kernel<<<n_img, 32, smem, (cudaStream_t)stream>>>((const long long*)seeds, Hf, Wf, P, n, max_iter, imp,
+                                                                      out_centres, out_counts);
   count_launch(CNT_OTHER);
   PHT_LAUNCH_CHECK();
   return PHT_OK;

@@ -32,7 +32,7 @@ struct WgP {
   int srcOy[3], srcOx[3];
   WgKTile kt[WG_MAX_KT];
   float* ws;       // [splits][T][N][Ktot]
-  float* bias_ws;  // [splits][N] partial column sums of dy, or nullptr
+  float* bias_ws;  // [splits][T][N] partial column sums of dy, or nullptr
 };
 
 template <int MH> struct WgCfg {
@@ -70,8 +70,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
   const int pt_beg = split * P.ptiles_per_split;
   const int pt_end = min(pt_beg + P.ptiles_per_split, P.ptiles_total);
   const int npt = pt_end - pt_beg;
-  // this job also produces the bias-gradient partial of its (split, n-tile): centre tap, first k-tile
-  const bool do_bias = P.bias_ws != nullptr && kti == 0 && t == (P.T >> 1);
+  // this job also produces a bias-gradient partial of its (split, n-tile): first k-tile only
+  // (the T tap-jobs of a split stream the same dy tiles: job t sums every T-th tile, so the work is spread evenly)
+  const bool do_bias = P.bias_ws != nullptr && kti == 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmDy);
@@ -151,10 +152,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
       for (int i = 0; i < npt; ++i) {
         mbar_wait(&full_bar[stage], phase);
         const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const bool mine = (pt_beg + i) % P.T == t;
 #pragma unroll
         for (int h = 0; h < MH; ++h) {
           const uint32_t box = a_base + (h * 4 + ew) * WG_BOX_BYTES + ((lane & 3) << 2);   // 4 warps x MH boxes
-          if (h * 4 + ew < 2 * MH) {
+          if (mine && h * 4 + ew < 2 * MH) {
             float e0 = 0.f, e1 = 0.f, o0 = 0.f, o1 = 0.f;   // two independent add chains per channel
 #pragma unroll
             for (int r = 0; r < WG_PIX; r += 2) {
@@ -178,7 +180,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
       for (int h = 0; h < MH; ++h) {
         const int bidx = h * 4 + ew;
         if (bidx < 2 * MH) {
-          float* dst = P.bias_ws + (size_t)split * P.N + n0 + bidx * 64 + lane * 2;
+          float* dst = P.bias_ws + ((size_t)split * P.T + t) * P.N + n0 + bidx * 64 + lane * 2;
           dst[0] = bs[h][0];
           dst[1] = bs[h][1];
         }
@@ -219,11 +221,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
 
 // fixed-order (deterministic) sum of the split partials; the LAST block reduces the bias partials [splits][N]
 __global__ void wgrad_reduce_splits_kernel(const float4* __restrict__ ws, float4* __restrict__ dw, long long n4, int splits,
-                                           const float* __restrict__ bias_ws, float* __restrict__ dbias, int N) {
+                                           const float* __restrict__ bias_ws, int bias_rows, float* __restrict__ dbias, int N) {
   if (bias_ws != nullptr && blockIdx.x == gridDim.x - 1) {
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
       float a = 0.f;
-      for (int s = 0; s < splits; ++s) a += bias_ws[(long long)s * N + n];
+      for (int s = 0; s < bias_rows; ++s) a += bias_ws[(long long)s * N + n];
       dbias[n] = a;
     }
     return;
@@ -290,7 +292,7 @@ static WgPlan wg_plan(const pht_wgrad_args* a, size_t ws_limit_bytes) {
   // one CTA per SM (192 KB of smem): never spill a few jobs into a second wave
   int splits = base_jobs >= sms ? 1 : sms / base_jobs;
   if (splits > p.ptiles_total) splits = p.ptiles_total;
-  size_t per_split_bytes = ((size_t)p.T * a->N * p.Ktot + a->N) * sizeof(float);   // + one bias partial row
+  size_t per_split_bytes = ((size_t)p.T * a->N * p.Ktot + (size_t)p.T * a->N) * sizeof(float);   // + T bias partial rows
   if (ws_limit_bytes > 0) {
     size_t max_splits = ws_limit_bytes / per_split_bytes;
     if (max_splits < 1) return p;
@@ -306,7 +308,7 @@ static WgPlan wg_plan(const pht_wgrad_args* a, size_t ws_limit_bytes) {
 size_t wgrad_tc_workspace_bytes(const pht_wgrad_args* a) {
   WgPlan p = wg_plan(a, 0);
   if (!p.ok) return 0;
-  return (size_t)p.splits * ((size_t)p.T * a->N * p.Ktot + a->N) * sizeof(float);
+  return (size_t)p.splits * ((size_t)p.T * a->N * p.Ktot + (size_t)p.T * a->N) * sizeof(float);
 }
 
 static int wg_tmap(CUtensorMap* tm, const pht_view& v, int B) {
@@ -364,7 +366,7 @@ int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled) {
   int cap = sm_count() * 8;
   if (grid > cap) grid = cap;
   wgrad_reduce_splits_kernel<<<grid + (P.bias_ws ? 1 : 0), 256, 0, st>>>((const float4*)a->workspace, (float4*)a->dw, n4, p.splits,
-                                                                       P.bias_ws, a->dbias, a->N);
+                                                                       P.bias_ws, p.splits * p.T, a->dbias, a->N);
   PHT_LAUNCH_CHECK();
   count_launch(CNT_WGRAD_TC);
   count_launch(CNT_OTHER);

@@ -8,7 +8,8 @@ BASELINE.json asks for synthetic EXR-shaped tensors, so here:
 
 * ``synthetic_frames`` makes radiance + aux frames of the reference's layout
   (NHWC fp32: noisy/gt 3 ch, aux = normal(3) | depth(1) | albedo(3));
-* patch positions come from the bit-exact CUDA dart-throwing sampler;
+* patch positions come from the CUDA importance sampler (importance map + bit-exact dart throwing and
+  error-diffusion pruning, preprocessing.py:119-322);
 * ``PatchDataset.batch_device`` gathers + preprocesses a batch straight from
   the HBM-resident frames in one fused pass (``pht_crop_preprocess``);
 * ``PatchDataset.batch_host`` returns the raw NHWC patches in pinned host
@@ -45,15 +46,30 @@ def synthetic_frames(num_images: int, height: int, width: int, seed: int, device
 class PatchDataset:
     """Frames resident in HBM + sampled patch centres."""
 
-    def __init__(self, frames: dict[str, torch.Tensor], patch_size: int, num_patches: int, seed: int):
+    def __init__(self, frames: dict[str, torch.Tensor], patch_size: int, num_patches: int, seed: int,
+                 importance: bool = True):
+        """``importance=True`` is the reference's get_cropped_patches (preprocessing.py:347-359): dart throwing
+        followed by importance pruning, so every image yields <= num_patches patches; ``False`` keeps every dart."""
         self.frames, self.P = frames, patch_size
         dev = frames["noisy"].device
         n_img, hf, wf, _ = frames["noisy"].shape
         seeds = torch.arange(n_img, dtype=torch.int64, device=dev) + seed
-        corners = ops.sample_patches(seeds, (hf, wf), patch_size, num_patches)       # [n_img, n, 2] (x, y)
-        # importance_sampling() shifts corners by P/2 to centres (preprocessing.py:309-322)
-        self.centres = (corners + patch_size // 2).reshape(-1, 2).contiguous()
-        self.img_idx = torch.arange(n_img, dtype=torch.int32, device=dev).repeat_interleave(num_patches).contiguous()
+        img = torch.arange(n_img, dtype=torch.int32, device=dev).repeat_interleave(num_patches)
+        if importance:
+            self.importance_map = ops.importance_map(frames["noisy"], frames["aux"], patch_size)
+            centres, counts = ops.importance_sample(seeds, self.importance_map, patch_size, num_patches)
+            if bool((counts < 0).any()):
+                raise RuntimeError("patch sampler: dart throwing did not converge")
+            keep = (centres[:, :, 0] >= 0).reshape(-1)
+            self.centres = centres.reshape(-1, 2)[keep].contiguous()
+            self.img_idx = img[keep].contiguous()
+            self.counts = counts
+        else:
+            corners = ops.sample_patches(seeds, (hf, wf), patch_size, num_patches)       # [n_img, n, 2] (x, y)
+            # importance_sampling() shifts corners by P/2 to centres (preprocessing.py:309-322)
+            self.centres = (corners + patch_size // 2).reshape(-1, 2).contiguous()
+            self.img_idx = img.contiguous()
+            self.counts = torch.full((n_img,), num_patches, dtype=torch.int32, device=dev)
         self._host = None
 
     def __len__(self) -> int:

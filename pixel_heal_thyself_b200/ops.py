@@ -312,3 +312,29 @@ def sample_patches(seeds, frame_hw, P, n, max_iter=5000):
     L.check(lib.pht_sample_patches(seeds.data_ptr(), seeds.numel(), frame_hw[0], frame_hw[1], P, n, max_iter,
                                    out.data_ptr(), L.stream_ptr()), "pht_sample_patches")
     return out
+
+
+def importance_map(noisy_f, aux_f, P):
+    """frames [n_img, Hf, Wf, 3] / [n_img, Hf, Wf, 7] fp32 (raw, HBM-resident) -> importance map fp32 [n_img, Hf, Wf]."""
+    L.require_cuda(noisy_f, aux_f)
+    assert noisy_f.is_contiguous() and aux_f.is_contiguous() and noisy_f.dtype == torch.float32 and aux_f.dtype == torch.float32
+    n_img, Hf, Wf, _ = noisy_f.shape
+    imp = torch.empty(n_img, Hf, Wf, dtype=torch.float32, device=noisy_f.device)
+    nbytes = int(lib.pht_importance_map_ws_bytes(n_img, Hf, Wf))
+    ws = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=noisy_f.device)
+    L.check(lib.pht_importance_map(noisy_f.data_ptr(), aux_f.data_ptr(), n_img, Hf, Wf, P, imp.data_ptr(), ws.data_ptr(),
+                                   ws.numel() * 4, L.stream_ptr()), "pht_importance_map")
+    return imp
+
+
+def importance_sample(seeds, imp, P, n, max_iter=5000):
+    """seeds int64 [n_img] (CUDA), imp fp32 [n_img, Hf, Wf] -> (centres int32 [n_img, n, 2] (-1 padded), counts int32 [n_img])."""
+    L.require_cuda(seeds, imp)
+    assert seeds.dtype == torch.int64 and imp.dtype == torch.float32 and imp.is_contiguous()
+    n_img, Hf, Wf = imp.shape
+    assert seeds.numel() == n_img
+    out = torch.empty(n_img, n, 2, dtype=torch.int32, device=seeds.device)
+    counts = torch.empty(n_img, dtype=torch.int32, device=seeds.device)
+    L.check(lib.pht_importance_sample(seeds.data_ptr(), n_img, Hf, Wf, P, n, max_iter, imp.data_ptr(), out.data_ptr(),
+                                      counts.data_ptr(), L.stream_ptr()), "pht_importance_sample")
+    return out, counts

@@ -441,3 +441,47 @@ def test_sampler_many_images_matches_oracle():
     # Poisson-disk property at full size: all accepted points are distinct
     big = ops.sample_patches(torch.tensor([5], dtype=torch.int64, device=DEV), (1024, 1024), 128, 400)[0].cpu().numpy()
     assert len({tuple(p) for p in big}) == 400 and big.min() >= 0 and big.max() <= 1024 - 128 - 1
+
+
+def test_importance_map_and_sampling_match_reference_golden():
+    """pht_importance_map ~ reference map (float, <= 2e-6 abs on a [0,1] map) and pht_importance_sample == the
+    reference's kept patch centres bit for bit (dart throwing + prune on one MT19937 stream), from the GPU map."""
+    ops = _ops()
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from importance_inputs import CASES, SEEDS, frames
+    g = load_npz("importance.npz")
+    for name, (h, w, p, n) in CASES.items():
+        noisy, normal, aux = frames(h, w)
+        # raw frames may hold NaN normals / negative radiance: the kernel applies preprocess_data's cleaning
+        raw_aux = aux.copy()
+        raw_noisy = noisy.copy()
+        noisy_d = torch.from_numpy(np.stack([raw_noisy, raw_noisy])).to(DEV)
+        aux_d = torch.from_numpy(np.stack([raw_aux, raw_aux])).to(DEV)
+        imp = ops.importance_map(noisy_d, aux_d, p)
+        ref = torch.from_numpy(g[f"{name}__imp"]).to(DEV)
+        assert float((imp[0] - ref).abs().max()) < 2e-6, name
+        assert torch.equal(imp[0], imp[1])
+        # (not bit-identical: numpy's float32 power is a SIMD routine that is itself 1-2 ulp off correct rounding)
+        assert float((imp[0] - ref).abs().mean()) < 1e-7, name
+        for s0, s1 in ((SEEDS[0], SEEDS[1]), (SEEDS[2], SEEDS[3])):
+            seeds = torch.tensor([s0, s1], dtype=torch.int64, device=DEV)
+            centres, counts = ops.importance_sample(seeds, imp, p, n)
+            for k, seed in enumerate((s0, s1)):
+                want = g[f"{name}__seed{seed}"]
+                assert int(counts[k]) == len(want), (name, seed)
+                assert np.array_equal(centres[k, :len(want)].cpu().numpy(), want), (name, seed)
+                assert bool((centres[k, len(want):] == -1).all())
+
+
+def test_importance_map_cleans_nan_normals_and_negative_radiance():
+    ops = _ops()
+    from oracle import sampler_oracle as S
+    rs = np.random.default_rng(7)
+    h, w, p = 64, 96, 32
+    noisy = rs.standard_normal((h, w, 3)).astype(np.float32)          # negative values: clipped at 0 by preprocess_data
+    aux = rs.uniform(-1, 1, (h, w, 7)).astype(np.float32)
+    aux[rs.uniform(size=(h, w, 7)) < 0.02] = np.nan
+    imp = ops.importance_map(torch.from_numpy(noisy[None]).to(DEV), torch.from_numpy(aux[None]).to(DEV), p)
+    ref = S.importance_map(np.clip(np.nan_to_num(noisy), 0, None), np.nan_to_num(aux[..., :3]), p)
+    assert float((imp[0].cpu() - torch.from_numpy(ref)).abs().max()) < 2e-6

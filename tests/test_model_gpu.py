@@ -211,7 +211,7 @@ def test_trainer_gan_step_runs_and_learns():
     tr = AFGSATrainer(cfg)
     tr.setup()
     ds = tr.setup_data()
-    assert len(ds) == 16
+    assert 8 <= len(ds) <= 16 and len(ds) == int(ds.counts.sum())   # importance pruning keeps a subset of the 16 darts
     idx = torch.arange(2, device=tr.device)
     noisy, gt, aux = ds.batch_device(idx)
     assert noisy.shape == (2, 3, 32, 32) and aux.shape == (2, 7, 32, 32) and not torch.isnan(aux).any()

@@ -100,3 +100,28 @@ def test_adam_oracle_matches_torch():
         opt.step()
         O.adam_step(p, g, m, v, step, 1e-3)
     assert (p - ref.detach()).abs().max() < 1e-6
+
+
+def test_importance_map_and_sampling_match_reference_golden():
+    """oracle importance map / prune (scipy uniform_filter restated in numpy) == fixtures from the real reference, bit for bit."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from importance_inputs import CASES, SEEDS, frames
+    g = load_npz("importance.npz")
+    for name, (h, w, p, n) in CASES.items():
+        noisy, normal, _ = frames(h, w)
+        imp = S.importance_map(noisy, normal, p)
+        assert np.array_equal(imp, g[f"{name}__imp"]), name
+        for seed in SEEDS[:2]:
+            kept = S.importance_sampling(noisy, normal, p, n, S.MT19937(seed), imp=imp)
+            assert np.array_equal(kept, g[f"{name}__seed{seed}"].astype(np.int64)), (name, seed)
+            kept2 = S.importance_sampling(noisy, normal, p, n, random.Random(seed), imp=imp)
+            assert np.array_equal(kept, kept2)
+
+
+def test_uniform_filter_restatement_matches_scipy():
+    ndimage = pytest.importorskip("scipy.ndimage")
+    rs = np.random.default_rng(0)
+    a = rs.standard_normal((37, 53, 3)).astype(np.float32)
+    for size in (1, 2, 5, 8, 32):
+        assert np.array_equal(S.uniform_filter_pp1(a, size), ndimage.uniform_filter(a, size=(size, size, 1))), size
