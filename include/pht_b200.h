@@ -313,7 +313,8 @@ void pht_get_counters(uint64_t* counters8);
 void pht_reset_counters(void);
 /* 1 = never use tcgen05 paths (debug / A-B testing) */
 void pht_set_force_simple(int on);
-/* tuning / A-B knobs: "tc_cfg" = 0 auto, 1 prefer the deep-ring conv_gemm config, 2 force the wide-epilogue one */
+/* tuning / A-B knobs: "tc_cfg" = 0 auto, 1 prefer the deep-ring conv_gemm config, 2 force the wide-epilogue one;
+ * "wgrad_split_div" = d: 1x1 weight-gradients use 1/d of the pixel splits (fewer fp32 partials) */
 int pht_set_option(const char* name, int value);
 
 #ifdef __cplusplus
