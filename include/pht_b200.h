@@ -121,6 +121,24 @@ typedef struct pht_wgrad_args {
 size_t pht_wgrad_workspace_bytes(const pht_wgrad_args* args);
 int pht_wgrad(const pht_wgrad_args* args, void* stream);
 
+/* Deferred variant for batching: pht_wgrad_partial() runs only the split GEMM and leaves the fp32 partials in
+ * args->workspace (which must stay untouched until the reduce); *job receives the descriptor of the pending
+ * fixed-order reduction (into args->dw / args->dbias).  Returns PHT_ERR_UNSUPPORTED when the shape is not taken by the
+ * split tensor-core kernel (call pht_wgrad instead).  pht_wgrad_reduce_batched() then finishes ANY number of pending
+ * jobs in ONE launch (`jobs` is a host array; `table_dev` caller-owned device scratch of n * sizeof(job) bytes,
+ * upload != 0 (re)writes it). */
+typedef struct pht_wgrad_reduce_job {
+  const float* partials;    /* [splits][elems] */
+  float* dw;                /* [elems] */
+  const float* bias_partials; /* [bias_rows][N] or NULL */
+  float* dbias;             /* [N] */
+  int64_t elems;            /* multiple of 4 */
+  int32_t splits, bias_rows, N, pad_;
+} pht_wgrad_reduce_job;
+int pht_wgrad_partial(const pht_wgrad_args* args, pht_wgrad_reduce_job* job, void* stream);
+int pht_wgrad_reduce_batched(const pht_wgrad_reduce_job* jobs, int32_t n, void* table_dev, size_t table_bytes, int32_t upload,
+                             void* stream);
+
 /* Fill the 1-pixel border of a padded NHWC buffer [B][H+2][W+2][C] from its
  * interior (replicate = clamp to edge, reflect = mirror without the edge).
  * Replaces F.pad inside nn.Conv2d(padding_mode=...) (model.py:607-622, 552-569,
@@ -259,6 +277,9 @@ int pht_unpack_wgrad(const pht_pack_args* a, void* stream);
 size_t pht_pack_table_bytes(int32_t n);
 int pht_pack_weights_batched(const pht_pack_args* jobs, int32_t n, void* table_dev, size_t table_bytes, int32_t upload,
                              void* stream);
+/* the same for pht_unpack_wgrad (jobs[i].packed is the fp32 packed gradient, jobs[i].w the OIHW destination) */
+int pht_unpack_wgrads_batched(const pht_pack_args* jobs, int32_t n, void* table_dev, size_t table_bytes, int32_t upload,
+                              void* stream);
 
 /* Decoder tail on the tensor-core path (model.py:707-714, 732): the 256->3 zero-padded 3x3 conv runs as a 64-wide
  * pht_conv_gemm with fp32 output y [B*H*W][ldy]; this adds bias and the residual and transposes to NCHW:

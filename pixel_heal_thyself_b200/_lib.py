@@ -42,6 +42,11 @@ class WgradArgs(C.Structure):
                 ("dw", C.c_void_p), ("dbias", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class WgradReduceJob(C.Structure):
+    _fields_ = [("partials", C.c_void_p), ("dw", C.c_void_p), ("bias_partials", C.c_void_p), ("dbias", C.c_void_p),
+                ("elems", C.c_int64), ("splits", C.c_int32), ("bias_rows", C.c_int32), ("N", C.c_int32), ("pad_", C.c_int32)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("heads", C.c_int32),
                 ("head_dim", C.c_int32), ("block", C.c_int32), ("halo", C.c_int32), ("q", PhtView), ("k", PhtView),
@@ -85,6 +90,9 @@ SYMBOLS = {
     "pht_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "pht_pack_weight": (C.c_int, [C.POINTER(PackArgs), _vp]),
     "pht_unpack_wgrad": (C.c_int, [C.POINTER(PackArgs), _vp]),
+    "pht_wgrad_partial": (C.c_int, [C.POINTER(WgradArgs), C.POINTER(WgradReduceJob), _vp]),
+    "pht_wgrad_reduce_batched": (C.c_int, [C.POINTER(WgradReduceJob), _i32, _vp, _sz, _i32, _vp]),
+    "pht_unpack_wgrads_batched": (C.c_int, [C.POINTER(PackArgs), _i32, _vp, _sz, _i32, _vp]),
     "pht_pack_table_bytes": (_sz, [_i32]),
     "pht_pack_weights_batched": (C.c_int, [C.POINTER(PackArgs), _i32, _vp, _sz, _i32, _vp]),
     "pht_tail_finish": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

@@ -521,6 +521,23 @@ __global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs) {
   }
 }
 
+__global__ void unpack_wgrads_batched_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  const PackP a = j.p;
+  long long total = (long long)a.O * a.I * a.ks * a.ks;
+  float* wg = const_cast<float*>(j.w);
+  const float* src = (const float*)j.dst;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int kx = (int)(idx % a.ks);
+    long long r = idx / a.ks;
+    int ky = (int)(r % a.ks); r /= a.ks;
+    int i = (int)(r % a.I);
+    int o = (int)(r / a.I);
+    if (i < a.i_begin || i >= a.i_begin + a.i_count) continue;
+    wg[idx] = src[packed_index(a, o, i - a.i_begin, ky, kx)] * a.scale;
+  }
+}
+
 // decoder tail on the GEMM path: out = y[..., 0:3] + bias + x  (y = fp32 [B,H,W,64] conv result, NHWC -> NCHW)
 __global__ void tail_finish_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ bias,
                                    const float* __restrict__ x, float* __restrict__ out, int B, int H, int W) {
@@ -834,9 +851,34 @@ int pht_pack_weights_batched(const pht_pack_args* jobs, int32_t n, void* table_d
   }
   if (upload) PHT_CUDA(cudaMemcpyAsync(table_dev, host.data(), (size_t)n * sizeof(PackJob), cudaMemcpyHostToDevice, st));
   int gx = (int)((max_total + 255) / 256);
-  if (gx > 64) gx = 64;
+  if (gx > 592) gx = 592;
   dim3 grid(gx, n);
   pack_weights_batched_kernel<<<grid, 256, 0, st>>>((const PackJob*)table_dev);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_unpack_wgrads_batched(const pht_pack_args* jobs, int32_t n, void* table_dev, size_t table_bytes, int32_t upload,
+                              void* stream) {
+  PHT_CHECK_ARG(jobs && n > 0 && table_dev && table_bytes >= pht_pack_table_bytes(n), "unpack_batched: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long max_total = 0;
+  static thread_local std::vector<PackJob> host;
+  host.resize(n);
+  for (int i = 0; i < n; ++i) {
+    PackP p;
+    int rc = check_pack(&jobs[i], &p);
+    if (rc) return rc;
+    host[i].w = jobs[i].w; host[i].dst = jobs[i].packed; host[i].p = p; host[i].dtype = PHT_F32; host[i].pad_ = 0;
+    long long total = (long long)p.O * p.I * p.ks * p.ks;
+    if (total > max_total) max_total = total;
+  }
+  if (upload) PHT_CUDA(cudaMemcpyAsync(table_dev, host.data(), (size_t)n * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+  int gx = (int)((max_total + 255) / 256);
+  if (gx > 592) gx = 592;
+  dim3 grid(gx, n);
+  unpack_wgrads_batched_kernel<<<grid, 256, 0, st>>>((const PackJob*)table_dev);
   count_launch(CNT_OTHER);
   PHT_LAUNCH_CHECK();
   return PHT_OK;

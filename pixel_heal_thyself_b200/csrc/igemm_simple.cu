@@ -10,7 +10,8 @@
 namespace pht {
 
 int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled);  // igemm_tc.cu
-int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled);          // igemm_tc.cu
+int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled, pht_wgrad_reduce_job* defer);  // wgrad_tc.cu
+int wgrad_reduce_batched(const pht_wgrad_reduce_job* jobs, int n, void* table_dev, size_t table_bytes, int upload, cudaStream_t st);
 size_t wgrad_tc_workspace_bytes(const pht_wgrad_args* a);
 
 struct GemmP {
@@ -501,7 +502,7 @@ int pht_wgrad(const pht_wgrad_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (a->dtype == PHT_BF16 && !force_simple()) {
     bool handled = false;
-    int rc = wgrad_tc(a, st, &handled);   // also produces dbias (fused column sums)
+    int rc = wgrad_tc(a, st, &handled, nullptr);   // also produces dbias (fused column sums)
     if (rc) return rc;
     if (handled) return PHT_OK;
   }
@@ -510,6 +511,25 @@ int pht_wgrad(const pht_wgrad_args* a, void* stream) {
     if (rc) return rc;
   }
   return wgrad_simple(a, st);
+}
+
+int pht_wgrad_partial(const pht_wgrad_args* a, pht_wgrad_reduce_job* job, void* stream) {
+  PHT_CHECK_ARG(a != nullptr && a->dw && job, "wgrad_partial: null args");
+  PHT_CHECK_ARG(a->ksize == 1 || a->ksize == 3 || a->ksize == 5, "wgrad_partial: ksize must be 1, 3 or 5");
+  PHT_CHECK_ARG(a->n_src >= 1 && a->n_src <= 3, "wgrad_partial: n_src must be 1..3");
+  if (a->dtype == PHT_BF16 && !force_simple()) {
+    bool handled = false;
+    int rc = wgrad_tc(a, (cudaStream_t)stream, &handled, job);
+    if (rc) return rc;
+    if (handled) return PHT_OK;
+  }
+  set_error("wgrad_partial: shape not taken by the split tensor-core kernel");
+  return PHT_ERR_UNSUPPORTED;
+}
+
+int pht_wgrad_reduce_batched(const pht_wgrad_reduce_job* jobs, int32_t n, void* table_dev, size_t table_bytes, int32_t upload,
+                             void* stream) {
+  return wgrad_reduce_batched(jobs, n, table_dev, table_bytes, upload, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -326,7 +326,47 @@ static int wg_tmap(CUtensorMap* tm, const pht_view& v, int B) {
   return make_tmap_bf16(tm, v.ptr, 4, dims, strides, box);
 }
 
-int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled) {
+// every pending reduction of a bucket in one launch: blockIdx.y = job, blockIdx.x strides over the job's float4s
+// (the last x-block of a job reduces its bias partials); fixed summation order => deterministic
+__global__ void wgrad_reduce_batched_kernel(const pht_wgrad_reduce_job* __restrict__ jobs) {
+  const pht_wgrad_reduce_job j = jobs[blockIdx.y];
+  if (j.bias_partials != nullptr && blockIdx.x == gridDim.x - 1) {
+    for (int n = threadIdx.x; n < j.N; n += blockDim.x) {
+      float a = 0.f;
+      for (int s = 0; s < j.bias_rows; ++s) a += j.bias_partials[(long long)s * j.N + n];
+      j.dbias[n] = a;
+    }
+    return;
+  }
+  const long long n4 = j.elems >> 2;
+  const float4* ws = reinterpret_cast<const float4*>(j.partials);
+  float4* dw = reinterpret_cast<float4*>(j.dw);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)(gridDim.x - 1) * blockDim.x) {
+    float4 a = ws[i];
+    for (int s = 1; s < j.splits; ++s) {
+      float4 b = ws[(long long)s * n4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dw[i] = a;
+  }
+}
+
+int wgrad_reduce_batched(const pht_wgrad_reduce_job* jobs, int n, void* table_dev, size_t table_bytes, int upload, cudaStream_t st) {
+  PHT_CHECK_ARG(jobs && n > 0 && table_dev && table_bytes >= (size_t)n * sizeof(pht_wgrad_reduce_job), "wgrad_reduce_batched: bad args");
+  for (int i = 0; i < n; ++i)
+    PHT_CHECK_ARG(jobs[i].partials && jobs[i].dw && jobs[i].elems % 4 == 0 && jobs[i].splits >= 1 &&
+                  !((uintptr_t)jobs[i].partials & 15) && !((uintptr_t)jobs[i].dw & 15), "wgrad_reduce_batched: bad job");
+  if (upload) PHT_CUDA(cudaMemcpyAsync(table_dev, jobs, (size_t)n * sizeof(pht_wgrad_reduce_job), cudaMemcpyHostToDevice, st));
+  int gx = 4 * sm_count() / n;                        // ~4 CTAs per SM over all jobs
+  if (gx < 16) gx = 16;
+  dim3 grid(gx + 1, n);                                 // + each job's bias block
+  wgrad_reduce_batched_kernel<<<grid, 256, 0, st>>>((const pht_wgrad_reduce_job*)table_dev);
+  PHT_LAUNCH_CHECK();
+  count_launch(CNT_OTHER);
+  return PHT_OK;
+}
+
+int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled, pht_wgrad_reduce_job* defer) {
   *handled = false;
   if (!a->workspace || ((uintptr_t)a->workspace & 15) || ((uintptr_t)a->dw & 15)) return PHT_OK;
   WgPlan p = wg_plan(a, a->workspace_bytes);
@@ -369,6 +409,14 @@ int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled) {
     wgrad_tc_kernel<1><<<jobs, WG_THREADS, WgCfg<1>::SMEM_BYTES, st>>>(tmDy, tmS[0], tmS[1], tmS[2], P);
   }
   PHT_LAUNCH_CHECK();
+  if (defer) {   // leave the partials in the workspace; the caller batches the reduction
+    defer->partials = P.ws; defer->dw = a->dw; defer->bias_partials = P.bias_ws; defer->dbias = a->dbias;
+    defer->elems = (int64_t)p.T * a->N * p.Ktot; defer->splits = p.splits; defer->bias_rows = p.splits * p.T; defer->N = a->N;
+    defer->pad_ = 0;
+    count_launch(CNT_WGRAD_TC);
+    *handled = true;
+    return PHT_OK;
+  }
   long long n4 = (long long)p.T * a->N * p.Ktot / 4;
   int grid = (int)((n4 + 255) / 256);
   int cap = sm_count() * 8;

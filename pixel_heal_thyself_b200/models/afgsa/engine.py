@@ -58,6 +58,7 @@ class AfgsaEngine:
         self._consts: dict[str, torch.Tensor] = {}
         self._packed_key = None
         self._pack_plans = {}
+        self._wg_bucket = None
         self._saved_gen = {}
         self._gen = 0
         # data-parallel hook: called with "decoder" / "block<i>" / "encoders" as soon as that group's
@@ -303,12 +304,46 @@ class AfgsaEngine:
                     torch.float32)
         tail_ws = g("tail_ws", (max(ops.dec_tail_ws_bytes(B, H, W, C), 16) // 4,), torch.float32)
         wg_ws = g("wg_ws", (64 * 1024 * 1024 // 4,), torch.float32)
+        # bf16: weight-gradients of a bucket are deferred and finished by one batched reduce + one batched unpack
+        bucket = None
+        if T == torch.bfloat16 and not getattr(self, "no_wgrad_batching", False):
+            bucket = self._wg_bucket
+            if bucket is None or bucket.ws.device != self.device:
+                bucket = self._wg_bucket = ops.WgradBucket(self.device)
+        tmp_off = [0]
+
+        def tmp(numel):
+            """fp32 staging for packed gradients: one slice per job of the current bucket"""
+            o = tmp_off[0]
+            tmp_off[0] = o + (numel + 63) // 64 * 64
+            assert tmp_off[0] <= wtmp_b.numel()
+            return wtmp_b[o:o + numel]
+
+        wtmp_b = g("wtmp_b", (6 * 9 * C * C + 4 * 768 * 256,), torch.float32)
+
+        def wgrad(dy, srcs, dw, **kw):
+            if bucket is None:
+                ops.wgrad(dy, srcs, dw, workspace=wg_ws, **kw)
+            else:
+                bucket.wgrad(dy, srcs, dw, **kw)
+
+        def unpack(wg, packed, **kw):
+            if bucket is None:
+                ops.unpack_wgrad(wg, packed, **kw)
+            else:
+                bucket.unpack(wg, packed, **kw)
+
+        def ready(tag):
+            if bucket is not None:
+                bucket.flush()
+            tmp_off[0] = 0
+            self._ready(tag)
         pdom = (B, H + 2, W + 2)
 
         def conv3_wgrad(dy, src_pad, name):
-            w = wtmp[: 9 * C * C].view(9, C, C)
-            ops.wgrad(dy, [src_pad], w, ksize=3, dbias=G[name + ".bias"], workspace=wg_ws, src_offsets=[(1, 1)])
-            ops.unpack_wgrad(G[name + ".weight"], w, ksize=3, Ntot=C, Ktot=C)
+            w = tmp(9 * C * C).view(9, C, C)
+            wgrad(dy, [src_pad], w, ksize=3, dbias=G[name + ".bias"], src_offsets=[(1, 1)])
+            unpack(G[name + ".weight"], w, ksize=3, Ntot=C, Ktot=C)
 
         def conv3_dgrad(dy, wT, *, resid=None, mask=None, out1=None, out2=None):
             """d(input of a padded 3x3 conv): data-gradient over the padded domain, border folded back into the
@@ -329,9 +364,9 @@ class AfgsaEngine:
         if T == torch.bfloat16:
             tailA = g("tailA", (B, H, W, 64), T)               # a[p][t*3+co] = d_out[p - tap_t][co]
             ops.tail_im2col_bwd(d_out, tailA, G["decoder.2.0.bias"])
-            dw2 = wtmp[: 64 * C].view(1, C, 64)                # dw2[c][t*3+co] = sum_p D2[p][c] a[p][t*3+co]
-            ops.wgrad(D2, [tailA], dw2, workspace=wg_ws)
-            ops.unpack_wgrad(G["decoder.2.0.weight"], dw2, ksize=3, Ntot=C, Ktot=64, transpose=2)
+            dw2 = tmp(64 * C).view(1, C, 64)                   # dw2[c][t*3+co] = sum_p D2[p][c] a[p][t*3+co]
+            wgrad(D2, [tailA], dw2)
+            unpack(G["decoder.2.0.weight"], dw2, ksize=3, Ntot=C, Ktot=64, transpose=2)
             ops.conv_gemm([tailA], pk["dec2g.T"], C, mask=D2, mslope=relu0, out2=G0)   # G0 = d(D2 pre-act)
         else:
             dw2 = wtmp[: 27 * C].view(3, 9, C)
@@ -344,7 +379,7 @@ class AfgsaEngine:
         self._dbg("dD1pre", G1)
         Xlast = g(f"Xp{self.num_sa}", (B, H + 2, W + 2, C), T)
         conv3_wgrad(G1, Xlast, "decoder.0.0")
-        self._ready("decoder")
+        ready("decoder")
         if self.num_sa > 0:
             conv3_dgrad(G1, pk["dec0.T"], mask=g(f"H2{self.num_sa - 1}", (B, H, W, C), T), out1=GX, out2=G0)
             self._dbg("dXlast", GX); self._dbg("dH2pre_last", G0)
@@ -368,15 +403,14 @@ class AfgsaEngine:
             ops.attn_bwd(QK[..., :C], QK[..., C:], V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], lse, G2,
                          dQK[..., :C], dQK[..., C:], dV, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,
                          heads=self.heads, block=self.block, halo=self.halo)
-            wqk = wtmp[: 2 * C * C].view(1, 2 * C, C)
-            ops.wgrad(dQK, [M], wqk, workspace=wg_ws)
-            ops.unpack_wgrad(G[pre + "attention.q_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=0, scale=self.scale)
-            ops.unpack_wgrad(G[pre + "attention.k_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=C)
-            ops.wgrad(dV, [X], G[pre + "attention.v_conv.weight"], workspace=wg_ws)
+            wqk = tmp(2 * C * C).view(1, 2 * C, C)
+            wgrad(dQK, [M], wqk)
+            unpack(G[pre + "attention.q_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=0, scale=self.scale)
+            unpack(G[pre + "attention.k_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=C)
+            wgrad(dV, [X], G[pre + "attention.v_conv.weight"])
             ops.conv_gemm([dQK], pk[f"b{i}.qk.T"], C, mask=M, mslope=relu0, out2=G1)       # G1 = d(M pre-act)
-            ops.wgrad(G1, [X, Af], G[pre + "attention.conv_map.0.weight"], dbias=G[pre + "attention.conv_map.0.bias"],
-                      workspace=wg_ws)
-            self._ready(f"block{i}")
+            wgrad(G1, [X, Af], G[pre + "attention.conv_map.0.weight"], dbias=G[pre + "attention.conv_map.0.bias"])
+            ready(f"block{i}")
             # d(block input) = dX1 + dV Wv + dMpre Wmap[:, :C]; also emit the next layer's masked gradient
             if i > 0:
                 ops.conv_gemm([dV, G1], pk[f"b{i}.x.T"], C, resid=G2, resid_mode="pre",
@@ -395,28 +429,28 @@ class AfgsaEngine:
         catN, catA = g("catN", (B, H, W, 768), T), g("catA", (B, H, W, 768), T)
         colN = g("colN", (B, H, W, pk["encN"].shape[-1]), T)
         colA = g("colA", (B, H, W, pk["encA"].shape[-1]), T)
-        ops.wgrad(G0, [catN], G["conv_map.0.weight"], dbias=G["conv_map.0.bias"], workspace=wg_ws)
+        wgrad(G0, [catN], G["conv_map.0.weight"], dbias=G["conv_map.0.bias"])
         ops.conv_gemm([G0], pk["conv_map.T"], 768, mask=catN, mslope=slopeN, out2=dcat)
-        self._encoder_wgrad(dcat, colN, ("conv1", "conv3", "conv5"), net.input_channels, wtmp, btmp, wg_ws, G)
+        self._encoder_wgrad(dcat, colN, ("conv1", "conv3", "conv5"), G, tmp, wgrad, unpack)
         # ---- aux encoder: G2 = d(conv_aenc2 pre-act) ------------------------------------------------
         if self.num_sa > 0:
-            ops.wgrad(G2, [A1], G["conv_aenc2.0.weight"], dbias=G["conv_aenc2.0.bias"], workspace=wg_ws)
+            wgrad(G2, [A1], G["conv_aenc2.0.weight"], dbias=G["conv_aenc2.0.bias"])
             ops.conv_gemm([G2], pk["conv_aenc2.T"], C, mask=A1, mslope=leaky, out2=G1)   # G1 = d(aenc1 pre-act)
-            ops.wgrad(G1, [catA], G["conv_aenc1.0.weight"], dbias=G["conv_aenc1.0.bias"], workspace=wg_ws)
+            wgrad(G1, [catA], G["conv_aenc1.0.weight"], dbias=G["conv_aenc1.0.bias"])
             ops.conv_gemm([G1], pk["conv_aenc1.T"], 768, mask=catA, mslope=slopeA, out2=dcat)
-            self._encoder_wgrad(dcat, colA, ("conv_a1", "conv_a3", "conv_a5"), net.aux_input_channels, wtmp, btmp,
-                                wg_ws, G)
+            self._encoder_wgrad(dcat, colA, ("conv_a1", "conv_a3", "conv_a5"), G, tmp, wgrad, unpack)
         else:  # no attention block consumes the aux features: their gradient is zero
             for n in ("conv_a1", "conv_a3", "conv_a5", "conv_aenc1", "conv_aenc2"):
                 G[n + ".0.weight"].zero_()
                 G[n + ".0.bias"].zero_()
-        self._ready("encoders")
+        ready("encoders")
         del self._saved_gen[(B, H, W)]
 
-    def _encoder_wgrad(self, dcat, col, names, cin, wtmp, btmp, wg_ws, G):
+    def _encoder_wgrad(self, dcat, col, names, G, tmp, wgrad, unpack):
         kpad = col.shape[-1]
-        w = wtmp[: 768 * kpad].view(1, 768, kpad)
-        ops.wgrad(dcat, [col], w, dbias=btmp, workspace=wg_ws)
+        w = tmp(768 * kpad).view(1, 768, kpad)
+        b = tmp(768)
+        wgrad(dcat, [col], w, dbias=b)
         for j, (nm, ks) in enumerate(zip(names, (1, 3, 5))):
-            ops.unpack_wgrad(G[f"{nm}.0.weight"], w, ksize=ks, Ntot=768, Ktot=kpad, n_off=256 * j, grid=5)
-            ops.unpack_wgrad(G[f"{nm}.0.bias"].view(256, 1), btmp, ksize=1, Ntot=768, Ktot=1, n_off=256 * j)
+            unpack(G[f"{nm}.0.weight"], w, ksize=ks, Ntot=768, Ktot=kpad, n_off=256 * j, grid=5)
+            unpack(G[f"{nm}.0.bias"].view(256, 1), b, ksize=1, Ntot=768, Ktot=1, n_off=256 * j)

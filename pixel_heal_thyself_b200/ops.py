@@ -95,6 +95,70 @@ def wgrad(dy, srcs, dw, *, ksize=1, dbias=None, workspace=None, src_offsets=None
     L.check(lib.pht_wgrad(C.byref(a), L.stream_ptr()), "pht_wgrad")
 
 
+class WgradBucket:
+    """Deferred weight-gradients of one gradient bucket (decoder / one transformer block / encoders).
+
+    ``wgrad()`` launches only the split GEMM (``pht_wgrad_partial``) into this bucket's private workspace;
+    ``unpack()`` queues a packed -> OIHW scatter; ``flush()`` then finishes every pending reduction in ONE launch
+    (``pht_wgrad_reduce_batched``) and every scatter in one more (``pht_unpack_wgrads_batched``).  The descriptor
+    tables are cached on the device and only re-uploaded when a pointer or shape changes (the first step)."""
+
+    def __init__(self, device, workspace_bytes=320 << 20):
+        self.ws = torch.empty(workspace_bytes // 4, dtype=torch.float32, device=device)
+        self.cursor = 0
+        self.jobs, self.unpacks = [], []
+        self._rsig = self._usig = None
+        self._rarr = self._uarr = self._rtab = self._utab = None
+
+    def wgrad(self, dy, srcs, dw, *, ksize=1, dbias=None, src_offsets=None):
+        L.require_cuda(dy, *srcs, dw)
+        a = _wgrad_args(dy, srcs, ksize, dw, dbias, src_offsets)
+        need = int(lib.pht_wgrad_workspace_bytes(C.byref(a)))
+        need = (need + 255) // 256 * 256
+        if self.cursor * 4 + need > self.ws.numel() * 4:
+            raise RuntimeError("WgradBucket: workspace exhausted")
+        a.workspace, a.workspace_bytes = self.ws.data_ptr() + self.cursor * 4, need
+        job = L.WgradReduceJob()
+        rc = lib.pht_wgrad_partial(C.byref(a), C.byref(job), L.stream_ptr())
+        if rc == -3:     # PHT_ERR_UNSUPPORTED: not a split tensor-core shape -> immediate path
+            L.check(lib.pht_wgrad(C.byref(a), L.stream_ptr()), "pht_wgrad")
+            return
+        L.check(rc, "pht_wgrad_partial")
+        self.cursor += need // 4
+        self.jobs.append(job)
+
+    def unpack(self, w_grad, packed, **kw):
+        L.require_cuda(w_grad, packed)
+        assert w_grad.is_contiguous() and w_grad.dtype == torch.float32 and packed.dtype == torch.float32
+        self.unpacks.append(_pack_args(w_grad, packed, **kw))
+
+    @staticmethod
+    def _table(items, ctype, sig_old, arr_old, tab_old, device, key, nbytes):
+        sig = tuple(key(x) for x in items)
+        if sig == sig_old:
+            return sig, arr_old, tab_old, 0
+        arr = (ctype * len(items))(*items)
+        tab = torch.empty(nbytes + 64, dtype=torch.uint8, device=device)
+        return sig, arr, tab, 1
+
+    def flush(self):
+        if self.jobs:
+            self._rsig, self._rarr, self._rtab, up = self._table(
+                self.jobs, L.WgradReduceJob, self._rsig, self._rarr, self._rtab, self.ws.device,
+                lambda j: (j.partials, j.dw, j.bias_partials, j.dbias, j.elems, j.splits, j.bias_rows, j.N),
+                C.sizeof(L.WgradReduceJob) * len(self.jobs))
+            L.check(lib.pht_wgrad_reduce_batched(self._rarr, len(self.jobs), self._rtab.data_ptr(), self._rtab.numel(), up,
+                                                 L.stream_ptr()), "pht_wgrad_reduce_batched")
+        if self.unpacks:
+            self._usig, self._uarr, self._utab, up = self._table(
+                self.unpacks, L.PackArgs, self._usig, self._uarr, self._utab, self.ws.device,
+                lambda a: (a.w, a.packed, a.O, a.I, a.ksize, a.Ntot, a.Ktot, a.n_off, a.k_off, a.transpose, a.grid,
+                           a.i_begin, a.i_count, a.scale), int(lib.pht_pack_table_bytes(len(self.unpacks))))
+            L.check(lib.pht_unpack_wgrads_batched(self._uarr, len(self.unpacks), self._utab.data_ptr(), self._utab.numel(),
+                                                  up, L.stream_ptr()), "pht_unpack_wgrads_batched")
+        self.jobs, self.unpacks, self.cursor = [], [], 0
+
+
 def border_fill(buf, mode):
     """buf: padded [B, H+2, W+2, C] contiguous."""
     L.require_cuda(buf)

@@ -27,8 +27,10 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes(tmp_path):
     """sizeof of every ABI struct as gcc sees the header == sizeof of the ctypes mirror."""
     from pixel_heal_thyself_b200 import _lib
-    names = ["pht_view", "pht_conv_gemm_args", "pht_wgrad_args", "pht_attn_args", "pht_attn_bwd_args", "pht_pack_args"]
-    mirrors = [_lib.PhtView, _lib.ConvGemmArgs, _lib.WgradArgs, _lib.AttnArgs, _lib.AttnBwdArgs, _lib.PackArgs]
+    names = ["pht_view", "pht_conv_gemm_args", "pht_wgrad_args", "pht_attn_args", "pht_attn_bwd_args", "pht_pack_args",
+             "pht_wgrad_reduce_job"]
+    mirrors = [_lib.PhtView, _lib.ConvGemmArgs, _lib.WgradArgs, _lib.AttnArgs, _lib.AttnBwdArgs, _lib.PackArgs,
+               _lib.WgradReduceJob]
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "pht_b200.h"\nint main(void){' +
                    "".join(f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}\n")
