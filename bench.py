@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                          "-lms", "50", "-i", str(self.idx)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
