@@ -189,6 +189,58 @@ __global__ void im2col5_vec8_kernel(const float* __restrict__ x, T* col, int B, 
   }
 }
 
+// tiled variant: a block stages a (4+4) x (32+4) x Cin input tile (padding mode applied while loading) and a k ->
+// tile-offset table in shared memory; every thread then emits 16-byte groups of 8 consecutive k with no integer
+// division and no global reads in the inner loop.
+constexpr int I2C_TH = 4, I2C_TW = 32;
+template <typename T>
+__global__ void __launch_bounds__(256) im2col5_tile_kernel(const float* __restrict__ x, T* col, int B, int Cin, int H, int W,
+                                                           int Kpad, int mode) {
+  extern __shared__ float i2c_sm[];
+  float* tile = i2c_sm;                                                  // [(TH+4)][(TW+4)][Cin]
+  int* koff = reinterpret_cast<int*>(tile + (I2C_TH + 4) * (I2C_TW + 4) * Cin);   // [Kpad]
+  const int tiles_x = (W + I2C_TW - 1) / I2C_TW, tiles_y = (H + I2C_TH - 1) / I2C_TH;
+  const int b = blockIdx.x / (tiles_x * tiles_y), tr = blockIdx.x % (tiles_x * tiles_y);
+  const int y0 = (tr / tiles_x) * I2C_TH, x0 = (tr % tiles_x) * I2C_TW;
+  const int TWp = I2C_TW + 4, n_in = (I2C_TH + 4) * TWp * Cin;
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
+    const int ci = i % Cin, q = i / Cin;
+    const int ty = q / TWp, tx = q - ty * TWp;
+    const int sy = pad_index(min(y0 + ty - 2, H + 1), H, mode), sx = pad_index(min(x0 + tx - 2, W + 1), W, mode);
+    tile[i] = x[(((long long)b * Cin + ci) * H + sy) * W + sx];
+  }
+  const int kreal = 25 * Cin;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int off = -1;
+    if (k < kreal) {
+      const int ci = k % Cin, t = k / Cin;
+      off = ((t / 5) * TWp + (t % 5)) * Cin + ci;
+    }
+    koff[k] = off;
+  }
+  __syncthreads();
+  const int kv = Kpad / 8, items = I2C_TH * I2C_TW * kv;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int g = it % kv, p = it / kv;
+    const int py = p / I2C_TW, px = p - py * I2C_TW;
+    if (y0 + py >= H || x0 + px >= W) continue;
+    const float* base = tile + (py * TWp + px) * Cin;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = koff[g * 8 + j];
+      v[j] = o >= 0 ? base[o] : 0.f;
+    }
+    T* dst = col + (((long long)b * H + y0 + py) * W + x0 + px) * Kpad + g * 8;
+    if (sizeof(T) == 2) {
+      Vec<bf16>::st((bf16*)dst, v);
+    } else {
+      Vec<float>::st((float*)dst, v);
+      Vec<float>::st((float*)dst + 4, v + 4);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // decoder tail (256 -> 3, zero padding) forward / data-grad / weight-grad
 // ---------------------------------------------------------------------------------------------
@@ -341,8 +393,7 @@ __global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__
   const float4* a4 = reinterpret_cast<const float4*>(a);
   const float4* b4 = reinterpret_cast<const float4*>(b);
   float4* g4 = reinterpret_cast<float4*>(grad);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 x = a4[i], y = b4[i];
+  auto one = [&](const float4& x, const float4& y, long long i) {
     float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
     s += fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
     if (grad) {
@@ -353,7 +404,15 @@ __global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__
       g.w = d3 > 0.f ? gs : (d3 < 0.f ? -gs : 0.f);
       g4[i] = g;
     }
+  };
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {   // 8 independent 16-byte loads in flight per thread
+    float4 x0 = a4[i], x1 = a4[i + stride], x2 = a4[i + 2 * stride], x3 = a4[i + 3 * stride];
+    float4 y0 = b4[i], y1 = b4[i + stride], y2 = b4[i + 2 * stride], y3 = b4[i + 3 * stride];
+    one(x0, y0, i); one(x1, y1, i + stride); one(x2, y2, i + 2 * stride); one(x3, y3, i + 3 * stride);
   }
+  for (; i < n4; i += stride) one(a4[i], b4[i], i);
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float d = a[i] - b[i];
     s += fabsf(d);
@@ -399,28 +458,105 @@ __device__ __forceinline__ float prep_normal(float v) {
   return fmaxf(fminf(v, 1.0f), 0.0f);
 }
 
-// frames NHWC [Hf][Wf][C] (or patches [n][P][P][C] when centres == NULL) -> NCHW [n][C][P][P]
-__global__ void crop_preprocess_kernel(const float* __restrict__ src, float* __restrict__ dst, int Hf, int Wf, int C,
-                                       const int* __restrict__ centres, const int* __restrict__ img_idx, int n, int P,
-                                       int kind /*0 log1p, 1 aux*/) {
-  long long total = (long long)n * C * P * P;
+// frames NHWC [Hf][Wf][C] (or patches [n][PH][PW][C] when centres == NULL) -> NCHW [n][C][PH][PW].
+// ONE launch for noisy + gt + aux, one thread per output pixel.  A warp reads 32 consecutive pixels =
+// 384 / 896 contiguous bytes per tensor (every fetched sector fully used) and writes one coalesced 128-byte row per
+// channel plane.
+__global__ void __launch_bounds__(256) crop_preprocess_px_kernel(const float* __restrict__ noisy, const float* __restrict__ gt,
+                                                                 const float* __restrict__ aux, float* __restrict__ noisy_o,
+                                                                 float* __restrict__ gt_o, float* __restrict__ aux_o, int Hf,
+                                                                 int Wf, const int* __restrict__ centres,
+                                                                 const int* __restrict__ img_idx, int n, int P, int PW) {
+  const long long pp = (long long)P * PW, total = (long long)n * pp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int x = (int)(i % P);
-    long long r = i / P;
-    int y = (int)(r % P); r /= P;
-    int c = (int)(r % C);
-    int b = (int)(r / C);
-    float v;
+    const int b = (int)(i / pp);
+    const int r = (int)(i - (long long)b * pp);
+    const int y = r / PW, x = r - y * PW;
+    long long sp;   // source pixel index
     if (centres) {
-      int cx = centres[2 * b], cy = centres[2 * b + 1];
-      long long f = img_idx ? (long long)img_idx[b] * Hf * Wf : 0;
-      v = src[(f + (long long)(cy - P / 2 + y) * Wf + (cx - P / 2 + x)) * C + c];
+      const int cx = centres[2 * b], cy = centres[2 * b + 1];
+      const long long f = img_idx ? (long long)img_idx[b] * Hf * Wf : 0;
+      sp = f + (long long)(cy - P / 2 + y) * Wf + (cx - PW / 2 + x);
     } else {
-      v = src[(((long long)b * P + y) * P + x) * C + c];
+      sp = i;
     }
-    if (kind == 0) v = logf(v + 1.0f);
-    else if (c < 3) v = prep_normal(v);
-    dst[i] = v;
+    const float* s3 = noisy + sp * 3;
+    float* d3 = noisy_o + (long long)b * 3 * pp + r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) __stcs(d3 + c * pp, logf(__ldcs(s3 + c) + 1.0f));
+    if (gt) {
+      const float* g3 = gt + sp * 3;
+      float* e3 = gt_o + (long long)b * 3 * pp + r;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) __stcs(e3 + c * pp, logf(__ldcs(g3 + c) + 1.0f));
+    }
+    const float* s7 = aux + sp * 7;
+    float* d7 = aux_o + (long long)b * 7 * pp + r;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      const float v = __ldcs(s7 + c);
+      __stcs(d7 + c * pp, c < 3 ? prep_normal(v) : v);
+    }
+  }
+}
+
+// 4 consecutive pixels of a row per thread (PW % 4 == 0): 12 / 28 contiguous input floats (16-byte loads when the
+// source pixel index is a multiple of 4, which always holds without a crop), one 16-byte store per channel plane.
+template <int n>
+__device__ __forceinline__ void ld_run(const float* p, float* o, bool aligned) {
+  if (aligned) {
+#pragma unroll
+    for (int i = 0; i < n; i += 4) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(p + i));
+      o[i] = v.x; o[i + 1] = v.y; o[i + 2] = v.z; o[i + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < n; ++i) o[i] = __ldcs(p + i);
+  }
+}
+__global__ void __launch_bounds__(256) crop_preprocess_px4_kernel(const float* __restrict__ noisy, const float* __restrict__ gt,
+                                                                  const float* __restrict__ aux, float* __restrict__ noisy_o,
+                                                                  float* __restrict__ gt_o, float* __restrict__ aux_o, int Hf,
+                                                                  int Wf, const int* __restrict__ centres,
+                                                                  const int* __restrict__ img_idx, int n, int P, int PW) {
+  const long long pp = (long long)P * PW, q4 = pp >> 2, total = (long long)n * q4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / q4);
+    const int r = (int)(i - (long long)b * q4) << 2;      // first of 4 pixels inside the patch
+    const int y = r / PW, x = r - y * PW;
+    long long sp;
+    if (centres) {
+      const int cx = centres[2 * b], cy = centres[2 * b + 1];
+      const long long f = img_idx ? (long long)img_idx[b] * Hf * Wf : 0;
+      sp = f + (long long)(cy - P / 2 + y) * Wf + (cx - PW / 2 + x);
+    } else {
+      sp = (long long)b * pp + r;
+    }
+    const bool al = (sp & 3) == 0;
+    float v[28];
+    ld_run<12>(noisy + sp * 3, v, al);
+    float* d3 = noisy_o + (long long)b * 3 * pp + r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      __stcs(reinterpret_cast<float4*>(d3 + c * pp), make_float4(logf(v[c] + 1.0f), logf(v[3 + c] + 1.0f), logf(v[6 + c] + 1.0f),
+                                                                logf(v[9 + c] + 1.0f)));
+    if (gt) {
+      ld_run<12>(gt + sp * 3, v, al);
+      float* e3 = gt_o + (long long)b * 3 * pp + r;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        __stcs(reinterpret_cast<float4*>(e3 + c * pp), make_float4(logf(v[c] + 1.0f), logf(v[3 + c] + 1.0f), logf(v[6 + c] + 1.0f),
+                                                                  logf(v[9 + c] + 1.0f)));
+    }
+    ld_run<28>(aux + sp * 7, v, al);
+    float* d7 = aux_o + (long long)b * 7 * pp + r;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      float4 o = make_float4(v[c], v[7 + c], v[14 + c], v[21 + c]);
+      if (c < 3) o = make_float4(prep_normal(o.x), prep_normal(o.y), prep_normal(o.z), prep_normal(o.w));
+      __stcs(reinterpret_cast<float4*>(d7 + c * pp), o);
+    }
   }
 }
 
@@ -659,6 +795,15 @@ int pht_im2col5(const float* x, void* col, int32_t dtype, int32_t B, int32_t Cin
   PHT_CHECK_ARG(mode == PHT_PAD_REPLICATE || (H > 2 && W > 2), "im2col5: reflect needs H,W > 2");
   cudaStream_t st = (cudaStream_t)stream;
   long long items = (long long)B * H * W * Kpad;
+  if (Kpad % 8 == 0 && ((uintptr_t)col & 15) == 0 && Cin <= 16) {
+    const int tiles = B * ((H + I2C_TH - 1) / I2C_TH) * ((W + I2C_TW - 1) / I2C_TW);
+    const size_t smem = (size_t)(I2C_TH + 4) * (I2C_TW + 4) * Cin * sizeof(float) + (size_t)Kpad * sizeof(int);
+    if (dtype == PHT_F32) im2col5_tile_kernel<float><<<tiles, 256, smem, st>>>(x, (float*)col, B, Cin, H, W, Kpad, mode);
+    else im2col5_tile_kernel<bf16><<<tiles, 256, smem, st>>>(x, (bf16*)col, B, Cin, H, W, Kpad, mode);
+    count_launch(CNT_OTHER);
+    PHT_LAUNCH_CHECK();
+    return PHT_OK;
+  }
   if (Kpad % 8 == 0 && ((uintptr_t)col & 15) == 0) {
     if (dtype == PHT_F32) im2col5_vec8_kernel<float><<<grid_for(items / 8, 256), 256, 0, st>>>(x, (float*)col, B, Cin, H, W, Kpad, mode);
     else im2col5_vec8_kernel<bf16><<<grid_for(items / 8, 256), 256, 0, st>>>(x, (bf16*)col, B, Cin, H, W, Kpad, mode);
@@ -751,6 +896,8 @@ int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, flo
   PHT_CHECK_ARG(a && b && loss && n > 0, "l1_loss: bad args");
   PHT_CHECK_ARG((((uintptr_t)a | (uintptr_t)b | (uintptr_t)grad) & 15) == 0, "l1_loss: pointers must be 16B aligned");
   int grid = grid_for((n + 3) / 4, 256);
+  const int one_wave = num_sms() * 8;   // 8 resident 256-thread blocks per SM: exactly one wave, grid-stride inside
+  if (grid > one_wave) grid = one_wave;
   if (grid > L1_MAX_BLOCKS) grid = L1_MAX_BLOCKS;
   l1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, (long long)n, grad_scale, loss, grad);
   count_launch(CNT_OTHER);
@@ -760,13 +907,18 @@ int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, flo
 
 int pht_preprocess(const float* noisy, const float* gt, const float* aux, float* noisy_o, float* gt_o, float* aux_o,
                    int32_t B, int32_t H, int32_t W, void* stream) {
-  PHT_CHECK_ARG(noisy && aux && noisy_o && aux_o && H == W, "preprocess: bad args (square patches only)");
+  PHT_CHECK_ARG(noisy && aux && noisy_o && aux_o && B > 0 && H > 0 && W > 0, "preprocess: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  long long n3 = (long long)B * 3 * H * W, n7 = (long long)B * 7 * H * W;
-  crop_preprocess_kernel<<<grid_for(n3, 256), 256, 0, st>>>(noisy, noisy_o, 0, 0, 3, nullptr, nullptr, B, H, 0);
-  if (gt) crop_preprocess_kernel<<<grid_for(n3, 256), 256, 0, st>>>(gt, gt_o, 0, 0, 3, nullptr, nullptr, B, H, 0);
-  crop_preprocess_kernel<<<grid_for(n7, 256), 256, 0, st>>>(aux, aux_o, 0, 0, 7, nullptr, nullptr, B, H, 1);
-  count_launch(CNT_OTHER, gt ? 3 : 2);
+  PHT_CHECK_ARG(!gt || gt_o, "preprocess: gt without gt output");
+  const bool al16 = ((((uintptr_t)noisy | (uintptr_t)(gt ? gt : noisy) | (uintptr_t)aux | (uintptr_t)noisy_o | (uintptr_t)(gt_o ? gt_o : noisy_o) |
+                       (uintptr_t)aux_o) & 15) == 0);
+  if (W % 4 == 0 && ((long long)H * W) % 4 == 0 && al16)
+    crop_preprocess_px4_kernel<<<grid_for((long long)B * H * W / 4, 256), 256, 0, st>>>(noisy, gt, aux, noisy_o, gt_o, aux_o, 0, 0,
+                                                                                        nullptr, nullptr, B, H, W);
+  else
+    crop_preprocess_px_kernel<<<grid_for((long long)B * H * W, 256), 256, 0, st>>>(noisy, gt, aux, noisy_o, gt_o, aux_o, 0, 0,
+                                                                                   nullptr, nullptr, B, H, W);
+  count_launch(CNT_OTHER);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
@@ -776,11 +928,16 @@ int pht_crop_preprocess(const float* noisy_f, const float* gt_f, const float* au
                         float* gt_o, float* aux_o, void* stream) {
   PHT_CHECK_ARG(noisy_f && aux_f && centres && noisy_o && aux_o && n > 0 && P > 0, "crop_preprocess: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  long long n3 = (long long)n * 3 * P * P, n7 = (long long)n * 7 * P * P;
-  crop_preprocess_kernel<<<grid_for(n3, 256), 256, 0, st>>>(noisy_f, noisy_o, Hf, Wf, 3, centres, img_idx, n, P, 0);
-  if (gt_f) crop_preprocess_kernel<<<grid_for(n3, 256), 256, 0, st>>>(gt_f, gt_o, Hf, Wf, 3, centres, img_idx, n, P, 0);
-  crop_preprocess_kernel<<<grid_for(n7, 256), 256, 0, st>>>(aux_f, aux_o, Hf, Wf, 7, centres, img_idx, n, P, 1);
-  count_launch(CNT_OTHER, gt_f ? 3 : 2);
+  PHT_CHECK_ARG(!gt_f || gt_o, "crop_preprocess: gt without gt output");
+  const bool al16 = ((((uintptr_t)noisy_f | (uintptr_t)(gt_f ? gt_f : noisy_f) | (uintptr_t)aux_f | (uintptr_t)noisy_o |
+                       (uintptr_t)(gt_o ? gt_o : noisy_o) | (uintptr_t)aux_o) & 15) == 0);
+  if (P % 4 == 0 && al16)
+    crop_preprocess_px4_kernel<<<grid_for((long long)n * P * P / 4, 256), 256, 0, st>>>(noisy_f, gt_f, aux_f, noisy_o, gt_o, aux_o,
+                                                                                        Hf, Wf, centres, img_idx, n, P, P);
+  else
+    crop_preprocess_px_kernel<<<grid_for((long long)n * P * P, 256), 256, 0, st>>>(noisy_f, gt_f, aux_f, noisy_o, gt_o, aux_o, Hf,
+                                                                                   Wf, centres, img_idx, n, P, P);
+  count_launch(CNT_OTHER);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
