@@ -5,31 +5,33 @@
 // halves of every TMEM sub-partition, so all 128 lanes / softmax threads are busy):
 //   TMA      Q box [8x8 px x 64 ch] and K / V boxes [14x14 px x 64 ch] per head; window pixels outside the image
 //            are zero-filled by TMA (== the reference's zero-padded, un-masked keys).
-//   S = Q K'^T   one tcgen05.mma chain M=64, N=240, K=64 per head.  The key tile has 240 rows: 196 keys, 12 zero
-//            rows, then 32 "relative position rows" [rel_h[r] | 0] and [0 | rel_w[c]], so columns 208..239 of S
-//            hold q_h.rel_h[r] and q_w.rel_w[c]:  S'[q, (r,c)] = S[q, key] + S[q, 208+r] + S[q, 224+c]
-//            == q.(k + rel) of the reference, without ever materialising K + rel.
-//   softmax  128 threads, one (head, query) row each, two passes over TMEM (max, then exp2 / sum), P -> bf16 into a
+//   S = Q K^T + Q REL^T   two accumulating tcgen05.mma chains M=64, N=200, K=64 per head.  REL is a constant smem tile
+//            [key (r,c)][rel_h[r] | rel_w[c]], so S == q.(k + rel) of the reference (model.py:496-501) without ever
+//            materialising K + rel and without any per-element bias arithmetic in the softmax.
+//   softmax  128 threads, one (head, query) row each, two passes over TMEM (max, then exp2 / sum) in 32-column chunks
+//            with the next chunk's tcgen05.ld in flight while the current one is processed; P -> bf16 into a
 //            128B-swizzled K-major smem tile.
 //   O = P V  tcgen05.mma M=64, N=64, K=208 with V consumed MN-major straight from its TMA box; O overwrites
 //            the first 64 columns of the (already consumed) S region.
-//   epilogue O / sum + residual -> bf16 NHWC, log-sum-exp saved for the backward.
+//   epilogue O / sum + residual (TMA-loaded tile, updated in place) -> bf16 tile -> TMA store; log-sum-exp saved.
 // Two TMEM regions (one per head pair) ping-pong so S(it+1) is computed while softmax(it) runs.
+// Warps: 0 TMA producer, 1 MMA issuer, 2..5 softmax/epilogue, 6 output store + residual prefetch.
 #include "tc_common.cuh"
 
 namespace pht {
 
 using namespace tc;
 
-constexpr int AT_THREADS = 192;
-constexpr int AT_NK = 196, AT_NKP = 208, AT_NS = 240;          // keys, keys padded to 16, S columns incl. rel rows
+constexpr int AT_THREADS = 192;                                // backward kernel
+constexpr int AF_THREADS = 224;                                // forward kernel (7 warps)
+constexpr int AT_NK = 196, AT_NKP = 208, AT_NS = 200;          // keys, keys padded to 16 (P / V), S columns = K-tile rows
 constexpr int AT_Q_BYTES = 64 * 128;                           // 8 KB per head
-constexpr int AT_K_BYTES = AT_NS * 128;                        // 30720
+constexpr int AT_K_BYTES = AT_NS * 128;                        // 25600 (25 swizzle atoms)
 constexpr int AT_V_BYTES = AT_NKP * 128;                       // 26624
 constexpr int AT_P_BYTES = 4 * 64 * 128;                       // 4 K-tiles of 64 keys
 constexpr int AT_KV_BOX_BYTES = AT_NK * 128;                   // 25088 written by one TMA box
-constexpr int AT_RO_BYTES = 2 * AT_Q_BYTES;                    // residual-in / output staging: 2 heads x [64 px][64 ch]
-constexpr int AT_SMEM = 2 * (AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES + AT_P_BYTES) + 2 * AT_RO_BYTES + 256 + 1024;
+constexpr int AT_RO_BYTES = 2 * AT_Q_BYTES;                    // residual-in == output staging: 2 heads x [64 px][64 ch]
+constexpr int AT_SMEM = 2 * (AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES + AT_P_BYTES) + AT_K_BYTES + AT_RO_BYTES + 256 + 1024;
 static_assert(AT_SMEM <= 232448, "attn_fwd_tc: shared memory budget");
 
 struct AtP {
@@ -46,20 +48,19 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AF_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmR,
                    const __grid_constant__ CUtensorMap tmO, const AtP P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
   uint8_t* Qs = smem;                                   // [2][64 x 128B]
-  uint8_t* Ks = Qs + 2 * AT_Q_BYTES;                    // [2][240 x 128B]
-  uint8_t* Vs = Ks + 2 * AT_K_BYTES;                    // [2][208 x 128B]
+  uint8_t* Ks = Qs + 2 * AT_Q_BYTES;                    // [2][200 x 128B]
+  uint8_t* RELs = Ks + 2 * AT_K_BYTES;                  // [200 x 128B]  row (r,c) = [rel_h[r] | rel_w[c]]
+  uint8_t* Vs = RELs + AT_K_BYTES;                      // [2][208 x 128B]
   uint8_t* Ps = Vs + 2 * AT_V_BYTES;                    // [2][4][64 x 128B]
-  uint8_t* Rs = Ps + 2 * AT_P_BYTES;                    // [2][64 x 128B] residual tiles (TMA in)
-  uint8_t* Os = Rs + AT_RO_BYTES;                       // [2][64 x 128B] output staging (TMA out)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Os + AT_RO_BYTES);
-  uint64_t* r_full = bars + 10;
+  uint8_t* ROs = Ps + 2 * AT_P_BYTES;                   // [2][64 x 128B] residual tile in, output tile out (in place)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ROs + AT_RO_BYTES);
   uint64_t* qk_full = bars + 0;
   uint64_t* qk_empty = bars + 1;
   uint64_t* v_full = bars + 2;
@@ -67,31 +68,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* p_full = bars + 4;
   uint64_t* s_full = bars + 5;     // [2]
   uint64_t* tmem_free = bars + 7;  // [2]
+  uint64_t* ro_in = bars + 9;      // residual tile of the iteration has landed / the staging tile is free
+  uint64_t* ro_out = bars + 10;    // output tile complete (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // one-time smem constants: zero pad rows of K / V, relative-position rows of K (swizzled like a TMA box)
-  for (int i = threadIdx.x; i < 2 * (AT_NS - AT_NK) * 8; i += blockDim.x) {  // K rows 196..239, 16B chunks
-    const int h = i / ((AT_NS - AT_NK) * 8), rem = i % ((AT_NS - AT_NK) * 8);
-    const int R = AT_NK + rem / 8, ch = rem % 8;
+  // one-time smem constants: zero pad rows of K / V, the relative-position tile (swizzled like a TMA box)
+  for (int i = threadIdx.x; i < AT_NS * 8; i += blockDim.x) {   // REL rows 0..199, 16-byte chunks
+    const int R = i >> 3, ch = i & 7;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (R >= AT_NKP) {
-      const int rr = R - AT_NKP;                 // 0..31
-      if (rr < 14 && ch < 4) {                   // [rel_h[r] | 0]
+    if (R < AT_NK) {
+      const int wr = R / 14, wc = R - wr * 14;
+      const float* src = ch < 4 ? P.rel_h + wr * 32 + ch * 8 : P.rel_w + wc * 32 + (ch - 4) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = P.rel_h[rr * 32 + ch * 8 + j];
-      } else if (rr >= 16 && rr < 30 && ch >= 4) {  // [0 | rel_w[c]]
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = P.rel_w[(rr - 16) * 32 + (ch - 4) * 8 + j];
-      }
+      for (int j = 0; j < 8; ++j) v[j] = src[j];
     }
     uint4 u;
     __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
     for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(Ks + h * AT_K_BYTES + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
+    *reinterpret_cast<uint4*>(RELs + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
+  }
+  for (int i = threadIdx.x; i < 2 * (AT_NS - AT_NK) * 8; i += blockDim.x) {   // K rows 196..199
+    const int h = i / ((AT_NS - AT_NK) * 8), rem = i % ((AT_NS - AT_NK) * 8);
+    *reinterpret_cast<uint4*>(Ks + h * AT_K_BYTES + (AT_NK + rem / 8) * 128 + (rem % 8) * 16) = make_uint4(0, 0, 0, 0);
   }
   for (int i = threadIdx.x; i < 2 * (AT_NKP - AT_NK) * 8; i += blockDim.x) {  // V rows 196..207
     const int h = i / ((AT_NKP - AT_NK) * 8), rem = i % ((AT_NKP - AT_NK) * 8);
@@ -106,7 +108,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(v_full, 1);
     mbar_init(pv_done, 1);
     mbar_init(p_full, 128);
-    mbar_init(r_full, 1);
+    mbar_init(ro_in, 1);
+    mbar_init(ro_out, 128);
     for (int r = 0; r < 2; ++r) {
       mbar_init(&s_full[r], 1);
       mbar_init(&tmem_free[r], 128);
@@ -150,6 +153,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(64, AT_NS, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(64, 64, 0, 1);  // B = V is MN-major
+      const uint64_t reld = umma_desc_k_sw128(smem_u32(RELs));
       auto issue_s = [&](int it) {
         const int r = it & 1;
         mbar_wait(qk_full, it & 1);
@@ -162,6 +166,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint32_t d = tmem_base + r * 256 + ((uint32_t)(h * 16) << 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, reld + 2 * k, idesc_s, 1u);   // += q . [rel_h | rel_w]
         }
         umma_commit(qk_empty);
         umma_commit(&s_full[r]);
@@ -188,42 +194,60 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(pv_done);
       }
     }
+  } else if (warp == 6) {
+    // ================================ output store + residual prefetch ================================
+    if (lane == 0) {
+      auto load_resid = [&](int it) {
+        if (P.has_resid) {
+          const int blk = blockIdx.x + (it >> 1) * gridDim.x, pair = it & 1;
+          const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+          mbar_expect_tx(ro_in, AT_RO_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_4d(ROs + h * AT_Q_BYTES, &tmR, ro_in, (pair * 2 + h) * 64, bx * 8 + P.residOx, by * 8 + P.residOy, b);
+        } else {
+          mbar_arrive(ro_in);   // no residual: the staging tile is simply free
+        }
+      };
+      if (n_it > 0) load_resid(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int blk = blockIdx.x + (it >> 1) * gridDim.x, pair = it & 1;
+        const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+        mbar_wait(ro_out, it & 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(ROs + h * AT_Q_BYTES)), "r"((pair * 2 + h) * 64),
+                         "r"(bx * 8 + P.outOx), "r"(by * 8 + P.outOy), "r"(b)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile may be overwritten again
+        if (it + 1 < n_it) load_resid(it + 1);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before exit
+    }
   } else {
     // ================================ softmax + epilogue (warps 2..5) ================================
     const int quad = warp & 3;
     const int hp = lane >> 4;                    // head inside the pair (TMEM lane half)
     const int q = quad * 16 + (lane & 15);       // query row
     const int qy = q >> 3, qx = q & 7;
+    const int qsw = q & 7;
     const float LOG2E = 1.4426950408889634f;
     float prev_m = 0.f, prev_sum = 1.f;
     int prev_blk = 0, prev_pair = 0;
-
-    const bool issuer = (warp == 2 && lane == 0);
-    // residual tiles of iteration `it` (both heads of the pair) -> Rs, signalled on r_full
-    auto load_resid = [&](int it) {
-      const int blk = blockIdx.x + (it >> 1) * gridDim.x, pair = it & 1;
-      const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
-      mbar_expect_tx(r_full, AT_RO_BYTES);
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        tma_load_4d(Rs + h * AT_Q_BYTES, &tmR, r_full, (pair * 2 + h) * 64, bx * 8 + P.residOx, by * 8 + P.residOy, b);
-    };
-    if (issuer && P.has_resid && n_it > 0) load_resid(0);
 
     auto epilogue = [&](int it, float m, float sum, int blk, int pair) {
       const int r = it & 1;
       mbar_wait(pv_done, it & 1);
       tc_fence_after();
-      if (P.has_resid) mbar_wait(r_full, it & 1);
-      // the previous iteration's TMA store has finished reading the staging tile
-      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(ro_in, it & 1);                  // residual tile landed (or staging tile free)
       const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
       const int y = by * 8 + qy, x = bx * 8 + qx, head = pair * 2 + hp;
       const float inv = 1.f / sum;
       const uint32_t t_addr = tmem_base + r * 256 + ((uint32_t)(quad * 32) << 16);
-      const uint8_t* rrow = Rs + hp * AT_Q_BYTES + q * 128;
-      uint8_t* orow = Os + hp * AT_Q_BYTES + q * 128;
+      uint8_t* row = ROs + hp * AT_Q_BYTES + q * 128;
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t o[32];
@@ -234,9 +258,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(o[g * 8 + j]) * inv;
-          const int ch = ((c0 >> 3) + g) ^ (q & 7);      // 128B-swizzled 16-byte chunk of this row
+          uint4* cell = reinterpret_cast<uint4*>(row + ((((c0 >> 3) + g) ^ qsw) * 16));   // 128B-swizzled 16-byte chunk
           if (P.has_resid) {
-            uint4 ru = *reinterpret_cast<const uint4*>(rrow + ch * 16);
+            const uint4 ru = *cell;
             const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&ru);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -249,25 +273,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          *reinterpret_cast<uint4*>(orow + ch * 16) = u;
+          *cell = u;
         }
       }
       if (P.lse) P.lse[(((long long)b * P.H + y) * P.W + x) * 4 + head] = m + logf(sum);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&tmem_free[r]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // staging complete, residual tile consumed
-      if (issuer) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                       ::"l"(reinterpret_cast<uint64_t>(&tmO)), "r"(smem_u32(Os + h * AT_Q_BYTES)), "r"((pair * 2 + h) * 64),
-                         "r"(bx * 8 + P.outOx), "r"(by * 8 + P.outOy), "r"(b)
-                       : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (P.has_resid && it + 1 < n_it) load_resid(it + 1);
-      }
+      mbar_arrive(ro_out);
     };
 
     for (int it = 0; it < n_it; ++it) {
@@ -276,59 +289,75 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&s_full[r], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + r * 256 + ((uint32_t)(quad * 32) << 16);
-      uint32_t rr[32];
-      tmem_ld32(t_addr + AT_NKP, rr);  // [0..13] = q_h.rel_h[r], [16..29] = q_w.rel_w[c]
-      tmem_ld_wait();
-      // pass 1: row maximum
+      uint32_t a[32], bq[32];
+      // ---- pass 1: row maximum (chunks of 32 keys; the next chunk's tcgen05.ld is in flight while this one is reduced)
       float m = -INFINITY;
+      tmem_ld32(t_addr, a);
+      tmem_ld_wait();
+#pragma unroll 1
+      for (int c = 0; c < 6; c += 2) {
+        tmem_ld32(t_addr + (c + 1) * 32, bq);
 #pragma unroll
-      for (int c0 = 0; c0 < 224; c0 += 32) {
-        uint32_t s[32];
-        tmem_ld32(t_addr + c0, s);
+        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(a[j]), __uint_as_float(a[j + 1])));
         tmem_ld_wait();
+        tmem_ld32(t_addr + (c + 2) * 32, a);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = c0 + j;
-          if (key < AT_NK) {
-            const float v = __uint_as_float(s[j]) + __uint_as_float(rr[key / 14]) + __uint_as_float(rr[16 + key % 14]);
-            m = fmaxf(m, v);
-          }
-        }
+        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(bq[j]), __uint_as_float(bq[j + 1])));
+        tmem_ld_wait();
       }
+#pragma unroll
+      for (int j = 0; j < AT_NK - 192; ++j) m = fmaxf(m, __uint_as_float(a[j]));   // keys 192..195
       // the previous pair's O is final by now: write it out and free its TMEM region for S(it+1)
       if (it > 0) epilogue(it - 1, prev_m, prev_sum, prev_blk, prev_pair);
-      // pass 2: p = exp(s - m), row sum, bf16 P tile (K-major, 128B swizzle)
+      // ---- pass 2: p = exp(s - m), row sum, bf16 P tile (K-major, 128B swizzle)
       const float m2 = m * LOG2E;
       float sum = 0.f;
       uint8_t* prow = Ps + hp * AT_P_BYTES + q * 128;
-#pragma unroll
-      for (int c0 = 0; c0 < 224; c0 += 32) {
-        uint32_t s[32];
-        tmem_ld32(t_addr + c0, s);
-        tmem_ld_wait();
+      auto emit = [&](const uint32_t* s, int c) {   // 32 keys starting at 32*c, all valid
+        uint8_t* base = prow + (c >> 1) * 8192;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int key0 = c0 + g * 8;
-          if (key0 < AT_NKP) {
-            float p[8];
+          float p[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int key = key0 + j;
-              if (key < AT_NK) {
-                const float v = __uint_as_float(s[g * 8 + j]) + __uint_as_float(rr[key / 14]) + __uint_as_float(rr[16 + key % 14]);
-                p[j] = ex2(fmaf(v, LOG2E, -m2));
-                sum += p[j];
-              } else {
-                p[j] = 0.f;
-              }
-            }
-            uint4 u;
-            __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
-            const int tile = key0 >> 6, ch = (key0 & 63) >> 3;
-            *reinterpret_cast<uint4*>(prow + tile * 8192 + ((ch ^ (q & 7)) * 16)) = u;
+          for (int j = 0; j < 8; ++j) {
+            p[j] = ex2(fmaf(__uint_as_float(s[g * 8 + j]), LOG2E, -m2));
+            sum += p[j];
           }
+          uint4 u;
+          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
+          *reinterpret_cast<uint4*>(base + ((((c & 1) * 4 + g) ^ qsw) * 16)) = u;
+        }
+      };
+      tmem_ld32(t_addr, a);
+      tmem_ld_wait();
+#pragma unroll 1
+      for (int c = 0; c < 6; c += 2) {
+        tmem_ld32(t_addr + (c + 1) * 32, bq);
+        emit(a, c);
+        tmem_ld_wait();
+        tmem_ld32(t_addr + (c + 2) * 32, a);
+        emit(bq, c + 1);
+        tmem_ld_wait();
+      }
+      {  // keys 192..207: 4 real keys, 12 zero columns (the P.V MMA runs over 208 keys)
+        float p[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          p[j] = 0.f;
+          if (j < AT_NK - 192) {
+            p[j] = ex2(fmaf(__uint_as_float(a[j]), LOG2E, -m2));
+            sum += p[j];
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 u;
+          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(p[g * 8 + 2 * j], p[g * 8 + 2 * j + 1]);
+          *reinterpret_cast<uint4*>(prow + 3 * 8192 + ((g ^ qsw) * 16)) = u;
         }
       }
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -337,7 +366,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       prev_m = m; prev_sum = sum; prev_blk = blk; prev_pair = pair;
     }
     if (n_it > 0) epilogue(n_it - 1, prev_m, prev_sum, prev_blk, prev_pair);
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before exit
   }
 
   tc_fence_before();
@@ -397,7 +425,7 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.nblocks < sms ? P.nblocks : sms;
-  attn_fwd_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, tmR, tmO, P);
+  attn_fwd_tc_kernel<<<grid, AF_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, tmR, tmO, P);
   PHT_LAUNCH_CHECK();
   count_launch(CNT_ATTN_TC);
   *handled = true;
