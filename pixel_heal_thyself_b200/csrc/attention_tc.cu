@@ -435,22 +435,22 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
 
 // =================================================================================================
 // Backward (recompute), one (block, head) per iteration, everything on tcgen05:
-//   S' = Q K'^T, dP = dO V^T            (keys 0..111 in TMEM lanes +0, keys 112..223 in lanes +16: both 16-lane
+//   S = Q K^T + Q REL^T, dP = dO V^T    (keys 0..111 in TMEM lanes +0, keys 112..223 in lanes +16: both 16-lane
 //                                         halves of every sub-partition hold one query row -> 128 busy threads)
-//   P = exp(S' - lse), delta = sum P.dP, dS = P.(dP - delta)   -> bf16 P / dS tiles in smem (128B swizzle)
+//   P = exp(S - lse), delta = sum P.dP, dS = P.(dP - delta)   -> bf16 P / dS tiles in smem (128B swizzle)
 //   dV = P^T dO, dK = dS^T Q             (A operands MN-major: the [query x key] tiles are read transposed)
-//   dQ = dS_ext K_ext                    (K_ext rows 256..287 = relative-position rows, dS_ext cols 256..287 =
-//                                         row / column sums of dS over the 14x14 window => dS.(K + rel) exactly)
-//   d_rel += dS_ext[:, 256..287]^T Q     (one M=64 accumulator that lives in TMEM for the whole kernel)
+//   dQ = dS K + dS REL                   (== dS.(K + rel) exactly, REL = the constant [key][rel_h[r] | rel_w[c]] tile)
+//   dREL += dS^T Q                       (the same product as dK, accumulated in TMEM over the whole kernel; its
+//                                         window-row / window-column sums are d rel_h / d rel_w)
 // dK / dV leave the SM window-major in bf16 (coalesced 128-byte rows, no atomics); a fold kernel sums the <= 4
 // overlapping windows of every pixel deterministically and writes the final NHWC gradients.
 // =================================================================================================
-constexpr int AB_K_ROWS = 288, AB_V_ROWS = 224;
+constexpr int AB_K_ROWS = 224, AB_V_ROWS = 224;                 // 2 x 112 keys (196 real)
 constexpr int AB_Q_BYTES = 8192, AB_K_BYTES = AB_K_ROWS * 128, AB_V_BYTES = AB_V_ROWS * 128;
-constexpr int AB_P_BYTES = 4 * 8192, AB_DS_BYTES = 5 * 8192;
-constexpr int AB_SMEM = 2 * AB_Q_BYTES + AB_K_BYTES + AB_V_BYTES + AB_P_BYTES + AB_DS_BYTES + 256 + 1024;
-constexpr int AB_COL_REL = 112, AB_COL_DP = 144, AB_COL_DV = 0, AB_COL_DK = 128, AB_COL_DQ = 256, AB_COL_RELACC = 448;
-constexpr int AB_REL_PART = 2 * 14 * 32;  // floats per CTA partial
+constexpr int AB_P_BYTES = 4 * 8192, AB_DS_BYTES = 4 * 8192;
+constexpr int AB_SMEM = 2 * AB_Q_BYTES + 2 * AB_K_BYTES + AB_V_BYTES + AB_P_BYTES + AB_DS_BYTES + 256 + 1024;
+constexpr int AB_COL_DP = 112, AB_COL_DV = 0, AB_COL_DK = 128, AB_COL_DQ = 256, AB_COL_RELACC = 320;
+constexpr int AB_REL_PART = AT_NK * 64;  // floats per CTA partial: dREL [196 keys][64]
 
 struct AbP {
   int B, H, W, nbx, nby, nblocks;
@@ -460,7 +460,7 @@ struct AbP {
   const float* lse;
   bf16* dk_scratch;   // [nblocks][4][196][64]
   bf16* dv_scratch;
-  float* rel_part;    // [gridDim.x][896]
+  float* rel_part;    // [gridDim.x][196][64]
 };
 
 __device__ __forceinline__ void st_row64_bf16(bf16* dst, const uint32_t* lo, const uint32_t* hi) {
@@ -483,7 +483,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* Qs = smem;
   uint8_t* dOs = Qs + AB_Q_BYTES;
   uint8_t* Ks = dOs + AB_Q_BYTES;
-  uint8_t* Vs = Ks + AB_K_BYTES;
+  uint8_t* RELs = Ks + AB_K_BYTES;
+  uint8_t* Vs = RELs + AB_K_BYTES;
   uint8_t* Ps = Vs + AB_V_BYTES;
   uint8_t* dSs = Ps + AB_P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(dSs + AB_DS_BYTES);
@@ -496,27 +497,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time smem constants --------------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < (AB_K_ROWS - AT_NK) * 8; i += blockDim.x) {  // K rows 196..287
-    const int R = AT_NK + i / 8, ch = i % 8;
+  for (int i = threadIdx.x; i < AB_K_ROWS * 8; i += blockDim.x) {   // REL tile rows 0..223
+    const int R = i >> 3, ch = i & 7;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (R >= 256) {
-      const int rr = R - 256;  // 0..31: rows 0..13 = [rel_h | 0], rows 16..29 = [0 | rel_w]
-      if (rr < 14 && ch < 4) {
+    if (R < AT_NK) {
+      const int wr = R / 14, wc = R - wr * 14;
+      const float* src = ch < 4 ? P.rel_h + wr * 32 + ch * 8 : P.rel_w + wc * 32 + (ch - 4) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = P.rel_h[rr * 32 + ch * 8 + j];
-      } else if (rr >= 16 && rr < 30 && ch >= 4) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = P.rel_w[(rr - 16) * 32 + (ch - 4) * 8 + j];
-      }
+      for (int j = 0; j < 8; ++j) v[j] = src[j];
     }
     uint4 u;
     __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
     for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(Ks + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
+    *reinterpret_cast<uint4*>(RELs + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
   }
+  for (int i = threadIdx.x; i < (AB_K_ROWS - AT_NK) * 8; i += blockDim.x)   // K rows 196..223
+    *reinterpret_cast<uint4*>(Ks + (AT_NK + i / 8) * 128 + (i % 8) * 16) = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < (AB_V_ROWS - AT_NK) * 8; i += blockDim.x)
     *reinterpret_cast<uint4*>(Vs + (AT_NK + i / 8) * 128 + (i % 8) * 16) = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < (AB_P_BYTES + AB_DS_BYTES) / 16; i += blockDim.x)
@@ -560,12 +559,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ================================ MMA issuer ================================
     if (lane == 0) {
       constexpr uint32_t id_s = umma_idesc_bf16(64, 112, 0, 0);
-      constexpr uint32_t id_rel = umma_idesc_bf16(64, 32, 0, 0);
       constexpr uint32_t id_dvk = umma_idesc_bf16(128, 64, 1, 1);
-      constexpr uint32_t id_racc = umma_idesc_bf16(64, 64, 1, 1);
       constexpr uint32_t id_dq = umma_idesc_bf16(64, 64, 0, 1);
-      const uint32_t q_a = smem_u32(Qs), do_a = smem_u32(dOs), k_a = smem_u32(Ks), v_a = smem_u32(Vs), p_a = smem_u32(Ps),
-                     ds_a = smem_u32(dSs);
+      const uint32_t q_a = smem_u32(Qs), do_a = smem_u32(dOs), k_a = smem_u32(Ks), rel_a = smem_u32(RELs), v_a = smem_u32(Vs),
+                     p_a = smem_u32(Ps), ds_a = smem_u32(dSs);
       for (int it = 0; it < n_it; ++it) {
         mbar_wait(in_full, it & 1);
         mbar_wait(tmem_free, (it & 1) ^ 1);
@@ -575,12 +572,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int hf = 0; hf < 2; ++hf) {  // lane half hf handles keys [112*hf, 112*hf + 112)
           const uint32_t d = tmem_base + ((uint32_t)(hf * 16) << 16);
           const uint64_t kd = umma_desc_k_sw128(k_a + hf * 112 * 128);
-          const uint64_t kr = umma_desc_k_sw128(k_a + 256 * 128);
+          const uint64_t rd = umma_desc_k_sw128(rel_a + hf * 112 * 128);
           const uint64_t vd = umma_desc_k_sw128(v_a + hf * 112 * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, id_s, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d + AB_COL_REL, qd + 2 * k, kr + 2 * k, id_rel, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, rd + 2 * k, id_s, 1u);          // += q . [rel_h | rel_w]
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d + AB_COL_DP, dod + 2 * k, vd + 2 * k, id_s, k ? 1u : 0u);
         }
@@ -597,21 +594,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint64_t qb = umma_desc_mn_sw128(q_a + k * 2048, 8192, 1024);
             umma_bf16(tmem_base + AB_COL_DV + t2 * 64, pa, dob, id_dvk, k ? 1u : 0u);
             umma_bf16(tmem_base + AB_COL_DK + t2 * 64, dsa, qb, id_dvk, k ? 1u : 0u);
+            umma_bf16(tmem_base + AB_COL_RELACC + t2 * 64, dsa, qb, id_dvk, (it | k) ? 1u : 0u);   // lives for the whole kernel
           }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ra = umma_desc_mn_sw128(ds_a + 4 * 8192 + k * 2048, 8192, 1024);
-          const uint64_t qb = umma_desc_mn_sw128(q_a + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base + AB_COL_RELACC, ra, qb, id_racc, (it | k) ? 1u : 0u);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 15; ++kk) {
-          const int tile = kk < 13 ? (kk >> 2) : 4, ks = kk < 13 ? (kk & 3) : kk - 13;
-          const int krow = kk < 13 ? kk * 16 : 256 + (kk - 13) * 16;
-          const uint64_t dsa = umma_desc_k_sw128(ds_a + tile * 8192) + 2 * ks;
-          const uint64_t kb = umma_desc_mn_sw128(k_a + krow * 128, 8192, 1024);
+        for (int kk = 0; kk < 13; ++kk) {   // keys 0..207 (196..207 are zero columns of dS)
+          const uint64_t dsa = umma_desc_k_sw128(ds_a + (kk >> 2) * 8192) + 2 * (kk & 3);
+          const uint64_t kb = umma_desc_mn_sw128(k_a + kk * 2048, 8192, 1024);
+          const uint64_t rb = umma_desc_mn_sw128(rel_a + kk * 2048, 8192, 1024);
           umma_bf16(tmem_base + AB_COL_DQ, dsa, kb, id_dq, kk ? 1u : 0u);
+          umma_bf16(tmem_base + AB_COL_DQ, dsa, rb, id_dq, 1u);
         }
         umma_commit(out_full);
       }
@@ -622,108 +614,80 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int hf = lane >> 4;                    // key half handled by this thread
     const int q = quad * 16 + (lane & 15);       // query row
     const int qy = q >> 3, qx = q & 7;
+    const int qsw = q & 7;
     const float LOG2E = 1.4426950408889634f;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int kvalid = hf ? 84 : 112;            // valid keys of this half: key = 112*hf + k' < 196
+    const int kvalid = hf ? AT_NK - 112 : 112;   // valid keys of this half: key = 112*hf + k' < 196
     uint8_t* prow = Ps + q * 128;
     uint8_t* dsrow = dSs + q * 128;
+    auto lse_of = [&](int it) -> float {
+      const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
+      const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+      return P.lse[(((long long)b * P.H + by * 8 + qy) * P.W + bx * 8 + qx) * 4 + head] * LOG2E;
+    };
+    float l2_next = n_it > 0 ? lse_of(0) : 0.f;
 
     for (int it = 0; it < n_it; ++it) {
       const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
       const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
-      const float l2 = P.lse[(((long long)b * P.H + by * 8 + qy) * P.W + bx * 8 + qx) * 4 + head] * LOG2E;
+      const float l2 = l2_next;
+      if (it + 1 < n_it) l2_next = lse_of(it + 1);   // prefetched one iteration ahead
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
-      uint32_t rr[32];
-      tmem_ld32(lane_addr + AB_COL_REL, rr);
-      tmem_ld_wait();
-      float rh[8], rw[14];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) rh[i] = __uint_as_float(hf ? rr[(8 + i) & 15] : rr[i]);
-#pragma unroll
-      for (int c = 0; c < 14; ++c) rw[c] = __uint_as_float(rr[16 + c]);
-      // ---- pass 1: P = exp(S' - lse) -> smem, delta = sum_j P dP ----
+      // ---- pass 1: P = exp(S - lse) -> smem (and packed registers), delta = sum_j P dP ----
       float delta = 0.f;
+      uint32_t ppk[56];                          // this thread's 112 probabilities, bf16x2
+      uint32_t s[2][16], dp[2][16];
+      tmem_ld16(lane_addr, s[0]);
+      tmem_ld16(lane_addr + AB_COL_DP, dp[0]);
+      tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
-        uint32_t s[16], dp[16];
-        tmem_ld16(lane_addr + i * 16, s);
-        tmem_ld16(lane_addr + AB_COL_DP + i * 16, dp);
-        tmem_ld_wait();
+        if (i < 6) {                             // next 16 columns in flight while these are processed
+          tmem_ld16(lane_addr + (i + 1) * 16, s[(i + 1) & 1]);
+          tmem_ld16(lane_addr + AB_COL_DP + (i + 1) * 16, dp[(i + 1) & 1]);
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           float p[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int kp = i * 16 + g * 8 + j;
-            const float sv = __uint_as_float(s[g * 8 + j]) + rh[kp / 14] + rw[kp % 14];
-            p[j] = kp < kvalid ? ex2(fmaf(sv, LOG2E, -l2)) : 0.f;
-            delta = fmaf(p[j], __uint_as_float(dp[g * 8 + j]), delta);
+            p[j] = kp < kvalid ? ex2(fmaf(__uint_as_float(s[i & 1][g * 8 + j]), LOG2E, -l2)) : 0.f;
+            delta = fmaf(p[j], __uint_as_float(dp[i & 1][g * 8 + j]), delta);
           }
           uint4 u;
           __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
+          ppk[i * 8 + g * 4 + 0] = u.x; ppk[i * 8 + g * 4 + 1] = u.y; ppk[i * 8 + g * 4 + 2] = u.z; ppk[i * 8 + g * 4 + 3] = u.w;
           const int key0 = hf * 112 + i * 16 + g * 8;
-          *reinterpret_cast<uint4*>(prow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ (q & 7)) * 16)) = u;
+          *reinterpret_cast<uint4*>(prow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ qsw) * 16)) = u;
         }
+        if (i < 6) tmem_ld_wait();
       }
       delta += __shfl_xor_sync(0xffffffffu, delta, 16);
-      // ---- pass 2: dS = P (dP - delta) -> smem, window row / column sums for the relative-position terms ----
-      float rsum[8], csum[14];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) rsum[i] = 0.f;
-#pragma unroll
-      for (int c = 0; c < 14; ++c) csum[c] = 0.f;
+      // ---- pass 2: dS = P (dP - delta) -> smem ----
+      tmem_ld16(lane_addr + AB_COL_DP, dp[0]);
+      tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
-        uint32_t dp[16];
-        tmem_ld16(lane_addr + AB_COL_DP + i * 16, dp);
-        tmem_ld_wait();
+        if (i < 6) tmem_ld16(lane_addr + AB_COL_DP + (i + 1) * 16, dp[(i + 1) & 1]);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const int key0 = hf * 112 + i * 16 + g * 8;
-          uint8_t* ppos = prow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ (q & 7)) * 16);
-          const uint4 pu = *reinterpret_cast<const uint4*>(ppos);
-          const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&pu);
-          float ds[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 pf = __bfloat1622float2(ph[j]);
-            ds[2 * j] = pf.x * (__uint_as_float(dp[g * 8 + 2 * j]) - delta);
-            ds[2 * j + 1] = pf.y * (__uint_as_float(dp[g * 8 + 2 * j + 1]) - delta);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int kp = i * 16 + g * 8 + j;
-            rsum[kp / 14] += ds[j];   // ds == 0 for invalid keys (P == 0)
-            csum[kp % 14] += ds[j];
-          }
           uint4 u;
           __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(ds[2 * j], ds[2 * j + 1]);
-          *reinterpret_cast<uint4*>(dsrow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ (q & 7)) * 16)) = u;
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t pw = ppk[i * 8 + g * 4 + j];
+            const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw));
+            uh[j] = __floats2bfloat162_rn(pf.x * (__uint_as_float(dp[i & 1][g * 8 + 2 * j]) - delta),
+                                          pf.y * (__uint_as_float(dp[i & 1][g * 8 + 2 * j + 1]) - delta));
+          }
+          const int key0 = hf * 112 + i * 16 + g * 8;
+          *reinterpret_cast<uint4*>(dsrow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ qsw) * 16)) = u;
         }
-      }
-#pragma unroll
-      for (int c = 0; c < 14; ++c) csum[c] += __shfl_xor_sync(0xffffffffu, csum[c], 16);
-      {
-        // dS_ext columns 256..271 = window-row sums (row r = 8*hf + i), 272..287 = window-column sums
-        uint4 u, w;
-        __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
-        __nv_bfloat162* wh = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a0 = (hf && 2 * j >= 6) ? 0.f : rsum[2 * j], a1 = (hf && 2 * j + 1 >= 6) ? 0.f : rsum[2 * j + 1];
-          uh[j] = __floats2bfloat162_rn(a0, a1);
-          const int c0 = hf * 8 + 2 * j;
-          const float b0 = c0 < 14 ? (hf ? csum[(8 + 2 * j) % 14] : csum[2 * j]) : 0.f;
-          const float b1 = c0 + 1 < 14 ? (hf ? csum[(9 + 2 * j) % 14] : csum[2 * j + 1]) : 0.f;
-          wh[j] = __floats2bfloat162_rn(b0, b1);
-        }
-        *reinterpret_cast<uint4*>(dsrow + 4 * 8192 + (((hf) ^ (q & 7)) * 16)) = u;
-        *reinterpret_cast<uint4*>(dsrow + 4 * 8192 + (((2 + hf) ^ (q & 7)) * 16)) = w;
+        if (i < 6) tmem_ld_wait();
       }
       fence_proxy_async();
       tc_fence_before();
@@ -757,20 +721,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     // relative-position gradient accumulator of this CTA (complete: the last out_full covered its MMAs)
     if (n_it > 0) {
-      uint32_t a[32], c[32];
-      tmem_ld32(lane_addr + AB_COL_RELACC, a);
-      tmem_ld32(lane_addr + AB_COL_RELACC + 32, c);
-      tmem_ld_wait();
-      if (hf == 0) {
-        float* part = P.rel_part + (long long)blockIdx.x * AB_REL_PART;
-        if (q < 14) {
+      float* part = P.rel_part + (long long)blockIdx.x * AB_REL_PART;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) part[q * 32 + j] = __uint_as_float(a[j]);          // d rel_h[q][:]
-        } else if (q >= 16 && q < 30) {
+      for (int t2 = 0; t2 < 2; ++t2) {
+        const int key = t2 * 128 + quad * 32 + lane;
+        uint32_t a[32], c[32];
+        tmem_ld32(lane_addr + AB_COL_RELACC + t2 * 64, a);
+        tmem_ld32(lane_addr + AB_COL_RELACC + t2 * 64 + 32, c);
+        tmem_ld_wait();
+        if (key < AT_NK) {
+          float4* dst = reinterpret_cast<float4*>(part + key * 64);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) part[448 + (q - 16) * 32 + j] = __uint_as_float(c[j]);  // d rel_w[q-16][:]
+          for (int j = 0; j < 8; ++j) {
+            dst[j] = make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]),
+                                 __uint_as_float(a[4 * j + 3]));
+            dst[8 + j] = make_float4(__uint_as_float(c[4 * j]), __uint_as_float(c[4 * j + 1]), __uint_as_float(c[4 * j + 2]),
+                                     __uint_as_float(c[4 * j + 3]));
+          }
         }
       }
+    } else {
+      float* part = P.rel_part + (long long)blockIdx.x * AB_REL_PART;
+      for (int i = threadIdx.x - 64; i < AB_REL_PART; i += 128) part[i] = 0.f;
     }
   }
   tc_fence_before();
@@ -827,14 +799,30 @@ __global__ void attn_bwd_fold_kernel(const bf16* __restrict__ dks, const bf16* _
   }
 }
 
+// d rel_h[r][j] = sum_parts sum_c dREL[(r,c)][j] (j < 32);  d rel_w[c][j] = sum_parts sum_r dREL[(r,c)][32 + j].
+// One block per output element, fixed summation order (deterministic).
 __global__ void attn_bwd_rel_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ d_rel_h,
                                            float* __restrict__ d_rel_w) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= AB_REL_PART) return;
+  const int o = blockIdx.x;            // 0..447: rel_h[r][j], 448..895: rel_w[c][j]
+  const bool is_w = o >= 448;
+  const int rc = (is_w ? o - 448 : o) / 32, j = (is_w ? o - 448 : o) % 32;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(long long)p * AB_REL_PART + i];
-  if (i < 448) d_rel_h[i] = s;
-  else d_rel_w[i - 448] = s;
+  for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
+    const float* base = part + (long long)p * AB_REL_PART;
+    for (int t = 0; t < 14; ++t) {
+      const int key = is_w ? t * 14 + rc : rc * 14 + t;
+      s += base[key * 64 + (is_w ? 32 + j : j)];
+    }
+  }
+  __shared__ float red[64];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)blockDim.x; ++i) t += red[i];
+    if (is_w) d_rel_w[o - 448] = t;
+    else d_rel_h[o] = t;
+  }
 }
 
 static int at_grid(int nblocks) {
@@ -889,7 +877,7 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
   if (fgrid > 148 * 16) fgrid = 148 * 16;
   attn_bwd_fold_kernel<<<fgrid, 256, 0, st>>>(P.dk_scratch, P.dv_scratch, make_view(a->dk), make_view(a->dv), f.B, f.H, f.W,
                                              P.nby, P.nbx);
-  attn_bwd_rel_reduce_kernel<<<(AB_REL_PART + 127) / 128, 128, 0, st>>>(P.rel_part, grid, a->d_rel_h, a->d_rel_w);
+  attn_bwd_rel_reduce_kernel<<<896, 64, 0, st>>>(P.rel_part, grid, a->d_rel_h, a->d_rel_w);
   PHT_LAUNCH_CHECK();
   count_launch(CNT_ATTN_TC);
   count_launch(CNT_OTHER, 2);
