@@ -16,13 +16,14 @@
 //   epilogue O / sum + residual (TMA-loaded tile, updated in place) -> bf16 tile -> TMA store; log-sum-exp saved.
 // Two TMEM regions (one per head pair) ping-pong so S(it+1) is computed while softmax(it) runs.
 // Warps: 0 TMA producer, 1 MMA issuer, 2..5 softmax/epilogue, 6 output store + residual prefetch.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace pht {
 
 using namespace tc;
 
-constexpr int AT_THREADS = 192;                                // backward kernel
 constexpr int AF_THREADS = 224;                                // forward kernel (7 warps)
 constexpr int AT_NK = 196, AT_NKP = 208, AT_NS = 200;          // keys, keys padded to 16 (P / V), S columns = K-tile rows
 constexpr int AT_Q_BYTES = 64 * 128;                           // 8 KB per head
@@ -435,25 +436,48 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
 
 // =================================================================================================
 // Backward (recompute), one (block, head) per iteration, everything on tcgen05:
-//   S = Q K^T + Q REL^T, dP = dO V^T    (keys 0..111 in TMEM lanes +0, keys 112..223 in lanes +16: both 16-lane
-//                                         halves of every sub-partition hold one query row -> 128 busy threads)
+//   S = Q K^T + Q REL^T, dP = dO V^T    (keys 0..103 in TMEM lanes +0, keys 104..207 in lanes +16: both 16-lane
+//                                         halves of every sub-partition hold one query row)
 //   P = exp(S - lse), delta = sum P.dP, dS = P.(dP - delta)   -> bf16 P / dS tiles in smem (128B swizzle)
-//   dV = P^T dO, dK = dS^T Q             (A operands MN-major: the [query x key] tiles are read transposed)
 //   dQ = dS K + dS REL                   (== dS.(K + rel) exactly, REL = the constant [key][rel_h[r] | rel_w[c]] tile)
-//   dREL += dS^T Q                       (the same product as dK, accumulated in TMEM over the whole kernel; its
-//                                         window-row / window-column sums are d rel_h / d rel_w)
+//   dV = P^T dO, dK = dS^T Q             (A operands MN-major: the [query x key] tiles are read transposed)
+//   dREL = sum over the CTA's iterations of dK, accumulated in fp32 registers by the read-out threads (its
+//          window-row / window-column sums are d rel_h / d rel_w)
+// Warps: 0 TMA producer, 1 MMA issuer, 2..9 softmax + read-out.  Two warps share each TMEM sub-partition: they split
+// the S / dP columns of a query row between them (partial deltas exchanged through smem) and the dV / dK key tiles.
+// Pipeline: the operands of iteration i+1 are prefetched (Q, dO, K double-buffered; V reloaded as soon as dP(i) is
+// done), S/dP(i+1) is issued right behind dQ/dV/dK(i) on the tensor pipe, and the dV/dK read-out of iteration i
+// runs while S/dP(i+1) is being computed.  TMEM: S [0,104) dP [104,208) (dQ re-uses [0,64)), dV [208,336), dK [336,464).
 // dK / dV leave the SM window-major in bf16 (coalesced 128-byte rows, no atomics); a fold kernel sums the <= 4
 // overlapping windows of every pixel deterministically and writes the final NHWC gradients.
 // =================================================================================================
-constexpr int AB_K_ROWS = 224, AB_V_ROWS = 224;                 // 2 x 112 keys (196 real)
-constexpr int AB_Q_BYTES = 8192, AB_K_BYTES = AB_K_ROWS * 128, AB_V_BYTES = AB_V_ROWS * 128;
+constexpr int AB_THREADS = 320;
+constexpr int AB_HALF = 104;                                    // keys per lane half (2 x 104 = 208 >= 196)
+constexpr int AB_ROWS = 2 * AB_HALF;                            // K / V / REL tile rows
+constexpr int AB_Q_BYTES = 8192, AB_K_BYTES = AB_ROWS * 128;
 constexpr int AB_P_BYTES = 4 * 8192, AB_DS_BYTES = 4 * 8192;
-constexpr int AB_SMEM = 2 * AB_Q_BYTES + 2 * AB_K_BYTES + AB_V_BYTES + AB_P_BYTES + AB_DS_BYTES + 256 + 1024;
-constexpr int AB_COL_DP = 112, AB_COL_DV = 0, AB_COL_DK = 128, AB_COL_DQ = 256, AB_COL_RELACC = 320;
+constexpr int AB_STAGE_BYTES = 2 * AB_Q_BYTES + AB_K_BYTES;     // Q, dO, K
+constexpr int AB_STG_BYTES = 32 * 64;                            // per-warp read-out staging tile: 32 key rows x 32 ch bf16
+constexpr int AB_SMEM = 2 * AB_STAGE_BYTES + 2 * AB_K_BYTES + AB_P_BYTES + AB_DS_BYTES + 8 * AB_STG_BYTES + 1024 + 1024;
+static_assert(AB_SMEM <= 232448, "attn_bwd_tc: shared memory budget");
+constexpr int AB_COL_DP = AB_HALF, AB_COL_DQ = 0, AB_COL_DV = 2 * AB_HALF, AB_COL_DK = 2 * AB_HALF + 128;
+static_assert(AB_COL_DK + 128 <= 512, "attn_bwd_tc: TMEM budget");
+constexpr int AB_PART0 = 56;                                    // S/dP columns of a lane half handled by warp part 0 (part 1: 48)
 constexpr int AB_REL_PART = AT_NK * 64;  // floats per CTA partial: dREL [196 keys][64]
 
+constexpr int AB_TRACE_ITERS = 48, AB_TRACE_EVENTS = 8;
+__device__ long long g_attn_bwd_trace[AB_TRACE_ITERS * AB_TRACE_EVENTS];   // clock64 stamps of CTA 0 (diagnostics)
+static int g_attn_trace_on = 0;
+void set_attn_trace(int v) { g_attn_trace_on = v; }
+int read_attn_trace(long long* host, int n) {
+  if (n > AB_TRACE_ITERS * AB_TRACE_EVENTS) n = AB_TRACE_ITERS * AB_TRACE_EVENTS;
+  PHT_CUDA(cudaDeviceSynchronize());
+  PHT_CUDA(cudaMemcpyFromSymbol(host, g_attn_bwd_trace, (size_t)n * sizeof(long long)));
+  return n;
+}
+
 struct AbP {
-  int B, H, W, nbx, nby, nblocks;
+  int B, H, W, nbx, nby, nblocks, trace;
   View dq;
   const float* rel_h;
   const float* rel_w;
@@ -463,41 +487,54 @@ struct AbP {
   float* rel_part;    // [gridDim.x][196][64]
 };
 
-__device__ __forceinline__ void st_row64_bf16(bf16* dst, const uint32_t* lo, const uint32_t* hi) {
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t u;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
+  return u;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_row32_bf16(bf16* dst, const uint32_t* r) {
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const uint32_t* r = g < 4 ? lo + g * 8 : hi + (g - 4) * 8;
+  for (int g = 0; g < 4; ++g) {
     uint4 u;
     __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
     *reinterpret_cast<uint4*>(dst + g * 8) = u;
   }
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AbP P) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const AbP P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
-  uint8_t* Qs = smem;
-  uint8_t* dOs = Qs + AB_Q_BYTES;
-  uint8_t* Ks = dOs + AB_Q_BYTES;
-  uint8_t* RELs = Ks + AB_K_BYTES;
+  uint8_t* St = smem;                                   // [2 stages][Q 8K | dO 8K | K 26K]
+  uint8_t* RELs = St + 2 * AB_STAGE_BYTES;
   uint8_t* Vs = RELs + AB_K_BYTES;
-  uint8_t* Ps = Vs + AB_V_BYTES;
+  uint8_t* Ps = Vs + AB_K_BYTES;
   uint8_t* dSs = Ps + AB_P_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dSs + AB_DS_BYTES);
-  uint64_t* in_full = bars + 0;
-  uint64_t* sdp_full = bars + 1;
-  uint64_t* ds_full = bars + 2;
-  uint64_t* out_full = bars + 3;
-  uint64_t* tmem_free = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* STG = dSs + AB_DS_BYTES;                      // [8 warps][32 rows x 64 B]
+  float* dpart = reinterpret_cast<float*>(STG + 8 * AB_STG_BYTES);   // [2 parts][64 queries] partial deltas
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dpart + 128);
+  uint64_t* qk_full = bars + 0;    // [2]
+  uint64_t* qk_empty = bars + 2;   // [2]
+  uint64_t* v_full = bars + 4;
+  uint64_t* v_empty = bars + 5;
+  uint64_t* sdp_full = bars + 6;
+  uint64_t* ds_full = bars + 7;
+  uint64_t* dq_full = bars + 8;
+  uint64_t* dq_free = bars + 9;
+  uint64_t* out_full = bars + 10;
+  uint64_t* dvk_free = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time smem constants --------------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < AB_K_ROWS * 8; i += blockDim.x) {   // REL tile rows 0..223
+  for (int i = threadIdx.x; i < AB_ROWS * 8; i += blockDim.x) {   // REL tile rows 0..207
     const int R = i >> 3, ch = i & 7;
     float v[8];
 #pragma unroll
@@ -514,10 +551,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
     *reinterpret_cast<uint4*>(RELs + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
   }
-  for (int i = threadIdx.x; i < (AB_K_ROWS - AT_NK) * 8; i += blockDim.x)   // K rows 196..223
-    *reinterpret_cast<uint4*>(Ks + (AT_NK + i / 8) * 128 + (i % 8) * 16) = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < (AB_V_ROWS - AT_NK) * 8; i += blockDim.x)
-    *reinterpret_cast<uint4*>(Vs + (AT_NK + i / 8) * 128 + (i % 8) * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 3 * (AB_ROWS - AT_NK) * 8; i += blockDim.x) {   // K (both stages) / V rows 196..207
+    const int which = i / ((AB_ROWS - AT_NK) * 8), rem = i % ((AB_ROWS - AT_NK) * 8);
+    uint8_t* tile = which < 2 ? St + which * AB_STAGE_BYTES + 2 * AB_Q_BYTES : Vs;
+    *reinterpret_cast<uint4*>(tile + (AT_NK + rem / 8) * 128 + (rem % 8) * 16) = make_uint4(0, 0, 0, 0);
+  }
   for (int i = threadIdx.x; i < (AB_P_BYTES + AB_DS_BYTES) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(Ps)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && lane == 0) {
@@ -525,11 +563,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     prefetch_tmap(&tmDO);
-    mbar_init(in_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qk_full[s], 1);
+      mbar_init(&qk_empty[s], 1);
+    }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
     mbar_init(sdp_full, 1);
-    mbar_init(ds_full, 128);
+    mbar_init(ds_full, 256);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 256);
     mbar_init(out_full, 1);
-    mbar_init(tmem_free, 128);
+    mbar_init(dvk_free, 256);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -540,6 +585,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const int my_blocks = (P.nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_it = 4 * my_blocks;  // (block, head) iterations
+  const bool tracing = P.trace && blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2);
+  auto stamp = [&](int it, int ev) {
+    if (tracing && it < AB_TRACE_ITERS) g_attn_bwd_trace[it * AB_TRACE_EVENTS + ev] = clock64();
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -547,43 +596,65 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int it = 0; it < n_it; ++it) {
         const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
         const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
-        mbar_wait(out_full, (it & 1) ^ 1);  // all MMAs of the previous iteration have read the operand buffers
-        mbar_expect_tx(in_full, 2 * AB_Q_BYTES + 2 * AT_KV_BOX_BYTES);
-        tma_load_4d(Qs, &tmQ, in_full, head * 64, bx * 8, by * 8, b);
-        tma_load_4d(dOs, &tmDO, in_full, head * 64, bx * 8, by * 8, b);
-        tma_load_4d(Ks, &tmK, in_full, head * 64, bx * 8 - 3, by * 8 - 3, b);
-        tma_load_4d(Vs, &tmV, in_full, head * 64, bx * 8 - 3, by * 8 - 3, b);
+        const int s = it & 1;
+        uint8_t* st = St + s * AB_STAGE_BYTES;
+        mbar_wait(&qk_empty[s], ((it >> 1) & 1) ^ 1);   // dQ/dV/dK MMAs of iteration it-2 have read this stage
+        mbar_expect_tx(&qk_full[s], 2 * AB_Q_BYTES + AT_KV_BOX_BYTES);
+        tma_load_4d(st, &tmQ, &qk_full[s], head * 64, bx * 8, by * 8, b);
+        tma_load_4d(st + AB_Q_BYTES, &tmDO, &qk_full[s], head * 64, bx * 8, by * 8, b);
+        tma_load_4d(st + 2 * AB_Q_BYTES, &tmK, &qk_full[s], head * 64, bx * 8 - 3, by * 8 - 3, b);
+        mbar_wait(v_empty, (it & 1) ^ 1);               // dP of iteration it-1 complete
+        mbar_expect_tx(v_full, AT_KV_BOX_BYTES);
+        tma_load_4d(Vs, &tmV, v_full, head * 64, bx * 8 - 3, by * 8 - 3, b);
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t id_s = umma_idesc_bf16(64, 112, 0, 0);
+      constexpr uint32_t id_s = umma_idesc_bf16(64, AB_HALF, 0, 0);
       constexpr uint32_t id_dvk = umma_idesc_bf16(128, 64, 1, 1);
       constexpr uint32_t id_dq = umma_idesc_bf16(64, 64, 0, 1);
-      const uint32_t q_a = smem_u32(Qs), do_a = smem_u32(dOs), k_a = smem_u32(Ks), rel_a = smem_u32(RELs), v_a = smem_u32(Vs),
-                     p_a = smem_u32(Ps), ds_a = smem_u32(dSs);
+      const uint32_t rel_a = smem_u32(RELs), v_a = smem_u32(Vs), p_a = smem_u32(Ps), ds_a = smem_u32(dSs);
       for (int it = 0; it < n_it; ++it) {
-        mbar_wait(in_full, it & 1);
-        mbar_wait(tmem_free, (it & 1) ^ 1);
+        const int s = it & 1;
+        const uint32_t q_a = smem_u32(St + s * AB_STAGE_BYTES), do_a = q_a + AB_Q_BYTES, k_a = q_a + 2 * AB_Q_BYTES;
+        mbar_wait(&qk_full[s], (it >> 1) & 1);
+        mbar_wait(v_full, it & 1);
+        if (it > 0) mbar_wait(dq_free, (it - 1) & 1);   // dQ(it-1) read out of the columns S(it) is about to overwrite
         tc_fence_after();
+        stamp(it, 0);
         const uint64_t qd = umma_desc_k_sw128(q_a), dod = umma_desc_k_sw128(do_a);
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {  // lane half hf handles keys [112*hf, 112*hf + 112)
+        for (int hf = 0; hf < 2; ++hf) {  // lane half hf handles keys [104*hf, 104*hf + 104)
           const uint32_t d = tmem_base + ((uint32_t)(hf * 16) << 16);
-          const uint64_t kd = umma_desc_k_sw128(k_a + hf * 112 * 128);
-          const uint64_t rd = umma_desc_k_sw128(rel_a + hf * 112 * 128);
-          const uint64_t vd = umma_desc_k_sw128(v_a + hf * 112 * 128);
+          const uint64_t kd = umma_desc_k_sw128(k_a + hf * AB_HALF * 128);
+          const uint64_t rd = umma_desc_k_sw128(rel_a + hf * AB_HALF * 128);
+          const uint64_t vd = umma_desc_k_sw128(v_a + hf * AB_HALF * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d + AB_COL_DP, dod + 2 * k, vd + 2 * k, id_s, k ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, id_s, k ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, rd + 2 * k, id_s, 1u);          // += q . [rel_h | rel_w]
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d + AB_COL_DP, dod + 2 * k, vd + 2 * k, id_s, k ? 1u : 0u);
         }
+        umma_commit(v_empty);
         umma_commit(sdp_full);
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
+        stamp(it, 1);
+#pragma unroll
+        for (int kk = 0; kk < 13; ++kk) {   // dQ first (keys 0..207; 196..207 are zero columns of dS)
+          const uint64_t dsa = umma_desc_k_sw128(ds_a + (kk >> 2) * 8192) + 2 * (kk & 3);
+          const uint64_t kb = umma_desc_mn_sw128(k_a + kk * 2048, 8192, 1024);
+          const uint64_t rb = umma_desc_mn_sw128(rel_a + kk * 2048, 8192, 1024);
+          umma_bf16(tmem_base + AB_COL_DQ, dsa, kb, id_dq, kk ? 1u : 0u);
+          umma_bf16(tmem_base + AB_COL_DQ, dsa, rb, id_dq, 1u);
+        }
+        umma_commit(dq_full);
+        if (it > 0) {
+          mbar_wait(dvk_free, (it - 1) & 1);            // dV/dK(it-1) read out
+          tc_fence_after();
+        }
 #pragma unroll
         for (int t2 = 0; t2 < 2; ++t2) {
 #pragma unroll
@@ -594,38 +665,117 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint64_t qb = umma_desc_mn_sw128(q_a + k * 2048, 8192, 1024);
             umma_bf16(tmem_base + AB_COL_DV + t2 * 64, pa, dob, id_dvk, k ? 1u : 0u);
             umma_bf16(tmem_base + AB_COL_DK + t2 * 64, dsa, qb, id_dvk, k ? 1u : 0u);
-            umma_bf16(tmem_base + AB_COL_RELACC + t2 * 64, dsa, qb, id_dvk, (it | k) ? 1u : 0u);   // lives for the whole kernel
           }
         }
-#pragma unroll
-        for (int kk = 0; kk < 13; ++kk) {   // keys 0..207 (196..207 are zero columns of dS)
-          const uint64_t dsa = umma_desc_k_sw128(ds_a + (kk >> 2) * 8192) + 2 * (kk & 3);
-          const uint64_t kb = umma_desc_mn_sw128(k_a + kk * 2048, 8192, 1024);
-          const uint64_t rb = umma_desc_mn_sw128(rel_a + kk * 2048, 8192, 1024);
-          umma_bf16(tmem_base + AB_COL_DQ, dsa, kb, id_dq, kk ? 1u : 0u);
-          umma_bf16(tmem_base + AB_COL_DQ, dsa, rb, id_dq, 1u);
-        }
         umma_commit(out_full);
+        umma_commit(&qk_empty[s]);
       }
     }
   } else {
-    // ================================ softmax / dS / read-out (warps 2..5) ================================
-    const int quad = warp & 3;
+    // ================================ softmax / dS / read-out (warps 2..9) ================================
+    const int sp = warp & 3;                     // TMEM sub-partition of this warp
+    const int part = (warp - 2) >> 2;            // which of the two warps sharing the sub-partition
     const int hf = lane >> 4;                    // key half handled by this thread
-    const int q = quad * 16 + (lane & 15);       // query row
+    const int q = sp * 16 + (lane & 15);         // query row
     const int qy = q >> 3, qx = q & 7;
     const int qsw = q & 7;
     const float LOG2E = 1.4426950408889634f;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int kvalid = hf ? AT_NK - 112 : 112;   // valid keys of this half: key = 112*hf + k' < 196
-    uint8_t* prow = Ps + q * 128;
-    uint8_t* dsrow = dSs + q * 128;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(sp * 32) << 16);
+    const int col0 = part * AB_PART0;            // first S/dP column of this thread (7 / 6 groups of 8 columns)
+    const uint32_t p_row = smem_u32(Ps + q * 128), ds_row = smem_u32(dSs + q * 128);
+    uint32_t goff[7];                            // byte offset of the 16-byte cell of column group g inside a P / dS row
+#pragma unroll
+    for (int g = 0; g < 7; ++g) {
+      const int key0 = hf * AB_HALF + col0 + g * 8;
+      goff[g] = (uint32_t)((key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ qsw) * 16));
+    }
+    const int row0 = part * 128 + sp * 32;            // first key row of dV / dK read out by this warp
+    const bool rows_valid = row0 < AT_NK;             // warp-uniform (the last warp's rows are all padding)
+    uint8_t* stage = STG + (warp - 2) * AB_STG_BYTES; // [32 rows][64 B] bf16, 64B-swizzled like the TMA box
+    const uint32_t stage_row = smem_u32(stage) + lane * 64;
+    const int ssw = (lane >> 1) & 3;
+    float racc[64];                                   // dREL row accumulator (== sum of this thread's dK rows)
+#pragma unroll
+    for (int j = 0; j < 64; ++j) racc[j] = 0.f;
     auto lse_of = [&](int it) -> float {
       const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
       const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
       return P.lse[(((long long)b * P.H + by * 8 + qy) * P.W + bx * 8 + qx) * 4 + head] * LOG2E;
     };
     float l2_next = n_it > 0 ? lse_of(0) : 0.f;
+
+    // P = exp(S - lse) -> smem (and packed registers), partial delta; then dS = P (dP - delta) -> smem.
+    // PART is a compile-time copy of `part` so that group counts and the padding mask fold away.
+    auto softmax_ds = [&](auto part_c, float l2) {
+      constexpr int PART = decltype(part_c)::value;
+      constexpr int NG = PART ? (AB_HALF - AB_PART0) / 8 : AB_PART0 / 8;   // 6 / 7 groups of 8 columns
+      constexpr int NC = (NG + 1) / 2;                                     // 16-column TMEM loads
+      constexpr int C0 = PART * AB_PART0;
+      uint32_t ppk[NG * 4];                      // this thread's probabilities, bf16x2
+      uint32_t s[2][16], dp[2][16];
+      float d0 = 0.f, d1 = 0.f;
+      tmem_ld16(lane_addr + C0, s[0]);
+      tmem_ld16(lane_addr + AB_COL_DP + C0, dp[0]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        if (i + 1 < NC) {                        // next 16 columns in flight while these are processed
+          tmem_ld16(lane_addr + C0 + (i + 1) * 16, s[(i + 1) & 1]);
+          tmem_ld16(lane_addr + AB_COL_DP + C0 + (i + 1) * 16, dp[(i + 1) & 1]);
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int gi = i * 2 + g;
+          if (gi < NG) {
+            float p[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              p[j] = ex2(fmaf(__uint_as_float(s[i & 1][g * 8 + j]), LOG2E, -l2));
+              // keys 196..207 (second lane half, columns 92..103) are padding
+              if (PART == 1 && C0 + gi * 8 + j >= AT_NK - AB_HALF) p[j] = hf ? 0.f : p[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              d0 = fmaf(p[j], __uint_as_float(dp[i & 1][g * 8 + j]), d0);
+              d1 = fmaf(p[j + 1], __uint_as_float(dp[i & 1][g * 8 + j + 1]), d1);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ppk[gi * 4 + j] = pack_bf16x2(p[2 * j], p[2 * j + 1]);
+            st_shared_v4(p_row + goff[gi], ppk[gi * 4], ppk[gi * 4 + 1], ppk[gi * 4 + 2], ppk[gi * 4 + 3]);
+          }
+        }
+        if (i + 1 < NC) tmem_ld_wait();
+      }
+      float delta = d0 + d1;
+      delta += __shfl_xor_sync(0xffffffffu, delta, 16);
+      if (hf == 0) dpart[PART * 64 + q] = delta;
+      tmem_ld16(lane_addr + AB_COL_DP + C0, dp[0]);   // re-read dP while waiting for the other warp's partial
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      delta = dpart[q] + dpart[64 + q];
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        if (i + 1 < NC) tmem_ld16(lane_addr + AB_COL_DP + C0 + (i + 1) * 16, dp[(i + 1) & 1]);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int gi = i * 2 + g;
+          if (gi < NG) {
+            uint32_t u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t pw = ppk[gi * 4 + j];
+              const float plo = __uint_as_float(pw << 16), phi = __uint_as_float(pw & 0xffff0000u);
+              u[j] = pack_bf16x2(plo * (__uint_as_float(dp[i & 1][g * 8 + 2 * j]) - delta),
+                                 phi * (__uint_as_float(dp[i & 1][g * 8 + 2 * j + 1]) - delta));
+            }
+            st_shared_v4(ds_row + goff[gi], u[0], u[1], u[2], u[3]);
+          }
+        }
+        if (i + 1 < NC) tmem_ld_wait();
+      }
+    };
 
     for (int it = 0; it < n_it; ++it) {
       const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
@@ -634,115 +784,81 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (it + 1 < n_it) l2_next = lse_of(it + 1);   // prefetched one iteration ahead
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
-      // ---- pass 1: P = exp(S - lse) -> smem (and packed registers), delta = sum_j P dP ----
-      float delta = 0.f;
-      uint32_t ppk[56];                          // this thread's 112 probabilities, bf16x2
-      uint32_t s[2][16], dp[2][16];
-      tmem_ld16(lane_addr, s[0]);
-      tmem_ld16(lane_addr + AB_COL_DP, dp[0]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        if (i < 6) {                             // next 16 columns in flight while these are processed
-          tmem_ld16(lane_addr + (i + 1) * 16, s[(i + 1) & 1]);
-          tmem_ld16(lane_addr + AB_COL_DP + (i + 1) * 16, dp[(i + 1) & 1]);
-        }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float p[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int kp = i * 16 + g * 8 + j;
-            p[j] = kp < kvalid ? ex2(fmaf(__uint_as_float(s[i & 1][g * 8 + j]), LOG2E, -l2)) : 0.f;
-            delta = fmaf(p[j], __uint_as_float(dp[i & 1][g * 8 + j]), delta);
-          }
-          uint4 u;
-          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
-          ppk[i * 8 + g * 4 + 0] = u.x; ppk[i * 8 + g * 4 + 1] = u.y; ppk[i * 8 + g * 4 + 2] = u.z; ppk[i * 8 + g * 4 + 3] = u.w;
-          const int key0 = hf * 112 + i * 16 + g * 8;
-          *reinterpret_cast<uint4*>(prow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ qsw) * 16)) = u;
-        }
-        if (i < 6) tmem_ld_wait();
-      }
-      delta += __shfl_xor_sync(0xffffffffu, delta, 16);
-      // ---- pass 2: dS = P (dP - delta) -> smem ----
-      tmem_ld16(lane_addr + AB_COL_DP, dp[0]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        if (i < 6) tmem_ld16(lane_addr + AB_COL_DP + (i + 1) * 16, dp[(i + 1) & 1]);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint4 u;
-          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t pw = ppk[i * 8 + g * 4 + j];
-            const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw));
-            uh[j] = __floats2bfloat162_rn(pf.x * (__uint_as_float(dp[i & 1][g * 8 + 2 * j]) - delta),
-                                          pf.y * (__uint_as_float(dp[i & 1][g * 8 + 2 * j + 1]) - delta));
-          }
-          const int key0 = hf * 112 + i * 16 + g * 8;
-          *reinterpret_cast<uint4*>(dsrow + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ qsw) * 16)) = u;
-        }
-        if (i < 6) tmem_ld_wait();
-      }
+      stamp(it, 2);
+      if (part == 0) softmax_ds(std::integral_constant<int, 0>{}, l2);
+      else softmax_ds(std::integral_constant<int, 1>{}, l2);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(ds_full);
-      // ---- read-out: dV, dK (window-major bf16 scratch), dQ ----
+      stamp(it, 3);
+      // ---- read-out: dQ (32 channels per warp part) ----
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      stamp(it, 4);
+      {
+        uint32_t a[32];
+        tmem_ld32(lane_addr + AB_COL_DQ + part * 32, a);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_free);
+        if (hf == 0) st_row32_bf16((bf16*)P.dq.ptr + view_off(P.dq, b, by * 8 + qy, bx * 8 + qx) + head * 64 + part * 32, a);
+      }
+      // ---- read-out: dV, dK rows -> 64B-swizzled smem tile -> TMA store into the window-major bf16 scratch;
+      //      dREL accumulation from the fp32 dK rows ----
       mbar_wait(out_full, it & 1);
       tc_fence_after();
-      const long long srow = ((long long)blk * 4 + head) * AT_NK;
-#pragma unroll
-      for (int t2 = 0; t2 < 2; ++t2) {
-        const int key = t2 * 128 + quad * 32 + lane;
-        uint32_t a[32], c[32];
-        tmem_ld32(lane_addr + AB_COL_DV + t2 * 64, a);
-        tmem_ld32(lane_addr + AB_COL_DV + t2 * 64 + 32, c);
-        tmem_ld_wait();
-        if (key < AT_NK) st_row64_bf16(P.dv_scratch + (srow + key) * 64, a, c);
-        tmem_ld32(lane_addr + AB_COL_DK + t2 * 64, a);
-        tmem_ld32(lane_addr + AB_COL_DK + t2 * 64 + 32, c);
-        tmem_ld_wait();
-        if (key < AT_NK) st_row64_bf16(P.dk_scratch + (srow + key) * 64, a, c);
-      }
+      stamp(it, 5);
       {
         uint32_t a[32], c[32];
-        tmem_ld32(lane_addr + AB_COL_DQ, a);
-        tmem_ld32(lane_addr + AB_COL_DQ + 32, c);
-        tmem_ld_wait();
-        if (hf == 0) st_row64_bf16((bf16*)P.dq.ptr + view_off(P.dq, b, by * 8 + qy, bx * 8 + qx) + head * 64, a, c);
-      }
-      tc_fence_before();
-      mbar_arrive(tmem_free);
-    }
-    // relative-position gradient accumulator of this CTA (complete: the last out_full covered its MMAs)
-    if (n_it > 0) {
-      float* part = P.rel_part + (long long)blockIdx.x * AB_REL_PART;
+        const int zrow = blk * 4 + head;
+        auto stage_store = [&](const uint32_t* r, const CUtensorMap* tm, int ch0) {
+          if (rows_valid) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous box read out
+            __syncwarp();
 #pragma unroll
-      for (int t2 = 0; t2 < 2; ++t2) {
-        const int key = t2 * 128 + quad * 32 + lane;
-        uint32_t a[32], c[32];
-        tmem_ld32(lane_addr + AB_COL_RELACC + t2 * 64, a);
-        tmem_ld32(lane_addr + AB_COL_RELACC + t2 * 64 + 32, c);
-        tmem_ld_wait();
-        if (key < AT_NK) {
-          float4* dst = reinterpret_cast<float4*>(part + key * 64);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            dst[j] = make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]),
-                                 __uint_as_float(a[4 * j + 3]));
-            dst[8 + j] = make_float4(__uint_as_float(c[4 * j]), __uint_as_float(c[4 * j + 1]), __uint_as_float(c[4 * j + 2]),
-                                     __uint_as_float(c[4 * j + 3]));
+            for (int g = 0; g < 4; ++g)
+              st_shared_v4(stage_row + ((g ^ ssw) * 16), pack_bf16x2(__uint_as_float(r[g * 8]), __uint_as_float(r[g * 8 + 1])),
+                           pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
+                           pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])),
+                           pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(stage)), "r"(ch0), "r"(row0), "r"(zrow)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
           }
-        }
+        };
+        tmem_ld32(lane_addr + AB_COL_DV + part * 64, a);
+        tmem_ld_wait();
+        tmem_ld32(lane_addr + AB_COL_DV + part * 64 + 32, c);
+        stage_store(a, &tmDV, 0);
+        tmem_ld_wait();
+        tmem_ld32(lane_addr + AB_COL_DK + part * 64, a);
+        stage_store(c, &tmDV, 32);
+        tmem_ld_wait();
+        tmem_ld32(lane_addr + AB_COL_DK + part * 64 + 32, c);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) racc[j] += __uint_as_float(a[j]);
+        stage_store(a, &tmDK, 0);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dvk_free);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) racc[32 + j] += __uint_as_float(c[j]);
+        stage_store(c, &tmDK, 32);
       }
-    } else {
-      float* part = P.rel_part + (long long)blockIdx.x * AB_REL_PART;
-      for (int i = threadIdx.x - 64; i < AB_REL_PART; i += 128) part[i] = 0.f;
+      stamp(it, 6);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all scratch stores complete before exit
+    // relative-position gradient partial of this CTA
+    const int rkey = row0 + lane;
+    if (rkey < AT_NK) {
+      float4* dst = reinterpret_cast<float4*>(P.rel_part + (long long)blockIdx.x * AB_REL_PART + rkey * 64);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[j] = make_float4(racc[4 * j], racc[4 * j + 1], racc[4 * j + 2], racc[4 * j + 3]);
     }
   }
   tc_fence_before();
@@ -860,17 +976,28 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
   P.B = f.B; P.H = f.H; P.W = f.W; P.nbx = f.W / 8; P.nby = f.H / 8; P.nblocks = f.B * P.nbx * P.nby;
   P.dq = make_view(a->dq);
   P.rel_h = f.rel_h; P.rel_w = f.rel_w; P.lse = f.lse;
+  P.trace = g_attn_trace_on;
   const size_t scratch = (size_t)P.nblocks * 4 * AT_NK * 64;
   P.dk_scratch = (bf16*)a->workspace;
   P.dv_scratch = P.dk_scratch + scratch;
   P.rel_part = (float*)(P.dv_scratch + scratch);
+  CUtensorMap tmDK, tmDV;   // window-major scratch as [nblocks*4][196 keys][64 ch], 32-key x 32-channel boxes, 64B swizzle
+  {
+    uint64_t dims[3] = {64, (uint64_t)AT_NK, (uint64_t)P.nblocks * 4};
+    uint64_t strides[2] = {128, (uint64_t)AT_NK * 128};
+    uint32_t box[3] = {32, 32, 1};
+    rc = make_tmap_bf16(&tmDK, P.dk_scratch, 3, dims, strides, box, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmDV, P.dv_scratch, 3, dims, strides, box, 64);
+    if (rc) return rc;
+  }
   static bool attr = false;
   if (!attr) {
     PHT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     attr = true;
   }
   const int grid = at_grid(P.nblocks);
-  attn_bwd_tc_kernel<<<grid, AT_THREADS, AB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, P);
+  attn_bwd_tc_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, tmDK, tmDV, P);
   PHT_LAUNCH_CHECK();
   long long items = (long long)f.B * f.H * f.W * 32;
   int fgrid = (int)((items + 255) / 256);

@@ -639,21 +639,27 @@ struct PackJob {
   int dtype;
   int pad_;
 };
+// One thread per (o, i) pair, looping over the taps: the thread re-reads its own contiguous OIHW taps (L1 hits after the
+// first) and the warp's stores are contiguous in the packed layout for every tap (the fastest thread index follows the
+// packed layout's fastest index: i for the forward [tap][N][K] pack, o for the transposed / tap-folded packs).
 __global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs) {
   const PackJob j = jobs[blockIdx.y];
   const PackP a = j.p;
-  long long total = (long long)a.O * a.I * a.ks * a.ks;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int kx = (int)(idx % a.ks);
-    long long r = idx / a.ks;
-    int ky = (int)(r % a.ks); r /= a.ks;
-    int i = (int)(r % a.I);
-    int o = (int)(r / a.I);
-    if (i < a.i_begin || i >= a.i_begin + a.i_count) continue;
-    const float v = j.w[idx] * a.scale;
-    const long long di = packed_index(a, o, i - a.i_begin, ky, kx);
-    if (j.dtype == PHT_F32) ((float*)j.dst)[di] = v;
-    else ((bf16*)j.dst)[di] = __float2bfloat16_rn(v);
+  const int T = a.ks * a.ks;
+  const long long pairs = (long long)a.O * a.i_count;
+  const bool o_fast = a.transpose != 0 && a.grid <= 0;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pairs; p += (long long)gridDim.x * blockDim.x) {
+    int o, i;
+    if (o_fast) { o = (int)(p % a.O); i = (int)(p / a.O); }
+    else { i = (int)(p % a.i_count); o = (int)(p / a.i_count); }
+    const float* src = j.w + ((long long)o * a.I + a.i_begin + i) * T;
+    for (int t = 0; t < T; ++t) {
+      const int ky = t / a.ks, kx = t - ky * a.ks;
+      const float v = __ldg(src + t) * a.scale;
+      const long long di = packed_index(a, o, i, ky, kx);
+      if (j.dtype == PHT_F32) ((float*)j.dst)[di] = v;
+      else ((bf16*)j.dst)[di] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -1003,7 +1009,7 @@ int pht_pack_weights_batched(const pht_pack_args* jobs, int32_t n, void* table_d
     if (rc) return rc;
     PHT_CHECK_ARG(jobs[i].dtype == PHT_F32 || jobs[i].dtype == PHT_BF16, "pack_batched: bad dtype");
     host[i].w = jobs[i].w; host[i].dst = jobs[i].packed; host[i].p = p; host[i].dtype = jobs[i].dtype; host[i].pad_ = 0;
-    long long total = (long long)p.O * p.I * p.ks * p.ks;
+    long long total = (long long)p.O * p.i_count;   // one thread per (o, i) pair
     if (total > max_total) max_total = total;
   }
   if (upload) PHT_CUDA(cudaMemcpyAsync(table_dev, host.data(), (size_t)n * sizeof(PackJob), cudaMemcpyHostToDevice, st));

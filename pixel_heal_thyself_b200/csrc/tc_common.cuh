@@ -146,9 +146,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
 
-// bf16 tensor map of rank `rank` (dims fastest-first, strides in BYTES for dims 1..rank-1), 128B swizzle, zero OOB fill
+// bf16 tensor map of rank `rank` (dims fastest-first, strides in BYTES for dims 1..rank-1), 128B (or 64B) swizzle,
+// zero OOB fill
 int make_tmap_bf16(CUtensorMap* out, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+                   const uint32_t* box, int swizzle_bytes = 128);
 
 }  // namespace tc
 }  // namespace pht

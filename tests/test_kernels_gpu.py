@@ -263,7 +263,7 @@ def _attn_inputs(B, C, H, W, dtype, seed):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,C,H,W", [(1, 256, 16, 24), (2, 32, 8, 8), (1, 256, 8, 8)])
+@pytest.mark.parametrize("B,C,H,W", [(1, 256, 16, 24), (2, 32, 8, 8), (1, 256, 8, 8), (2, 256, 96, 104)])
 def test_attention_forward_backward_matches_oracle(dtype, B, C, H, W):
     ops = _ops()
     q, k, v, rel_h, rel_w = _attn_inputs(B, C, H, W, dtype, 6)

@@ -1,0 +1,93 @@
+// tcgen05.mma issue-rate microbenchmark (sm_100a): clocks per MMA for a list of (M, N, a_major, b_major) shapes,
+// operands in shared memory (SS mode, bf16, K = 16 per instruction).  Used to size the attention kernels' tile shapes.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I pixel_heal_thyself_b200/csrc -o tools/_bin/mma_rate tools/mma_rate.cu
+#include <cstdio>
+#include <cstdlib>
+#include "tc_common.cuh"
+
+using namespace pht::tc;
+
+struct Shape { int M, N, amn, bmn, nacc; };
+
+__global__ void __launch_bounds__(128, 1) rate_kernel(const Shape* shapes, int nshape, int reps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) tmem_alloc(&slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  if (threadIdx.x == 0) {
+    uint32_t ph = 0;
+    for (int s = 0; s < nshape; ++s) {
+      const Shape sh = shapes[s];
+      const uint32_t idesc = umma_idesc_bf16(sh.M, sh.N, sh.amn, sh.bmn);
+      const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 64 * 1024);
+      for (int pass = 0; pass < 2; ++pass) {   // pass 0 warms up
+        const long long t0 = clock64();
+        uint64_t ad[4], bd[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ad[k] = sh.amn ? umma_desc_mn_sw128(a0 + k * 2048, 8192, 1024) : umma_desc_k_sw128(a0) + 2 * k;
+          bd[k] = sh.bmn ? umma_desc_mn_sw128(b0 + k * 2048, 8192, 1024) : umma_desc_k_sw128(b0) + 2 * k;
+        }
+        const uint32_t cstep = sh.nacc == 4 ? 128u : (sh.nacc == 2 ? 256u : 0u);
+#pragma unroll 1
+        for (int r = 0; r < reps; r += 8) {   // 8 MMAs per trip, no per-MMA integer work
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            umma_bf16(tm + (uint32_t)(u & 3) * cstep % 512u, ad[u & 3], bd[u & 3], idesc, 1u);
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, ph);
+        ph ^= 1;
+        const long long t1 = clock64();
+        if (pass) out[blockIdx.x * nshape + s] = t1 - t0;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
+}
+
+int main() {
+  const Shape hs[] = {
+      {128, 256, 0, 0, 1}, {128, 256, 0, 0, 2}, {128, 128, 0, 0, 1}, {128, 128, 0, 0, 2}, {128, 64, 0, 0, 1}, {128, 64, 0, 0, 2},
+      {128, 64, 0, 0, 4},  {128, 64, 1, 1, 4},  {128, 32, 0, 0, 4},  {128, 16, 0, 0, 4},  {64, 256, 0, 0, 1}, {64, 256, 0, 0, 2},
+      {64, 200, 0, 0, 2},  {64, 112, 0, 0, 2},  {64, 64, 0, 0, 1},   {64, 64, 0, 0, 2},   {64, 64, 0, 0, 4},  {64, 64, 0, 1, 4},
+      {64, 128, 0, 0, 2},  {128, 112, 0, 0, 2}, {128, 72, 0, 1, 4},  {64, 32, 0, 0, 4},   {64, 16, 0, 0, 4},  {128, 96, 0, 0, 4},
+  };
+  const int n = sizeof(hs) / sizeof(hs[0]);
+  const int reps = 256;
+  Shape* ds;
+  long long* dout;
+  const int grid = 148;
+  cudaMalloc(&ds, sizeof(hs));
+  cudaMalloc(&dout, sizeof(long long) * n * grid);
+  cudaMemcpy(ds, hs, sizeof(hs), cudaMemcpyHostToDevice);
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int g : {grid}) {
+    rate_kernel<<<g, 128, 200 * 1024>>>(ds, n, reps, dout);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+    long long* h = (long long*)malloc(sizeof(long long) * n * g);
+    cudaMemcpy(h, dout, sizeof(long long) * n * g, cudaMemcpyDeviceToHost);
+    printf("grid %d, %d back-to-back MMAs (K=16) per shape\n", g, reps);
+    printf("%5s %5s %4s %4s %4s %12s %14s %12s\n", "M", "N", "aMN", "bMN", "nacc", "clk/MMA", "MAC/clk/SM", "vs 128xN/256");
+    for (int s = 0; s < n; ++s) {
+      long long mx = 0;
+      for (int b = 0; b < g; ++b) mx = h[b * n + s] > mx ? h[b * n + s] : mx;
+      const double c = (double)mx / reps;
+      printf("%5d %5d %4d %4d %4d %12.1f %14.0f %12.2f\n", hs[s].M, hs[s].N, hs[s].amn, hs[s].bmn, hs[s].nacc, c,
+             (double)hs[s].M * hs[s].N * 16 / c, c / (128.0 * hs[s].N / 256.0));
+    }
+    free(h);
+  }
+  return 0;
+}
