@@ -10,7 +10,8 @@
 //   warp 1      MMA issuer: one elected thread issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of two
 //               TMEM accumulator buffers (2 x BN fp32 columns), tcgen05.commit releases the smem stage / publishes the
 //               accumulator.
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (each thread owns one output pixel = one TMEM lane), fused
+//   warps 2..5  epilogue (the "wide" config adds warps 7..10: two warps per TMEM quadrant take alternate 64-channel
+//               chunks, each group with its own staging tile, epilogue-input slot and named barrier): tcgen05.ld the accumulator (each thread owns one output pixel = one TMEM lane), fused
 //               bias / residual / (leaky)ReLU / activation-derivative mask, bf16 pack into a 128B-swizzled staging
 //               tile [128 px][64 ch] and one TMA tensor store per 64-channel chunk (full-line writes, ragged tiles
 //               clipped by the tensor map).  Runs concurrently with the MMAs of the next tile (double-buffered TMEM).
@@ -24,7 +25,7 @@ using namespace tc;
 
 constexpr int TILE_H = 8, TILE_W = 16, TILE_M = TILE_H * TILE_W;  // 128 output pixels per tile
 constexpr int BK = 64;                                            // bf16 elements per 128-byte swizzle row
-constexpr int TC_THREADS = 224;                                   // 7 warps: TMA, MMA, 4 x epilogue, aux TMA
+constexpr int TC_THREADS = 224;                                   // 7 warps: TMA, MMA, 4 x epilogue, aux TMA (+ 4 x epilogue, MODE 1)
 constexpr int MAX_VEC_N = 768;                                     // largest N (bias / slope vectors)
 constexpr int STG_BYTES = TILE_M * 128;  // one epilogue tile: 128 pixels x 64 bf16, 128B-swizzled rows
 
@@ -43,8 +44,8 @@ struct TcGemmP {
 };
 
 // MODE 0 "deep":     4-stage operand ring, one output staging tile, no epilogue inputs: K-heavy 3x3 convolutions.
-// MODE 1 "wide":     3-stage ring, two output staging tiles and a 2-slot ring of TMA-prefetched epilogue input tiles
-//                    (residual / activation mask): the HBM-bound 1x1 GEMMs.
+// MODE 1 "wide":     3-stage ring, TWO epilogue warp groups (their short K loop makes the 1x1 GEMMs epilogue-bound), each
+//                    with its own output staging tile and TMA-prefetched epilogue-input slot (residual / mask).
 // MODE 2 "deep+aux": 4-stage ring, one staging tile, one epilogue-input slot: 3x3 convolutions with a fused
 //                    residual / mask / second output / padding fold (their long K loop hides the serial epilogue);
 //                    slope vectors are read through the L1 instead of shared memory to fit in 227 KB.
@@ -54,6 +55,8 @@ template <int BN, int MODE> struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BN == 256 ? (MODE == 1 ? 3 : 4) : (BN == 128 ? 4 : 6);
   static constexpr int NSTG = MODE == 1 ? 2 : 1;
+  static constexpr int PARTS = MODE == 1 ? 2 : 1;                  // epilogue warp groups (4 warps = 128 rows each)
+  static constexpr int THREADS = PARTS == 2 ? TC_THREADS + 128 : TC_THREADS;
   static constexpr int AUX_SLOTS = MODE == 1 ? 2 : (MODE == 2 ? 1 : 0);
   static constexpr bool VEC_SMEM = MODE != 2;                      // slope / mslope staged in shared memory
   static constexpr int VEC_N = VEC_SMEM ? MAX_VEC_N : 256;         // largest N this config accepts
@@ -88,7 +91,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
 }
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((TcCfg<BN, MODE>::THREADS), 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -96,6 +99,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   using Cfg = TcCfg<BN, MODE>;
   constexpr int NCHUNK = BN / 64;
   constexpr bool AUX = Cfg::AUX_SLOTS > 0;
+  constexpr int PARTS = Cfg::PARTS;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B needs 1024-byte aligned stage bases
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
@@ -134,7 +138,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
+      mbar_init(&tempty_bar[a], 128 * PARTS);
       mbar_init(&afull_bar[a], 1);
       mbar_init(&aempty_bar[a], 128);
     }
@@ -218,14 +222,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       prefetch_tmap(&tmR);
       prefetch_tmap(&tmM);
       int j = 0;
+      int fills[2] = {0, 0};   // PARTS == 2: slot p is a depth-1 FIFO feeding epilogue group p (chunks c with c % 2 == p)
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
         const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
         const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
         const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * BN;
         for (int c = 0; c < NCHUNK; ++c) {
           for (int kind = P.has_resid ? 0 : 1; kind < (P.has_mask ? 2 : 1); ++kind, ++j) {
-            const int slot = j % NS;
-            mbar_wait(&aempty_bar[slot], ((j / NS) & 1) ^ 1);
+            const int slot = PARTS == 2 ? (c & 1) : j % NS;
+            const int fill = PARTS == 2 ? fills[slot]++ : j / NS;
+            mbar_wait(&aempty_bar[slot], (fill & 1) ^ 1);
             mbar_expect_tx(&afull_bar[slot], STG_BYTES);
             if (kind == 0) tma_load_4d(aux + slot * STG_BYTES, &tmR, &afull_bar[slot], n0 + c * 64, x0 - fo + P.residOx, y0 - fo + P.residOy, b);
             else tma_load_4d(aux + slot * STG_BYTES, &tmM, &afull_bar[slot], n0 + c * 64, x0 - fo + P.maskOx, y0 - fo + P.maskOy, b);
@@ -234,37 +240,37 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
     }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..5 [, 7..10]) ================================
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int part = (PARTS == 2 && warp >= 7) ? 1 : 0;   // epilogue group: takes the 64-channel chunks c with c % PARTS == part
     const int row = quad * 32 + lane;      // accumulator row == pixel index inside the tile
     const int py = row / TILE_W, px = row % TILE_W;
-    const bool issuer = (warp == 2 && lane == 0);
+    const bool issuer = ((warp == 2 || warp == 7) && lane == 0);
+    auto group_sync = [&]() {
+      if (part == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
     const int rsw = row & 7;
     int n_store = 0;                       // output tiles stored so far (selects the staging buffer)
     int j_aux = 0;                         // epilogue-input tiles consumed so far
     auto stage_and_store = [&](const float* v, const CUtensorMap* tm, int c_glob, int x0, int y0, int b) {
-      uint8_t* buf = stg + (Cfg::NSTG == 2 ? (n_store & 1) : 0) * STG_BYTES;
-      if (Cfg::NSTG == 1) {
-        // single staging tile: wait until the previous TMA store has finished READING it
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
+      uint8_t* buf = stg + part * STG_BYTES;   // one staging tile per epilogue group
+      // wait until the group's previous TMA store has finished READING the tile
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      group_sync();
       uint8_t* srow = buf + row * 128;
 #pragma unroll
       for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(srow + ((g ^ rsw) * 16)) = pack8(v + g * 8);
       fence_proxy_async();
-      // two staging tiles: the store issued one round ago read the OTHER tile; once it has finished reading, that
-      // tile is free for the next round (everyone learns it at the barrier below)
-      if (Cfg::NSTG == 2 && issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      group_sync();
       if (issuer) tma_store_4d(tm, buf, c_glob, x0, y0, b);
       ++n_store;
     };
     // v[64] (op)= the epilogue-input tile that is next in the stream; releases its slot
     auto aux_apply = [&](float* v, int c_abs, bool is_mask) {
       constexpr int NS = AUX ? Cfg::AUX_SLOTS : 1;
-      const int slot = j_aux % NS;
-      mbar_wait(&afull_bar[slot], (j_aux / NS) & 1);
+      const int slot = PARTS == 2 ? part : j_aux % NS;
+      mbar_wait(&afull_bar[slot], (PARTS == 2 ? j_aux : j_aux / NS) & 1);
       const uint8_t* arow = aux + slot * STG_BYTES + row * 128;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -295,8 +301,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+      if (part * 64 >= BN) {               // this group has no chunk of the tile
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {
+      for (int c0 = part * 64; c0 < BN; c0 += 64 * PARTS) {
         float v[64];
         {
           uint32_t r[32];
@@ -309,7 +319,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r[j]);
         }
-        if (c0 + 64 >= BN) {               // accumulator fully in registers: release it to the MMA warp
+        if (c0 + 64 * PARTS >= BN) {       // this group's share of the accumulator is in registers: release it
           tc_fence_before();
           mbar_arrive(&tempty_bar[acc]);
         }
@@ -456,7 +466,7 @@ static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
-  conv_gemm_tc_kernel<BN, MODE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(m.A[0], m.A[1], m.A[2], m.W, m.O[0], m.O[1], m.R, m.M, P);
+  conv_gemm_tc_kernel<BN, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(m.A[0], m.A[1], m.A[2], m.W, m.O[0], m.O[1], m.R, m.M, P);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }

@@ -192,24 +192,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
       mbar_wait(done_bar, 0);
       tc_fence_after();
     }
+    // Read-out: every thread owns one accumulator row (= output channel n), but a row-per-thread store would touch 32
+    // different 128-byte lines per instruction.  Each warp transposes its [32 rows][32 columns] fp32 chunk through a
+    // swizzled 4 KB tile of the (now idle) operand ring and writes whole 128-byte row segments: 4 lines per instruction.
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the column-sum warps are done reading the operand ring
+    const uint32_t xbuf = smem_u32(smem + (warp - 2) * 4096);
+    const int rsw = lane & 7;
 #pragma unroll 1
     for (int h = 0; h < MH; ++h) {
-      const int n = n0 + h * 128 + row;
-      float* dst = P.ws + (((size_t)split * P.T + t) * P.N + n) * P.Ktot + kt.koff;
+      float* dst0 = P.ws + (((size_t)split * P.T + t) * P.N + n0 + h * 128 + quad * 32) * P.Ktot + kt.koff;
       const uint32_t t_addr = tmem_base + h * 256 + ((uint32_t)(quad * 32) << 16);
+      uint32_t r[2][32];
+      if (npt > 0) tmem_ld32(t_addr, r[0]);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kt.wk; c0 += 32) {
-        uint32_t r[32];
-        if (npt > 0) {
-          tmem_ld32(t_addr + c0, r);
-          tmem_ld_wait();
-        } else {
+      for (int c0 = 0; c0 < kt.wk; c0 += 64) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        for (int u = 0; u < 2; ++u) {          // two 32-column chunks per trip (compile-time register buffers)
+          const int c = c0 + u * 32;
+          if (npt > 0) {
+            tmem_ld_wait();
+            if (c + 32 < kt.wk) tmem_ld32(t_addr + c + 32, r[u ^ 1]);   // next chunk in flight
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[u][j] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xbuf + lane * 128 + ((j ^ rsw) << 4)),
+                         "r"(r[u][4 * j]), "r"(r[u][4 * j + 1]), "r"(r[u][4 * j + 2]), "r"(r[u][4 * j + 3]) : "memory");
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3);
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(xbuf + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)));
+            *reinterpret_cast<uint4*>(dst0 + (size_t)rr * P.Ktot + c + (lane & 7) * 4) = v;
+          }
+          __syncwarp();
         }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
     }
   }
