@@ -8,14 +8,14 @@
 //   S = Q K^T + Q REL^T   two accumulating tcgen05.mma chains M=64, N=200, K=64 per head.  REL is a constant smem tile
 //            [key (r,c)][rel_h[r] | rel_w[c]], so S == q.(k + rel) of the reference (model.py:496-501) without ever
 //            materialising K + rel and without any per-element bias arithmetic in the softmax.
-//   softmax  128 threads, one (head, query) row each, two passes over TMEM (max, then exp2 / sum) in 32-column chunks
-//            with the next chunk's tcgen05.ld in flight while the current one is processed; P -> bf16 into a
-//            128B-swizzled K-major smem tile.
-//   O = P V  tcgen05.mma M=64, N=64, K=208 with V consumed MN-major straight from its TMA box; O overwrites
-//            the first 64 columns of the (already consumed) S region.
+//   softmax  256 threads: two warps per TMEM sub-partition share every (head, query) row (columns [0,104) / [104,200)),
+//            two passes over TMEM (max, then exp2 / sum) in 32-column chunks with the next chunk's tcgen05.ld in
+//            flight; partial maxima / sums are exchanged through smem; P -> bf16 into a 128B-swizzled K-major tile.
+//   O = P V  tcgen05.mma M=64, N=64, K=208 with V consumed MN-major straight from its TMA box, into its own TMEM
+//            columns.
 //   epilogue O / sum + residual (TMA-loaded tile, updated in place) -> bf16 tile -> TMA store; log-sum-exp saved.
-// Two TMEM regions (one per head pair) ping-pong so S(it+1) is computed while softmax(it) runs.
-// Warps: 0 TMA producer, 1 MMA issuer, 2..5 softmax/epilogue, 6 output store + residual prefetch.
+// Two S regions ping-pong: S runs two iterations ahead of P.V on the tensor pipe (S(it+2) is issued right behind P.V(it)).
+// Warps: 0 TMA producer, 1 MMA issuer, 2..5 and 7..10 softmax/epilogue, 6 output store + residual prefetch.
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -24,7 +24,7 @@ namespace pht {
 
 using namespace tc;
 
-constexpr int AF_THREADS = 224;                                // forward kernel (7 warps)
+constexpr int AF_THREADS = 352;                                // forward kernel (11 warps)
 constexpr int AT_NK = 196, AT_NKP = 208, AT_NS = 200;          // keys, keys padded to 16 (P / V), S columns = K-tile rows
 constexpr int AT_Q_BYTES = 64 * 128;                           // 8 KB per head
 constexpr int AT_K_BYTES = AT_NS * 128;                        // 25600 (25 swizzle atoms)
@@ -32,11 +32,24 @@ constexpr int AT_V_BYTES = AT_NKP * 128;                       // 26624
 constexpr int AT_P_BYTES = 4 * 64 * 128;                       // 4 K-tiles of 64 keys
 constexpr int AT_KV_BOX_BYTES = AT_NK * 128;                   // 25088 written by one TMA box
 constexpr int AT_RO_BYTES = 2 * AT_Q_BYTES;                    // residual-in == output staging: 2 heads x [64 px][64 ch]
-constexpr int AT_SMEM = 2 * (AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES + AT_P_BYTES) + AT_K_BYTES + AT_RO_BYTES + 256 + 1024;
+constexpr int AT_COL_O = 2 * AT_NS;                               // TMEM: S(even) [0,200), S(odd) [200,400), O [400,464)
+constexpr int AT_XCH_BYTES = 2 * 2 * 128 * 4;                      // [max | sum][part][128 rows] fp32 partials of the two warp groups
+constexpr int AT_SMEM = 2 * (AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES + AT_P_BYTES) + AT_K_BYTES + AT_RO_BYTES + AT_XCH_BYTES + 256 + 1024;
 static_assert(AT_SMEM <= 232448, "attn_fwd_tc: shared memory budget");
 
+constexpr int AB_TRACE_ITERS = 48, AB_TRACE_EVENTS = 8;
+__device__ long long g_attn_bwd_trace[AB_TRACE_ITERS * AB_TRACE_EVENTS];   // clock64 stamps of CTA 0 (diagnostics)
+static int g_attn_trace_on = 0;
+void set_attn_trace(int v) { g_attn_trace_on = v; }
+int read_attn_trace(long long* host, int n) {
+  if (n > AB_TRACE_ITERS * AB_TRACE_EVENTS) n = AB_TRACE_ITERS * AB_TRACE_EVENTS;
+  PHT_CUDA(cudaDeviceSynchronize());
+  PHT_CUDA(cudaMemcpyFromSymbol(host, g_attn_bwd_trace, (size_t)n * sizeof(long long)));
+  return n;
+}
+
 struct AtP {
-  int B, H, W, nbx, nby, nblocks;
+  int B, H, W, nbx, nby, nblocks, trace;
   int has_resid, residOy, residOx, outOy, outOx;
   const float* rel_h;
   const float* rel_w;
@@ -47,6 +60,15 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t u;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
+  return u;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 __global__ void __launch_bounds__(AF_THREADS, 1)
@@ -61,14 +83,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* Vs = RELs + AT_K_BYTES;                      // [2][208 x 128B]
   uint8_t* Ps = Vs + 2 * AT_V_BYTES;                    // [2][4][64 x 128B]
   uint8_t* ROs = Ps + 2 * AT_P_BYTES;                   // [2][64 x 128B] residual tile in, output tile out (in place)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ROs + AT_RO_BYTES);
+  float* xmax = reinterpret_cast<float*>(ROs + AT_RO_BYTES);   // [2 parts][128 rows]
+  float* xsum = xmax + 256;                                     // [2 parts][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xsum + 256);
   uint64_t* qk_full = bars + 0;
   uint64_t* qk_empty = bars + 1;
   uint64_t* v_full = bars + 2;
   uint64_t* pv_done = bars + 3;
   uint64_t* p_full = bars + 4;
   uint64_t* s_full = bars + 5;     // [2]
-  uint64_t* tmem_free = bars + 7;  // [2]
+  uint64_t* o_free = bars + 7;     // O read out of TMEM (256 arrivals)
   uint64_t* ro_in = bars + 9;      // residual tile of the iteration has landed / the staging tile is free
   uint64_t* ro_out = bars + 10;    // output tile complete (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
@@ -100,6 +124,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int h = i / ((AT_NKP - AT_NK) * 8), rem = i % ((AT_NKP - AT_NK) * 8);
     *reinterpret_cast<uint4*>(Vs + h * AT_V_BYTES + (AT_NK + rem / 8) * 128 + (rem % 8) * 16) = make_uint4(0, 0, 0, 0);
   }
+  for (int i = threadIdx.x; i < 2 * AT_P_BYTES / 16; i += blockDim.x)         // P columns 196..207 stay zero
+    reinterpret_cast<uint4*>(Ps)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
@@ -108,12 +134,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(qk_empty, 1);
     mbar_init(v_full, 1);
     mbar_init(pv_done, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(ro_in, 1);
-    mbar_init(ro_out, 128);
+    mbar_init(ro_out, 256);
+    mbar_init(o_free, 256);
     for (int r = 0; r < 2; ++r) {
       mbar_init(&s_full[r], 1);
-      mbar_init(&tmem_free[r], 128);
     }
     mbar_fence_init();
   }
@@ -126,27 +152,39 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const int my_blocks = (P.nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_it = 2 * my_blocks;  // (block, head pair) iterations
+  const bool tracing = P.trace && blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2);
+  auto stamp = [&](int it, int ev) {
+    if (tracing && it < AB_TRACE_ITERS) g_attn_bwd_trace[it * AB_TRACE_EVENTS + ev] = clock64();
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
+    // Two independent streams polled by one thread: Q/K(it) as soon as S(it-1) has consumed the tiles, V(it) as soon
+    // as P.V(it-1) has -- neither load may wait behind the other (S runs two iterations ahead of P.V).
     if (lane == 0) {
-      for (int it = 0; it < n_it; ++it) {
-        const int blk = blockIdx.x + (it >> 1) * gridDim.x, pair = it & 1;
-        const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
-        const uint32_t ph = it & 1;
-        mbar_wait(qk_empty, ph ^ 1);
-        mbar_expect_tx(qk_full, 2 * (AT_Q_BYTES + AT_KV_BOX_BYTES));
+      int qk_it = 0, v_it = 0;
+      while (qk_it < n_it || v_it < n_it) {
+        if (qk_it < n_it && mbar_try_wait(qk_empty, (qk_it & 1) ^ 1)) {
+          const int blk = blockIdx.x + (qk_it >> 1) * gridDim.x, pair = qk_it & 1;
+          const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+          mbar_expect_tx(qk_full, 2 * (AT_Q_BYTES + AT_KV_BOX_BYTES));
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c0 = (pair * 2 + h) * 64;
-          tma_load_4d(Qs + h * AT_Q_BYTES, &tmQ, qk_full, c0, bx * 8, by * 8, b);
-          tma_load_4d(Ks + h * AT_K_BYTES, &tmK, qk_full, c0, bx * 8 - 3, by * 8 - 3, b);
+          for (int h = 0; h < 2; ++h) {
+            const int c0 = (pair * 2 + h) * 64;
+            tma_load_4d(Qs + h * AT_Q_BYTES, &tmQ, qk_full, c0, bx * 8, by * 8, b);
+            tma_load_4d(Ks + h * AT_K_BYTES, &tmK, qk_full, c0, bx * 8 - 3, by * 8 - 3, b);
+          }
+          ++qk_it;
         }
-        mbar_wait(pv_done, ph ^ 1);  // V (and P) of the previous iteration consumed
-        mbar_expect_tx(v_full, 2 * AT_KV_BOX_BYTES);
+        if (v_it < n_it && mbar_try_wait(pv_done, (v_it & 1) ^ 1)) {   // V (and P) of the previous iteration consumed
+          const int blk = blockIdx.x + (v_it >> 1) * gridDim.x, pair = v_it & 1;
+          const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+          mbar_expect_tx(v_full, 2 * AT_KV_BOX_BYTES);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(Vs + h * AT_V_BYTES, &tmV, v_full, (pair * 2 + h) * 64, bx * 8 - 3, by * 8 - 3, b);
+          for (int h = 0; h < 2; ++h)
+            tma_load_4d(Vs + h * AT_V_BYTES, &tmV, v_full, (pair * 2 + h) * 64, bx * 8 - 3, by * 8 - 3, b);
+          ++v_it;
+        }
       }
     }
   } else if (warp == 1) {
@@ -157,14 +195,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint64_t reld = umma_desc_k_sw128(smem_u32(RELs));
       auto issue_s = [&](int it) {
         const int r = it & 1;
-        mbar_wait(qk_full, it & 1);
-        mbar_wait(&tmem_free[r], ((it >> 1) & 1) ^ 1);
+        mbar_wait(qk_full, it & 1);   // (the S region r is free: the caller has seen p_full of iteration it-2)
         tc_fence_after();
+        stamp(it, 0);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint64_t qd = umma_desc_k_sw128(smem_u32(Qs + h * AT_Q_BYTES));
           const uint64_t kd = umma_desc_k_sw128(smem_u32(Ks + h * AT_K_BYTES));
-          const uint32_t d = tmem_base + r * 256 + ((uint32_t)(h * 16) << 16);
+          const uint32_t d = tmem_base + r * AT_NS + ((uint32_t)(h * 16) << 16);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
 #pragma unroll
@@ -173,16 +211,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(qk_empty);
         umma_commit(&s_full[r]);
       };
+      // S runs two iterations ahead of P.V: S(it+2) is issued right behind P.V(it), so the tensor pipe never has a
+      // P.V waiting behind an S that itself waits for the epilogue.
       if (n_it > 0) issue_s(0);
+      if (n_it > 1) issue_s(1);
       for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) issue_s(it + 1);
-        const int r = it & 1;
-        mbar_wait(p_full, it & 1);
+        mbar_wait(p_full, it & 1);               // P(it) written; all reads of S(it) done -> its region is free
         mbar_wait(v_full, it & 1);
+        if (it > 0) mbar_wait(o_free, (it - 1) & 1);   // O(it-1) read out by the epilogue
         tc_fence_after();
+        stamp(it, 1);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint32_t d = tmem_base + r * 256 + ((uint32_t)(h * 16) << 16);
+          const uint32_t d = tmem_base + AT_COL_O + ((uint32_t)(h * 16) << 16);
           const uint32_t p_addr = smem_u32(Ps + h * AT_P_BYTES);
           const uint32_t v_addr = smem_u32(Vs + h * AT_V_BYTES);
 #pragma unroll
@@ -193,6 +234,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
         umma_commit(pv_done);
+        if (it + 2 < n_it) issue_s(it + 2);
       }
     }
   } else if (warp == 6) {
@@ -229,59 +271,129 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all output stores complete before exit
     }
   } else {
-    // ================================ softmax + epilogue (warps 2..5) ================================
-    const int quad = warp & 3;
+    // ================================ softmax + epilogue (warps 2..5, 7..10) ================================
+    const int quad = warp & 3;                   // TMEM sub-partition of this warp
+    const int part = warp >= 7 ? 1 : 0;          // which of the two warps sharing the sub-partition
     const int hp = lane >> 4;                    // head inside the pair (TMEM lane half)
     const int q = quad * 16 + (lane & 15);       // query row
+    const int xrow = hp * 64 + q;                // row in the exchange arrays
     const int qy = q >> 3, qx = q & 7;
     const int qsw = q & 7;
     const float LOG2E = 1.4426950408889634f;
-    float prev_m = 0.f, prev_sum = 1.f;
+    const uint32_t p_row = smem_u32(Ps + hp * AT_P_BYTES + q * 128);
+    float prev_m = 0.f;
     int prev_blk = 0, prev_pair = 0;
 
-    auto epilogue = [&](int it, float m, float sum, int blk, int pair) {
-      const int r = it & 1;
+    // O / sum + residual -> output tile (this warp's 32 of the 64 channels); needs the other group's partial sum.
+    // Everything that does not depend on O (coordinates, 1 / sum, lse, the residual cells) is done BEFORE waiting for
+    // P.V: the wait -> TMEM load -> scale -> store tail is on the kernel's critical path.
+    auto epilogue = [&](int it, float m, int blk, int pair) {
+      const float sum = xsum[xrow] + xsum[128 + xrow];
+      const float inv = 1.f / sum;
+      if (P.lse && part == 0) {
+        const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+        P.lse[(((long long)b * P.H + by * 8 + qy) * P.W + bx * 8 + qx) * 4 + pair * 2 + hp] = m + logf(sum);
+      }
+      uint8_t* row = ROs + hp * AT_Q_BYTES + q * 128;
+      uint4 ru[4];
+      mbar_wait(ro_in, it & 1);                  // residual tile landed (or staging tile free)
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        ru[g] = P.has_resid ? *reinterpret_cast<const uint4*>(row + (((part * 4 + g) ^ qsw) * 16)) : make_uint4(0, 0, 0, 0);
       mbar_wait(pv_done, it & 1);
       tc_fence_after();
-      mbar_wait(ro_in, it & 1);                  // residual tile landed (or staging tile free)
-      const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
-      const int y = by * 8 + qy, x = bx * 8 + qx, head = pair * 2 + hp;
-      const float inv = 1.f / sum;
-      const uint32_t t_addr = tmem_base + r * 256 + ((uint32_t)(quad * 32) << 16);
-      uint8_t* row = ROs + hp * AT_Q_BYTES + q * 128;
+      stamp(it, 6);
+      uint32_t o[32];
+      tmem_ld32(tmem_base + AT_COL_O + ((uint32_t)(quad * 32) << 16) + part * 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free);
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t o[32];
-        tmem_ld32(t_addr + c0, o);
-        tmem_ld_wait();
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t rw[4] = {ru[g].x, ru[g].y, ru[g].z, ru[g].w};
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          w[j] = pack_bf16x2(fmaf(__uint_as_float(o[g * 8 + 2 * j]), inv, __uint_as_float(rw[j] << 16)),
+                             fmaf(__uint_as_float(o[g * 8 + 2 * j + 1]), inv, __uint_as_float(rw[j] & 0xffff0000u)));
+        *reinterpret_cast<uint4*>(row + (((part * 4 + g) ^ qsw) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(ro_out);
+    };
+
+    // one softmax iteration for the columns of warp group PART (compile-time): 13 / 12 groups of 8 columns
+    auto softmax_it = [&](auto part_c, int it, uint32_t t_addr) {
+      constexpr int PART = decltype(part_c)::value;
+      constexpr int C0 = PART * 104;                       // first S column of this group
+      constexpr int NG = PART ? 12 : 13;                   // 8-column groups (the last group of PART 1 holds keys 192..195)
+      constexpr int NCH = (NG + 3) / 4;                    // 32-column TMEM loads (PART 0's last one is 8 columns wide)
+      uint32_t a[32], bq[32];
+      // ---- pass 1: row maximum of the own columns ----
+      float m = -INFINITY;
+      tmem_ld32(t_addr + C0, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t* cur = (c & 1) ? bq : a;
+        uint32_t* nxt = (c & 1) ? a : bq;
+        if (c + 1 < NCH) {
+          if (PART == 0 && c + 1 == NCH - 1) tmem_ld16(t_addr + C0 + (c + 1) * 32, nxt);   // 8 valid columns
+          else tmem_ld32(t_addr + C0 + (c + 1) * 32, nxt);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const int col = C0 + c * 32 + j;
+          if (col < (PART ? AT_NK : 104)) m = fmaxf(m, fmaxf(__uint_as_float(cur[j]), __uint_as_float(cur[j + 1])));
+        }
+        if (c + 1 < NCH) tmem_ld_wait();
+      }
+      xmax[PART * 128 + xrow] = m;
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // both groups' maxima (and the previous sums) are visible
+      m = fmaxf(xmax[xrow], xmax[128 + xrow]);
+      stamp(it, 3);
+      // the previous pair's O is final by now: write it out and free its TMEM region for S(it+1)
+      if (it > 0) epilogue(it - 1, prev_m, prev_blk, prev_pair);
+      stamp(it, 4);
+      // ---- pass 2: p = exp(s - m), partial row sum, bf16 P tile (K-major, 128B swizzle) ----
+      const float m2 = m * LOG2E;
+      float s0 = 0.f, s1 = 0.f;
+      tmem_ld32(t_addr + C0, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t* cur = (c & 1) ? bq : a;
+        uint32_t* nxt = (c & 1) ? a : bq;
+        if (c + 1 < NCH) {
+          if (PART == 0 && c + 1 == NCH - 1) tmem_ld16(t_addr + C0 + (c + 1) * 32, nxt);
+          else tmem_ld32(t_addr + C0 + (c + 1) * 32, nxt);
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float v[8];
+          const int gi = c * 4 + g;
+          if (gi < NG) {
+            float p[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(o[g * 8 + j]) * inv;
-          uint4* cell = reinterpret_cast<uint4*>(row + ((((c0 >> 3) + g) ^ qsw) * 16));   // 128B-swizzled 16-byte chunk
-          if (P.has_resid) {
-            const uint4 ru = *cell;
-            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&ru);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f = __bfloat1622float2(rh[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
+            for (int j = 0; j < 8; ++j) {
+              const int key = C0 + gi * 8 + j;
+              p[j] = key < AT_NK ? ex2(fmaf(__uint_as_float(cur[g * 8 + j]), LOG2E, -m2)) : 0.f;
             }
+            s0 += (p[0] + p[1]) + (p[2] + p[3]);
+            s1 += (p[4] + p[5]) + (p[6] + p[7]);
+            const int key0 = C0 + gi * 8;
+            st_shared_v4(p_row + (key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ qsw) * 16), pack_bf16x2(p[0], p[1]),
+                         pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
           }
-          uint4 u;
-          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          *cell = u;
         }
+        if (c + 1 < NCH) tmem_ld_wait();
       }
-      if (P.lse) P.lse[(((long long)b * P.H + y) * P.W + x) * 4 + head] = m + logf(sum);
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&tmem_free[r]);
-      mbar_arrive(ro_out);
+      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();     // all TMEM reads of S done before the MMA warp may overwrite the region with O
+      mbar_arrive(p_full);
+      stamp(it, 5);
+      asm volatile("bar.sync 2, 256;" ::: "memory");       // every thread has consumed the previous partial sums
+      xsum[PART * 128 + xrow] = s0 + s1;
+      return m;
     };
 
     for (int it = 0; it < n_it; ++it) {
@@ -289,84 +401,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int r = it & 1;
       mbar_wait(&s_full[r], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + r * 256 + ((uint32_t)(quad * 32) << 16);
-      uint32_t a[32], bq[32];
-      // ---- pass 1: row maximum (chunks of 32 keys; the next chunk's tcgen05.ld is in flight while this one is reduced)
-      float m = -INFINITY;
-      tmem_ld32(t_addr, a);
-      tmem_ld_wait();
-#pragma unroll 1
-      for (int c = 0; c < 6; c += 2) {
-        tmem_ld32(t_addr + (c + 1) * 32, bq);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(a[j]), __uint_as_float(a[j + 1])));
-        tmem_ld_wait();
-        tmem_ld32(t_addr + (c + 2) * 32, a);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(bq[j]), __uint_as_float(bq[j + 1])));
-        tmem_ld_wait();
-      }
-#pragma unroll
-      for (int j = 0; j < AT_NK - 192; ++j) m = fmaxf(m, __uint_as_float(a[j]));   // keys 192..195
-      // the previous pair's O is final by now: write it out and free its TMEM region for S(it+1)
-      if (it > 0) epilogue(it - 1, prev_m, prev_sum, prev_blk, prev_pair);
-      // ---- pass 2: p = exp(s - m), row sum, bf16 P tile (K-major, 128B swizzle)
-      const float m2 = m * LOG2E;
-      float sum = 0.f;
-      uint8_t* prow = Ps + hp * AT_P_BYTES + q * 128;
-      auto emit = [&](const uint32_t* s, int c) {   // 32 keys starting at 32*c, all valid
-        uint8_t* base = prow + (c >> 1) * 8192;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            p[j] = ex2(fmaf(__uint_as_float(s[g * 8 + j]), LOG2E, -m2));
-            sum += p[j];
-          }
-          uint4 u;
-          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
-          *reinterpret_cast<uint4*>(base + ((((c & 1) * 4 + g) ^ qsw) * 16)) = u;
-        }
-      };
-      tmem_ld32(t_addr, a);
-      tmem_ld_wait();
-#pragma unroll 1
-      for (int c = 0; c < 6; c += 2) {
-        tmem_ld32(t_addr + (c + 1) * 32, bq);
-        emit(a, c);
-        tmem_ld_wait();
-        tmem_ld32(t_addr + (c + 2) * 32, a);
-        emit(bq, c + 1);
-        tmem_ld_wait();
-      }
-      {  // keys 192..207: 4 real keys, 12 zero columns (the P.V MMA runs over 208 keys)
-        float p[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          p[j] = 0.f;
-          if (j < AT_NK - 192) {
-            p[j] = ex2(fmaf(__uint_as_float(a[j]), LOG2E, -m2));
-            sum += p[j];
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint4 u;
-          __nv_bfloat162* uh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) uh[j] = __floats2bfloat162_rn(p[g * 8 + 2 * j], p[g * 8 + 2 * j + 1]);
-          *reinterpret_cast<uint4*>(prow + 3 * 8192 + ((g ^ qsw) * 16)) = u;
-        }
-      }
-      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();     // all TMEM reads of S done before the MMA warp may overwrite the region with O
-      mbar_arrive(p_full);
-      prev_m = m; prev_sum = sum; prev_blk = blk; prev_pair = pair;
+      stamp(it, 2);
+      const uint32_t t_addr = tmem_base + r * AT_NS + ((uint32_t)(quad * 32) << 16);
+      float m;
+      if (part == 0) m = softmax_it(std::integral_constant<int, 0>{}, it, t_addr);
+      else m = softmax_it(std::integral_constant<int, 1>{}, it, t_addr);
+      prev_m = m; prev_blk = blk; prev_pair = pair;
     }
-    if (n_it > 0) epilogue(n_it - 1, prev_m, prev_sum, prev_blk, prev_pair);
+    if (n_it > 0) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // the last partial sums are visible
+      epilogue(n_it - 1, prev_m, prev_blk, prev_pair);
+    }
   }
 
   tc_fence_before();
@@ -417,6 +462,7 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   P.has_resid = a->resid.ptr ? 1 : 0;
   P.residOy = a->resid.oy; P.residOx = a->resid.ox; P.outOy = a->out.oy; P.outOx = a->out.ox;
   P.rel_h = a->rel_h; P.rel_w = a->rel_w; P.lse = a->lse;
+  P.trace = g_attn_trace_on == 2;
   static bool attr = false;
   if (!attr) {
     PHT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
@@ -465,17 +511,6 @@ static_assert(AB_COL_DK + 128 <= 512, "attn_bwd_tc: TMEM budget");
 constexpr int AB_PART0 = 56;                                    // S/dP columns of a lane half handled by warp part 0 (part 1: 48)
 constexpr int AB_REL_PART = AT_NK * 64;  // floats per CTA partial: dREL [196 keys][64]
 
-constexpr int AB_TRACE_ITERS = 48, AB_TRACE_EVENTS = 8;
-__device__ long long g_attn_bwd_trace[AB_TRACE_ITERS * AB_TRACE_EVENTS];   // clock64 stamps of CTA 0 (diagnostics)
-static int g_attn_trace_on = 0;
-void set_attn_trace(int v) { g_attn_trace_on = v; }
-int read_attn_trace(long long* host, int n) {
-  if (n > AB_TRACE_ITERS * AB_TRACE_EVENTS) n = AB_TRACE_ITERS * AB_TRACE_EVENTS;
-  PHT_CUDA(cudaDeviceSynchronize());
-  PHT_CUDA(cudaMemcpyFromSymbol(host, g_attn_bwd_trace, (size_t)n * sizeof(long long)));
-  return n;
-}
-
 struct AbP {
   int B, H, W, nbx, nby, nblocks, trace;
   View dq;
@@ -487,14 +522,6 @@ struct AbP {
   float* rel_part;    // [gridDim.x][196][64]
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t u;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
-  return u;
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ void st_row32_bf16(bf16* dst, const uint32_t* r) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -976,7 +1003,7 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
   P.B = f.B; P.H = f.H; P.W = f.W; P.nbx = f.W / 8; P.nby = f.H / 8; P.nblocks = f.B * P.nbx * P.nby;
   P.dq = make_view(a->dq);
   P.rel_h = f.rel_h; P.rel_w = f.rel_w; P.lse = f.lse;
-  P.trace = g_attn_trace_on;
+  P.trace = g_attn_trace_on == 1;
   const size_t scratch = (size_t)P.nblocks * 4 * AT_NK * 64;
   P.dk_scratch = (bf16*)a->workspace;
   P.dv_scratch = P.dk_scratch + scratch;

@@ -52,6 +52,21 @@ bwd = lambda: ops.attn_bwd(q, k, v, rel_h, rel_w, lse, do, dq, dk, dv, drh, drw,
 print("attn_fwd  median %.1f us  min %.1f us" % timed(fwd, args.iters))
 print("attn_bwd (+fold +rel reduce)  median %.1f us  min %.1f us" % timed(bwd, args.iters))
 if args.trace:
+    _lib.lib.pht_set_option(b"attn_trace", 2)
+    fwd()
+    buf = (C.c_int64 * (48 * 8))()
+    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * 8)
+    _lib.lib.pht_set_option(b"attn_trace", 0)
+    t = torch.tensor(list(buf)[:n]).view(-1, 8)
+    t0 = int(t[0, 0])
+    print("FORWARD events: 0=S issue(it) 1=PV issue(it) 2=s_full seen 3=max exchanged 4=epilogue(it-1) done 5=p_full arrive "
+          "6=pv_done(it) seen [in epilogue, during it+1]")
+    for i in range(4, 14):
+        print(f"it {i:2d}: " + " ".join(f"{int(x) - t0:8d}" for x in t[i, :7]))
+    d = t[4:24]
+    seg = lambda a, b: float((d[:, b] - d[:, a]).float().mean())
+    print("period %.0f | s_full seen->max %.0f | epilogue(it-1) %.0f | pass2 %.0f | p_full->PV issue %.0f | PV issue->pv_done seen %.0f"
+          % (float((t[24, 2] - t[4, 2]) / 20), seg(2, 3), seg(3, 4), seg(4, 5), seg(5, 1), seg(1, 6)))
     _lib.lib.pht_set_option(b"attn_trace", 1)
     bwd()
     buf = (C.c_int64 * (48 * 8))()
