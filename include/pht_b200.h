@@ -338,7 +338,7 @@ void pht_set_force_simple(int on);
  * "wgrad_split_div" = d: 1x1 weight-gradients use 1/d of the pixel splits (fewer fp32 partials);
  * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics) */
 int pht_set_option(const char* name, int value);
-/* Copies the stamps recorded under "attn_trace" ([iteration][8 events], first 48 iterations of CTA 0) to host memory
+/* Copies the stamps recorded under "attn_trace" ([iteration][12 events], first 48 iterations of CTA 0) to host memory
  * after a device synchronise; returns the number of values copied or a negative status. */
 int pht_attn_bwd_trace(int64_t* host, int32_t n);
 

@@ -13,7 +13,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpht_b200.so")
+LIB_PATH = os.environ.get("PHT_LIB_PATH") or os.path.join(_PKG, "libpht_b200.so")   # (override: A/B builds)
 
 PHT_F32, PHT_BF16 = 0, 1
 PAD_REPLICATE, PAD_REFLECT = 0, 1

@@ -37,7 +37,7 @@ constexpr int AT_XCH_BYTES = 2 * 2 * 128 * 4;                      // [max | sum
 constexpr int AT_SMEM = 2 * (AT_Q_BYTES + AT_K_BYTES + AT_V_BYTES + AT_P_BYTES) + AT_K_BYTES + AT_RO_BYTES + AT_XCH_BYTES + 256 + 1024;
 static_assert(AT_SMEM <= 232448, "attn_fwd_tc: shared memory budget");
 
-constexpr int AB_TRACE_ITERS = 48, AB_TRACE_EVENTS = 8;
+constexpr int AB_TRACE_ITERS = 48, AB_TRACE_EVENTS = 12;
 __device__ long long g_attn_bwd_trace[AB_TRACE_ITERS * AB_TRACE_EVENTS];   // clock64 stamps of CTA 0 (diagnostics)
 static int g_attn_trace_on = 0;
 void set_attn_trace(int v) { g_attn_trace_on = v; }
@@ -189,7 +189,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+#ifdef PHT_ATTN_FWD_LANE0_ISSUE
+    constexpr bool LANE0 = true;      // A/B switch: single-lane issue region (per-MMA broadcast loop in SASS)
+#else
+    constexpr bool LANE0 = false;     // all 32 lanes run the loop (warp-converged); one elected lane issues each instruction
+#endif
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t acc) {
+      if constexpr (LANE0) umma_bf16(d, ad, bd, id, acc);
+      else umma_bf16_elect(d, ad, bd, id, acc);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (LANE0) umma_commit(bar);
+      else umma_commit_elect(bar);
+    };
+    if (!LANE0 || lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(64, AT_NS, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(64, 64, 0, 1);  // B = V is MN-major
       const uint64_t reld = umma_desc_k_sw128(smem_u32(RELs));
@@ -204,12 +217,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t kd = umma_desc_k_sw128(smem_u32(Ks + h * AT_K_BYTES));
           const uint32_t d = tmem_base + r * AT_NS + ((uint32_t)(h * 16) << 16);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) mma(d, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, reld + 2 * k, idesc_s, 1u);   // += q . [rel_h | rel_w]
+          for (int k = 0; k < 4; ++k) mma(d, qd + 2 * k, reld + 2 * k, idesc_s, 1u);   // += q . [rel_h | rel_w]
         }
-        umma_commit(qk_empty);
-        umma_commit(&s_full[r]);
+        commit(qk_empty);
+        commit(&s_full[r]);
       };
       // S runs two iterations ahead of P.V: S(it+2) is issued right behind P.V(it), so the tensor pipe never has a
       // P.V waiting behind an S that itself waits for the epilogue.
@@ -230,10 +243,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int kk = 0; kk < AT_NKP / 16; ++kk) {
             const uint64_t pd = umma_desc_k_sw128(p_addr + (kk >> 2) * 8192) + 2 * (kk & 3);
             const uint64_t vd = umma_desc_mn_sw128(v_addr + kk * 2048, 8192, 1024);
-            umma_bf16(d, pd, vd, idesc_pv, kk ? 1u : 0u);
+            mma(d, pd, vd, idesc_pv, kk ? 1u : 0u);
           }
         }
-        umma_commit(pv_done);
+        commit(pv_done);
         if (it + 2 < n_it) issue_s(it + 2);
       }
     }
@@ -494,7 +507,7 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
 // Pipeline: the operands of iteration i+1 are prefetched (Q, dO, K double-buffered; V reloaded as soon as dP(i) is
 // done), S/dP(i+1) is issued right behind dQ/dV/dK(i) on the tensor pipe, and the dV/dK read-out of iteration i
 // runs while S/dP(i+1) is being computed.  TMEM: S [0,104) dP [104,208) (dQ re-uses [0,64)), dV [208,336), dK [336,464).
-// dK / dV leave the SM window-major in bf16 (coalesced 128-byte rows, no atomics); a fold kernel sums the <= 4
+// dK / dV leave the SM window-major in bf16 (rows transposed through smem into 64-byte segments, no atomics); a fold kernel sums the <= 4
 // overlapping windows of every pixel deterministically and writes the final NHWC gradients.
 // =================================================================================================
 constexpr int AB_THREADS = 320;
@@ -535,8 +548,7 @@ __device__ __forceinline__ void st_row32_bf16(bf16* dst, const uint32_t* r) {
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                   const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const AbP P) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AbP P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
   uint8_t* St = smem;                                   // [2 stages][Q 8K | dO 8K | K 26K]
@@ -637,7 +649,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {   // all 32 lanes run the loop (warp-converged); one elected lane issues each tcgen05 instruction
       constexpr uint32_t id_s = umma_idesc_bf16(64, AB_HALF, 0, 0);
       constexpr uint32_t id_dvk = umma_idesc_bf16(128, 64, 1, 1);
       constexpr uint32_t id_dq = umma_idesc_bf16(64, 64, 0, 1);
@@ -658,14 +670,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t rd = umma_desc_k_sw128(rel_a + hf * AB_HALF * 128);
           const uint64_t vd = umma_desc_k_sw128(v_a + hf * AB_HALF * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d + AB_COL_DP, dod + 2 * k, vd + 2 * k, id_s, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_elect(d + AB_COL_DP, dod + 2 * k, vd + 2 * k, id_s, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, id_s, k ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16_elect(d, qd + 2 * k, kd + 2 * k, id_s, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, qd + 2 * k, rd + 2 * k, id_s, 1u);          // += q . [rel_h | rel_w]
+          for (int k = 0; k < 4; ++k) umma_bf16_elect(d, qd + 2 * k, rd + 2 * k, id_s, 1u);          // += q . [rel_h | rel_w]
         }
-        umma_commit(v_empty);
-        umma_commit(sdp_full);
+        umma_commit_elect(v_empty);
+        umma_commit_elect(sdp_full);
+        if (tracing) {                 // diagnostics: when did S/dP(it) actually complete?
+          mbar_wait(sdp_full, it & 1);
+          stamp(it, 7);
+        }
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
         stamp(it, 1);
@@ -674,10 +690,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t dsa = umma_desc_k_sw128(ds_a + (kk >> 2) * 8192) + 2 * (kk & 3);
           const uint64_t kb = umma_desc_mn_sw128(k_a + kk * 2048, 8192, 1024);
           const uint64_t rb = umma_desc_mn_sw128(rel_a + kk * 2048, 8192, 1024);
-          umma_bf16(tmem_base + AB_COL_DQ, dsa, kb, id_dq, kk ? 1u : 0u);
-          umma_bf16(tmem_base + AB_COL_DQ, dsa, rb, id_dq, 1u);
+          umma_bf16_elect(tmem_base + AB_COL_DQ, dsa, kb, id_dq, kk ? 1u : 0u);
+          umma_bf16_elect(tmem_base + AB_COL_DQ, dsa, rb, id_dq, 1u);
         }
-        umma_commit(dq_full);
+        umma_commit_elect(dq_full);
+        if (tracing) {
+          mbar_wait(dq_full, it & 1);
+          stamp(it, 8);
+        }
         if (it > 0) {
           mbar_wait(dvk_free, (it - 1) & 1);            // dV/dK(it-1) read out
           tc_fence_after();
@@ -690,12 +710,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint64_t dsa = umma_desc_mn_sw128(ds_a + t2 * 16384 + k * 2048, 8192, 1024);
             const uint64_t dob = umma_desc_mn_sw128(do_a + k * 2048, 8192, 1024);
             const uint64_t qb = umma_desc_mn_sw128(q_a + k * 2048, 8192, 1024);
-            umma_bf16(tmem_base + AB_COL_DV + t2 * 64, pa, dob, id_dvk, k ? 1u : 0u);
-            umma_bf16(tmem_base + AB_COL_DK + t2 * 64, dsa, qb, id_dvk, k ? 1u : 0u);
+            umma_bf16_elect(tmem_base + AB_COL_DV + t2 * 64, pa, dob, id_dvk, k ? 1u : 0u);
+            umma_bf16_elect(tmem_base + AB_COL_DK + t2 * 64, dsa, qb, id_dvk, k ? 1u : 0u);
           }
         }
-        umma_commit(out_full);
-        umma_commit(&qk_empty[s]);
+        umma_commit_elect(out_full);
+        umma_commit_elect(&qk_empty[s]);
+        if (tracing) {
+          mbar_wait(out_full, it & 1);
+          stamp(it, 9);
+        }
       }
     }
   } else {
@@ -727,9 +751,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto lse_of = [&](int it) -> float {
       const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
       const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
-      return P.lse[(((long long)b * P.H + by * 8 + qy) * P.W + bx * 8 + qx) * 4 + head] * LOG2E;
+      return P.lse[(((long long)b * P.H + by * 8 + qy) * P.W + bx * 8 + qx) * 4 + head];
     };
-    float l2_next = n_it > 0 ? lse_of(0) : 0.f;
+    float lse_next = n_it > 0 ? lse_of(0) : 0.f;   // raw value: consumed (scaled) one iteration later, so the load never stalls
 
     // P = exp(S - lse) -> smem (and packed registers), partial delta; then dS = P (dP - delta) -> smem.
     // PART is a compile-time copy of `part` so that group counts and the padding mask fold away.
@@ -804,11 +828,60 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     };
 
+    // read-out helper: one 32-column chunk of this warp's dV / dK rows (thread = key row) is transposed through a
+    // swizzled 2 KB smem tile so that every store instruction writes eight complete 64-byte row segments of the
+    // window-major scratch (a row-per-thread store would touch 32 different lines per instruction)
+    auto stage_store = [&](const uint32_t* r, bf16* scratch, int ch0, int zrow) {
+      if (rows_valid) {
+        __syncwarp();                            // the previous chunk's reads of the tile are done
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          st_shared_v4(stage_row + ((g ^ ssw) * 16), pack_bf16x2(__uint_as_float(r[g * 8]), __uint_as_float(r[g * 8 + 1])),
+                       pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
+                       pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])),
+                       pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+        __syncwarp();
+        bf16* dst = scratch + ((long long)zrow * AT_NK + row0) * 64 + ch0 + (lane & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2);    // tile row handled by this lane in pass i
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(smem_u32(stage) + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4)));
+          if (row0 + rr < AT_NK) *reinterpret_cast<uint4*>(dst + rr * 64) = v;
+        }
+      }
+    };
+    // dK rows of iteration `it` (+ dREL accumulation); releases the dV / dK columns to the MMA warp
+    auto readout_dk = [&](int zrow, int it_dbg) {
+      uint32_t a[32], c[32];
+      tmem_ld32(lane_addr + AB_COL_DK + part * 64, a);
+      tmem_ld_wait();
+      stamp(it_dbg, 11);
+      tmem_ld32(lane_addr + AB_COL_DK + part * 64 + 32, c);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) racc[j] += __uint_as_float(a[j]);
+      stage_store(a, P.dk_scratch, 0, zrow);
+      stamp(it_dbg, 6);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dvk_free);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) racc[32 + j] += __uint_as_float(c[j]);
+      stage_store(c, P.dk_scratch, 32, zrow);
+    };
+
+    // (block, head) -> coordinates; the block index only changes every 4th iteration
+    int cbx = 0, cby = 0, cb = 0, zprev = 0;
+    auto coords = [&](int it) {
+      const int blk = blockIdx.x + (it >> 2) * gridDim.x;
+      cbx = blk % P.nbx; cby = (blk / P.nbx) % P.nby; cb = blk / (P.nbx * P.nby);
+    };
+    if (n_it > 0) coords(0);
     for (int it = 0; it < n_it; ++it) {
       const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
-      const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
-      const float l2 = l2_next;
-      if (it + 1 < n_it) l2_next = lse_of(it + 1);   // prefetched one iteration ahead
+      const int bx = cbx, by = cby, b = cb;
+      const float l2 = lse_next * LOG2E;
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
       stamp(it, 2);
@@ -818,6 +891,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       mbar_arrive(ds_full);
       stamp(it, 3);
+      // While the tensor core computes dQ(it): the deferred half of the previous iteration's read-out (dK rows), the
+      // next iteration's coordinates and lse.  dV/dK(it) are issued behind dQ(it) and wait for dvk_free.
+      if (it > 0) readout_dk(zprev, it);
+      stamp(it, 10);
+      if (it + 1 < n_it) {
+        if (((it + 1) & 3) == 0) coords(it + 1);
+        lse_next = P.lse[(((long long)cb * P.H + cby * 8 + qy) * P.W + cbx * 8 + qx) * 4 + ((it + 1) & 3)];
+      }
       // ---- read-out: dQ (32 channels per warp part) ----
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
@@ -830,56 +911,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_arrive(dq_free);
         if (hf == 0) st_row32_bf16((bf16*)P.dq.ptr + view_off(P.dq, b, by * 8 + qy, bx * 8 + qx) + head * 64 + part * 32, a);
       }
-      // ---- read-out: dV, dK rows -> 64B-swizzled smem tile -> TMA store into the window-major bf16 scratch;
-      //      dREL accumulation from the fp32 dK rows ----
+      // ---- read-out: dV rows -> 64B-swizzled smem tile -> TMA store into the window-major bf16 scratch (the dK
+      //      rows follow after the next softmax) ----
       mbar_wait(out_full, it & 1);
       tc_fence_after();
       stamp(it, 5);
+      zprev = blk * 4 + head;
       {
         uint32_t a[32], c[32];
-        const int zrow = blk * 4 + head;
-        auto stage_store = [&](const uint32_t* r, const CUtensorMap* tm, int ch0) {
-          if (rows_valid) {
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous box read out
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              st_shared_v4(stage_row + ((g ^ ssw) * 16), pack_bf16x2(__uint_as_float(r[g * 8]), __uint_as_float(r[g * 8 + 1])),
-                           pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
-                           pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])),
-                           pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                           ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(stage)), "r"(ch0), "r"(row0), "r"(zrow)
-                           : "memory");
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-          }
-        };
         tmem_ld32(lane_addr + AB_COL_DV + part * 64, a);
         tmem_ld_wait();
         tmem_ld32(lane_addr + AB_COL_DV + part * 64 + 32, c);
-        stage_store(a, &tmDV, 0);
+        stage_store(a, P.dv_scratch, 0, zprev);
         tmem_ld_wait();
-        tmem_ld32(lane_addr + AB_COL_DK + part * 64, a);
-        stage_store(c, &tmDV, 32);
-        tmem_ld_wait();
-        tmem_ld32(lane_addr + AB_COL_DK + part * 64 + 32, c);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) racc[j] += __uint_as_float(a[j]);
-        stage_store(a, &tmDK, 0);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(dvk_free);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) racc[32 + j] += __uint_as_float(c[j]);
-        stage_store(c, &tmDK, 32);
+        stage_store(c, P.dv_scratch, 32, zprev);
       }
-      stamp(it, 6);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all scratch stores complete before exit
+    if (n_it > 0) readout_dk(zprev, AB_TRACE_ITERS);
     // relative-position gradient partial of this CTA
     const int rkey = row0 + lane;
     if (rkey < AT_NK) {
@@ -1008,23 +1056,13 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
   P.dk_scratch = (bf16*)a->workspace;
   P.dv_scratch = P.dk_scratch + scratch;
   P.rel_part = (float*)(P.dv_scratch + scratch);
-  CUtensorMap tmDK, tmDV;   // window-major scratch as [nblocks*4][196 keys][64 ch], 32-key x 32-channel boxes, 64B swizzle
-  {
-    uint64_t dims[3] = {64, (uint64_t)AT_NK, (uint64_t)P.nblocks * 4};
-    uint64_t strides[2] = {128, (uint64_t)AT_NK * 128};
-    uint32_t box[3] = {32, 32, 1};
-    rc = make_tmap_bf16(&tmDK, P.dk_scratch, 3, dims, strides, box, 64);
-    if (rc) return rc;
-    rc = make_tmap_bf16(&tmDV, P.dv_scratch, 3, dims, strides, box, 64);
-    if (rc) return rc;
-  }
   static bool attr = false;
   if (!attr) {
     PHT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
     attr = true;
   }
   const int grid = at_grid(P.nblocks);
-  attn_bwd_tc_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, tmDK, tmDV, P);
+  attn_bwd_tc_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, P);
   PHT_LAUNCH_CHECK();
   long long items = (long long)f.B * f.H * f.W * 32;
   int fgrid = (int)((items + 255) / 256);

@@ -54,10 +54,10 @@ print("attn_bwd (+fold +rel reduce)  median %.1f us  min %.1f us" % timed(bwd, a
 if args.trace:
     _lib.lib.pht_set_option(b"attn_trace", 2)
     fwd()
-    buf = (C.c_int64 * (48 * 8))()
-    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * 8)
+    buf = (C.c_int64 * (48 * 12))()
+    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * 12)
     _lib.lib.pht_set_option(b"attn_trace", 0)
-    t = torch.tensor(list(buf)[:n]).view(-1, 8)
+    t = torch.tensor(list(buf)[:n]).view(-1, 12)
     t0 = int(t[0, 0])
     print("FORWARD events: 0=S issue(it) 1=PV issue(it) 2=s_full seen 3=max exchanged 4=epilogue(it-1) done 5=p_full arrive "
           "6=pv_done(it) seen [in epilogue, during it+1]")
@@ -69,19 +69,22 @@ if args.trace:
           % (float((t[24, 2] - t[4, 2]) / 20), seg(2, 3), seg(3, 4), seg(4, 5), seg(5, 1), seg(1, 6)))
     _lib.lib.pht_set_option(b"attn_trace", 1)
     bwd()
-    buf = (C.c_int64 * (48 * 8))()
-    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * 8)
+    buf = (C.c_int64 * (48 * 12))()
+    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * 12)
     _lib.lib.pht_set_option(b"attn_trace", 0)
-    t = torch.tensor(list(buf)[:n]).view(-1, 8)
+    t = torch.tensor(list(buf)[:n]).view(-1, 12)
     t0 = int(t[0, 0])
-    names = ["M1 issue", "M2 issue", "sdp_full seen", "ds arrive", "dq_full seen", "out_full seen", "R done", "-"]
+    names = ["M1 issue", "M2 issue", "sdp_full seen", "ds arrive", "dq_full seen", "out_full seen", "R done", "M1 done (MMA thread)"]
     print("events (clocks since M1 issue of iteration 0): " + ", ".join(f"{i}={n}" for i, n in enumerate(names)))
     for i in range(min(24, t.shape[0])):
-        print(f"it {i:2d}: " + " ".join(f"{int(x) - t0:8d}" for x in t[i]))
+        print(f"it {i:2d}: " + " ".join(f"{int(x) - t0:8d}" for x in t[i, :8]))
     d = t[8:40]
     print("mean per-iteration period (clk): %.0f" % float((t[40, 0] - t[8, 0]) / 32))
     seg = lambda a, b: float((d[:, b] - d[:, a]).float().mean())
     print("M1 issue->sdp_full seen %.0f | softmax/dS %.0f | ds arrive->M2 issue %.0f | M2 issue->dq_full %.0f | "
           "dq_full->out_full %.0f | out_full->R done %.0f" % (seg(0, 2), seg(2, 3), seg(3, 1), seg(1, 4), seg(4, 5), seg(5, 6)))
+    print("M1 issue -> M1 done %.0f | M2 issue -> dQ done (MMA thread) %.0f -> dV/dK done %.0f | ds arrive -> dK(it-1) read-out done %.0f"
+          % (seg(0, 7), seg(1, 8), seg(8, 9), seg(3, 10)))
+    print("dK read-out: ds arrive -> first ld done %.0f -> first chunk stored %.0f -> all done %.0f" % (seg(3, 11), seg(11, 6), seg(6, 10)))
     nxt = (t[9:41, 0] - d[:, 6]).float().mean()
     print("R done -> next M1 issue %.0f (negative = M1 already issued)" % float(nxt))

@@ -9,11 +9,13 @@ using namespace pht::tc;
 
 struct Shape { int M, N, amn, bmn, nacc; };
 
-__global__ void __launch_bounds__(128, 1) rate_kernel(const Shape* shapes, int nshape, int reps, long long* out) {
+__global__ void __launch_bounds__(160, 1) rate_kernel(const Shape* shapes, int nshape, int reps, long long* out, int ld_warps, int ld_cols, long long* ld_stats) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
+  __shared__ volatile int stop_flag;
+  if (threadIdx.x == 0) stop_flag = 0;
   for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   if (threadIdx.x < 32) tmem_alloc(&slot, 512);
@@ -51,6 +53,24 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(const Shape* shapes, int n
       }
     }
   }
+  if (threadIdx.x == 0) stop_flag = 1;
+  // warps 1..ld_warps hammer tcgen05.ld on their TMEM sub-partition while thread 0 issues the MMAs
+  if (threadIdx.x >= 32 && (int)(threadIdx.x >> 5) <= ld_warps) {
+    const uint32_t la = tm + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16) + ld_cols;
+    float acc = 0.f;
+    long long n = 0;
+    const long long t0 = clock64();
+    while (!stop_flag) {
+      uint32_t r[32];
+      tmem_ld32(la, r);
+      tmem_ld_wait();
+      acc += __uint_as_float(r[0] ^ r[31]);
+      ++n;
+    }
+    const long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) { ld_stats[(threadIdx.x >> 5) * 2] = n; ld_stats[(threadIdx.x >> 5) * 2 + 1] = t1 - t0; }
+    if (acc == 123.f) out[0] = 1;
+  }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
@@ -72,22 +92,29 @@ int main() {
   cudaMalloc(&dout, sizeof(long long) * n * grid);
   cudaMemcpy(ds, hs, sizeof(hs), cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  for (int g : {grid}) {
-    rate_kernel<<<g, 128, 200 * 1024>>>(ds, n, reps, dout);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
-    long long* h = (long long*)malloc(sizeof(long long) * n * g);
-    cudaMemcpy(h, dout, sizeof(long long) * n * g, cudaMemcpyDeviceToHost);
-    printf("grid %d, %d back-to-back MMAs (K=16) per shape\n", g, reps);
-    printf("%5s %5s %4s %4s %4s %12s %14s %12s\n", "M", "N", "aMN", "bMN", "nacc", "clk/MMA", "MAC/clk/SM", "vs 128xN/256");
+  long long* dstats;
+  cudaMalloc(&dstats, sizeof(long long) * 16);
+  for (int ldw : {0, 4, 104}) {
+    const int g = grid;
+    const int ld_warps = ldw % 100, ld_cols = ldw >= 100 ? 0 : 384;
+    printf("---- %d warps looping tcgen05.ld.x32 (+wait) at TMEM column %d (MMAs accumulate into columns [0,256)) ----\n", ld_warps, ld_cols);
+    printf("%5s %5s %4s %4s %4s %12s %14s %16s\n", "M", "N", "aMN", "bMN", "nacc", "clk/MMA", "MAC/clk/SM", "clk per ld+wait");
     for (int s = 0; s < n; ++s) {
+      cudaMemset(dstats, 0, sizeof(long long) * 16);
+      rate_kernel<<<g, 160, 200 * 1024>>>(ds + s, 1, reps, dout, ld_warps, ld_cols, dstats);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+      long long* h = (long long*)malloc(sizeof(long long) * g);
+      cudaMemcpy(h, dout, sizeof(long long) * g, cudaMemcpyDeviceToHost);
+      long long st[16];
+      cudaMemcpy(st, dstats, sizeof(st), cudaMemcpyDeviceToHost);
       long long mx = 0;
-      for (int b = 0; b < g; ++b) mx = h[b * n + s] > mx ? h[b * n + s] : mx;
+      for (int b = 0; b < g; ++b) mx = h[b] > mx ? h[b] : mx;
       const double c = (double)mx / reps;
-      printf("%5d %5d %4d %4d %4d %12.1f %14.0f %12.2f\n", hs[s].M, hs[s].N, hs[s].amn, hs[s].bmn, hs[s].nacc, c,
-             (double)hs[s].M * hs[s].N * 16 / c, c / (128.0 * hs[s].N / 256.0));
+      printf("%5d %5d %4d %4d %4d %12.1f %14.0f %16.1f\n", hs[s].M, hs[s].N, hs[s].amn, hs[s].bmn, hs[s].nacc, c,
+             (double)hs[s].M * hs[s].N * 16 / c, st[2] ? (double)st[3] / st[2] : 0.0);
+      free(h);
     }
-    free(h);
   }
   return 0;
 }
