@@ -336,6 +336,8 @@ void pht_reset_counters(void);
 void pht_set_force_simple(int on);
 /* tuning / A-B knobs: "tc_cfg" = 0 auto, 1 prefer the deep-ring conv_gemm config, 2 force the wide-epilogue one;
  * "wgrad_split_div" = d: 1x1 weight-gradients use 1/d of the pixel splits (fewer fp32 partials);
+ * "pdl" = 0 / 1 (default 1): launch the tcgen05 kernels with programmatic dependent launch (their preamble overlaps
+ * the previous kernel's tail);
  * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics) */
 int pht_set_option(const char* name, int value);
 /* Copies the stamps recorded under "attn_trace" ([iteration][12 events], first 48 iterations of CTA 0) to host memory

@@ -98,24 +98,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // one-time smem constants: zero pad rows of K / V, the relative-position tile (swizzled like a TMA box)
-  for (int i = threadIdx.x; i < AT_NS * 8; i += blockDim.x) {   // REL rows 0..199, 16-byte chunks
-    const int R = i >> 3, ch = i & 7;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (R < AT_NK) {
-      const int wr = R / 14, wc = R - wr * 14;
-      const float* src = ch < 4 ? P.rel_h + wr * 32 + ch * 8 : P.rel_w + wc * 32 + (ch - 4) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = src[j];
-    }
-    uint4 u;
-    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(RELs + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
-  }
+  // one-time smem constants that need no global memory: zero pad rows of K / V, zero P tile
   for (int i = threadIdx.x; i < 2 * (AT_NS - AT_NK) * 8; i += blockDim.x) {   // K rows 196..199
     const int h = i / ((AT_NS - AT_NK) * 8), rem = i % ((AT_NS - AT_NK) * 8);
     *reinterpret_cast<uint4*>(Ks + h * AT_K_BYTES + (AT_NK + rem / 8) * 128 + (rem % 8) * 16) = make_uint4(0, 0, 0, 0);
@@ -144,10 +127,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  griddep_wait();   // (programmatic dependent launch: the preamble above overlapped the previous kernel's tail)
+  // the relative-position tile (swizzled like a TMA box), built from the rel_h / rel_w parameters
+  for (int i = threadIdx.x; i < AT_NS * 8; i += blockDim.x) {   // REL rows 0..199, 16-byte chunks
+    const int R = i >> 3, ch = i & 7;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (R < AT_NK) {
+      const int wr = R / 14, wc = R - wr * 14;
+      const float* src = ch < 4 ? P.rel_h + wr * 32 + ch * 8 : P.rel_w + wc * 32 + (ch - 4) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = src[j];
+    }
+    uint4 u;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(RELs + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
 
   const int my_blocks = (P.nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -485,7 +488,7 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.nblocks < sms ? P.nblocks : sms;
-  attn_fwd_tc_kernel<<<grid, AF_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, tmR, tmO, P);
+  PHT_CUDA(launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(AF_THREADS), AT_SMEM, st, tmQ, tmK, tmV, tmR, tmO, P));
   PHT_LAUNCH_CHECK();
   count_launch(CNT_ATTN_TC);
   *handled = true;
@@ -572,24 +575,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- one-time smem constants --------------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < AB_ROWS * 8; i += blockDim.x) {   // REL tile rows 0..207
-    const int R = i >> 3, ch = i & 7;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (R < AT_NK) {
-      const int wr = R / 14, wc = R - wr * 14;
-      const float* src = ch < 4 ? P.rel_h + wr * 32 + ch * 8 : P.rel_w + wc * 32 + (ch - 4) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = src[j];
-    }
-    uint4 u;
-    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(RELs + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
-  }
+  // ---- one-time smem constants that need no global memory ----------------------------------------------------
   for (int i = threadIdx.x; i < 3 * (AB_ROWS - AT_NK) * 8; i += blockDim.x) {   // K (both stages) / V rows 196..207
     const int which = i / ((AB_ROWS - AT_NK) * 8), rem = i % ((AB_ROWS - AT_NK) * 8);
     uint8_t* tile = which < 2 ? St + which * AB_STAGE_BYTES + 2 * AB_Q_BYTES : Vs;
@@ -617,10 +603,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  griddep_wait();   // (programmatic dependent launch: the preamble above overlapped the previous kernel's tail)
+  // the relative-position tile, built from the rel_h / rel_w parameters
+  for (int i = threadIdx.x; i < AB_ROWS * 8; i += blockDim.x) {   // REL tile rows 0..207
+    const int R = i >> 3, ch = i & 7;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (R < AT_NK) {
+      const int wr = R / 14, wc = R - wr * 14;
+      const float* src = ch < 4 ? P.rel_h + wr * 32 + ch * 8 : P.rel_w + wc * 32 + (ch - 4) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = src[j];
+    }
+    uint4 u;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(RELs + R * 128 + ((ch ^ (R & 7)) * 16)) = u;
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
   const int my_blocks = (P.nblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_it = 4 * my_blocks;  // (block, head) iterations
@@ -1062,7 +1068,7 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
     attr = true;
   }
   const int grid = at_grid(P.nblocks);
-  attn_bwd_tc_kernel<<<grid, AB_THREADS, AB_SMEM, st>>>(tmQ, tmK, tmV, tmDO, P);
+  PHT_CUDA(launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, P));
   PHT_LAUNCH_CHECK();
   long long items = (long long)f.B * f.H * f.W * 32;
   int fgrid = (int)((items + 255) / 256);

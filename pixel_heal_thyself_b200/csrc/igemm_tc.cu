@@ -120,13 +120,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
-    s_bias[i] = P.bias ? P.bias[i] : 0.f;
-    if (Cfg::VEC_SMEM) {
-      s_slope[i] = P.slope ? P.slope[i] : 1.f;
-      s_mslope[i] = P.mslope ? P.mslope[i] : 0.f;
-    }
-  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
     if (P.n_src > 1) prefetch_tmap(&tmA1);
@@ -145,9 +138,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  griddep_wait();   // everything above overlapped the previous kernel's tail; global memory is read from here on
+  for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
+    s_bias[i] = P.bias ? P.bias[i] : 0.f;
+    if (Cfg::VEC_SMEM) {
+      s_slope[i] = P.slope ? P.slope[i] : 1.f;
+      s_mslope[i] = P.mslope ? P.mslope[i] : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
 
   const int T = P.ks * P.ks, half = P.ks / 2;
@@ -466,7 +468,8 @@ static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
-  conv_gemm_tc_kernel<BN, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(m.A[0], m.A[1], m.A[2], m.W, m.O[0], m.O[1], m.R, m.M, P);
+  PHT_CUDA(launch_pdl(conv_gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1], m.A[2], m.W,
+                      m.O[0], m.O[1], m.R, m.M, P));
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }

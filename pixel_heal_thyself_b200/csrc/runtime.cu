@@ -10,6 +10,7 @@ namespace pht {
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_counters[8];
 static std::atomic<int> g_force_simple{0};
+static std::atomic<int> g_pdl{1};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -23,6 +24,7 @@ void set_wgrad_split_div(int v);  // wgrad_tc.cu
 void set_attn_trace(int v);  // attention_tc.cu
 int read_attn_trace(long long* host, int n);  // attention_tc.cu
 bool force_simple() { return g_force_simple.load(std::memory_order_relaxed) != 0; }
+namespace tc { bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; } }
 
 }  // namespace pht
 
@@ -39,6 +41,7 @@ void pht_reset_counters(void) {
 int pht_set_option(const char* name, int value) {
   if (name && !strcmp(name, "tc_cfg")) { pht::set_tc_cfg(value); return PHT_OK; }
   if (name && !strcmp(name, "wgrad_split_div")) { pht::set_wgrad_split_div(value); return PHT_OK; }
+  if (name && !strcmp(name, "pdl")) { pht::g_pdl.store(value ? 1 : 0, std::memory_order_relaxed); return PHT_OK; }
   if (name && !strcmp(name, "attn_trace")) { pht::set_attn_trace(value); return PHT_OK; }
   pht::set_error("pht_set_option: unknown option");
   return PHT_ERR_INVALID;

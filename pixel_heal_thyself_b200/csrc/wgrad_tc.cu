@@ -87,9 +87,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  griddep_wait();   // (programmatic dependent launch: the preamble above overlapped the previous kernel's tail)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + (kt.wk / 64) * WG_BOX_BYTES);
 
@@ -420,14 +422,14 @@ int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled, pht_wgrad_
       PHT_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<2>::SMEM_BYTES));
       attr = true;
     }
-    wgrad_tc_kernel<2><<<jobs, WG_THREADS, WgCfg<2>::SMEM_BYTES, st>>>(tmDy, tmS[0], tmS[1], tmS[2], P);
+    PHT_CUDA(launch_pdl(wgrad_tc_kernel<2>, dim3(jobs), dim3(WG_THREADS), WgCfg<2>::SMEM_BYTES, st, tmDy, tmS[0], tmS[1], tmS[2], P));
   } else {
     static bool attr = false;
     if (!attr) {
       PHT_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<1>::SMEM_BYTES));
       attr = true;
     }
-    wgrad_tc_kernel<1><<<jobs, WG_THREADS, WgCfg<1>::SMEM_BYTES, st>>>(tmDy, tmS[0], tmS[1], tmS[2], P);
+    PHT_CUDA(launch_pdl(wgrad_tc_kernel<1>, dim3(jobs), dim3(WG_THREADS), WgCfg<1>::SMEM_BYTES, st, tmDy, tmS[0], tmS[1], tmS[2], P));
   }
   PHT_LAUNCH_CHECK();
   if (defer) {   // leave the partials in the workspace; the caller batches the reduction
