@@ -47,7 +47,7 @@ def _traffic():
     n = t["launches_per_step"]
     mean = (t["conv3x3_deep_bytes"] * n["deep"] + t["conv3x3_fused_bytes"] * n["fused"]) / (n["deep"] + n["fused"])
     return mean, {"deep": t["conv3x3_deep_bytes"], "fused_epilogue": t["conv3x3_fused_bytes"], "unit": "bytes/launch",
-                  "source": "profiles/r1_ncu_full_conv3x3.txt"}
+                  "source": "profiles/r1_ncu_full_conv_final.txt"}
 
 
 def _peaks():

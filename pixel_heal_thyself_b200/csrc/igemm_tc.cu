@@ -40,6 +40,7 @@ struct TcGemmP {
   View out1;          // only used when out1_f32
   int has_out1, has_out2, has_resid, has_mask;
   int out1_f32;       // out1 is fp32 (direct stores; used by the 64-wide decoder-tail GEMM only)
+  int rev;            // walk the tiles last-to-first
   int residOy, residOx, maskOy, maskOx, out1Oy, out1Ox, out2Oy, out2Ox;
 };
 
@@ -161,7 +162,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
+        const int nt = te % P.n_tiles, mt = te / P.n_tiles;
         const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
         const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * BN;
         for (int t = 0; t < T; ++t) {
@@ -226,7 +228,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int j = 0;
       int fills[2] = {0, 0};   // PARTS == 2: slot p is a depth-1 FIFO feeding epilogue group p (chunks c with c % 2 == p)
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+        const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
+        const int nt = te % P.n_tiles, mt = te / P.n_tiles;
         const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
         const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * BN;
         for (int c = 0; c < NCHUNK; ++c) {
@@ -293,7 +296,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % P.n_tiles, mt = tile / P.n_tiles;
+      const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
+        const int nt = te % P.n_tiles, mt = te / P.n_tiles;
       const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
       const int x0 = tx * TILE_W, y0 = ty * TILE_H;
       const int x = x0 + px, y = y0 + py, n0 = nt * BN;
@@ -475,6 +479,8 @@ static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
 }
 
 static std::atomic<int> g_tc_cfg{0};  // 0 = auto, 1 = force "deep" where legal, 2 = force "wide"
+static std::atomic<int> g_serpentine{1};
+void set_serpentine(int v) { g_serpentine.store(v, std::memory_order_relaxed); }
 void set_tc_cfg(int v) { g_tc_cfg.store(v, std::memory_order_relaxed); }
 
 int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
@@ -529,6 +535,11 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
     int rc = make_tmap_bf16(&m.W, const_cast<void*>(a->w), 3, dims, strides, box);
     if (rc) return rc;
   }
+  // Serpentine tile order: consecutive launches walk their tiles in opposite directions, so a kernel starts on the
+  // part of its input that the previous kernel wrote LAST and that is still resident in the 126 MB L2
+  // (the activations are 67-134 MB each; walking them in the same direction every time always misses).
+  static std::atomic<unsigned> launch_parity{0};
+  P.rev = (g_serpentine.load(std::memory_order_relaxed) && (launch_parity.fetch_add(1, std::memory_order_relaxed) & 1)) ? 1 : 0;
   P.tiles_x = ceil_div(a->Wo, TILE_W);
   P.tiles_y = ceil_div(a->Ho, TILE_H);
   P.n_tiles = a->N / BN;
