@@ -41,6 +41,8 @@ struct TcGemmP {
   int has_out1, has_out2, has_resid, has_mask;
   int out1_f32;       // out1 is fp32 (direct stores; used by the 64-wide decoder-tail GEMM only)
   int rev;            // walk the tiles last-to-first
+  int strip_rows;     // > 0: the last 2 output rows are covered by 2 x 64-pixel strip tiles (pad-fold domain, see conv_gemm_tc)
+  int n_strip, reg_tiles_y;
   int residOy, residOx, maskOy, maskOx, out1Oy, out1Ox, out2Oy, out2Ox;
 };
 
@@ -67,6 +69,29 @@ template <int BN, int MODE> struct TcCfg {
 };
 static_assert(TcCfg<256, 0>::SMEM_BYTES <= 232448 && TcCfg<256, 1>::SMEM_BYTES <= 232448 && TcCfg<256, 2>::SMEM_BYTES <= 232448,
               "conv_gemm_tc: shared memory budget");
+
+// tile index -> image, tile origin, shape.  Regular tiles are 8 x 16 pixels; with P.strip_rows the domain's last two
+// rows are covered by 2 x 64 strips (a 130-row padded domain needs 16 tile rows + 3 strips per image instead of 17 x 9
+// tiles: 147 instead of 153 tiles per image, i.e. 8 instead of 9 waves of 148 CTAs at B = 8)
+struct TileXY {
+  int b, x0, y0, nt, strip;
+};
+__device__ __forceinline__ TileXY decode_tile(const TcGemmP& P, int tile) {
+  const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
+  TileXY t;
+  t.nt = te % P.n_tiles;
+  const int mt = te / P.n_tiles;
+  const int reg = P.tiles_x * P.reg_tiles_y, per_img = reg + P.n_strip;
+  t.b = mt / per_img;
+  const int r = mt - t.b * per_img;
+  if (r < reg) {
+    const int ty = r / P.tiles_x;
+    t.strip = 0; t.x0 = (r - ty * P.tiles_x) * TILE_W; t.y0 = ty * TILE_H;
+  } else {
+    t.strip = 1; t.x0 = (r - reg) * 64; t.y0 = P.Ho - 2;
+  }
+  return t;
+}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -96,7 +121,10 @@ __global__ void __launch_bounds__((TcCfg<BN, MODE>::THREADS), 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
-                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmM, const TcGemmP P) {
+                    const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmM,
+                    const __grid_constant__ CUtensorMap tmA0s, const __grid_constant__ CUtensorMap tmO1s,
+                    const __grid_constant__ CUtensorMap tmO2s, const __grid_constant__ CUtensorMap tmRs,
+                    const __grid_constant__ CUtensorMap tmMs, const TcGemmP P) {
   using Cfg = TcCfg<BN, MODE>;
   constexpr int NCHUNK = BN / 64;
   constexpr bool AUX = Cfg::AUX_SLOTS > 0;
@@ -162,14 +190,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
-        const int nt = te % P.n_tiles, mt = te / P.n_tiles;
-        const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
-        const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * BN;
+        const TileXY tl = decode_tile(P, tile);
+        const int b = tl.b, x0 = tl.x0, y0 = tl.y0, n0 = tl.nt * BN;
         for (int t = 0; t < T; ++t) {
           const int dy = t / P.ks - half, dx = t % P.ks - half;
           for (int s = 0; s < P.n_src; ++s) {
-            const CUtensorMap* tm = s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2);
+            const CUtensorMap* tm = tl.strip ? &tmA0s : (s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2));
             for (int kc = 0; kc < P.srcC[s]; kc += BK) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* a_dst = stage_base + stage * Cfg::STAGE_BYTES;
@@ -228,18 +254,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int j = 0;
       int fills[2] = {0, 0};   // PARTS == 2: slot p is a depth-1 FIFO feeding epilogue group p (chunks c with c % 2 == p)
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
-        const int nt = te % P.n_tiles, mt = te / P.n_tiles;
-        const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
-        const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * BN;
+        const TileXY tl = decode_tile(P, tile);
+        const int b = tl.b, x0 = tl.x0, y0 = tl.y0, n0 = tl.nt * BN;
+        const CUtensorMap* tmRr = tl.strip ? &tmRs : &tmR;
+        const CUtensorMap* tmMm = tl.strip ? &tmMs : &tmM;
         for (int c = 0; c < NCHUNK; ++c) {
           for (int kind = P.has_resid ? 0 : 1; kind < (P.has_mask ? 2 : 1); ++kind, ++j) {
             const int slot = PARTS == 2 ? (c & 1) : j % NS;
             const int fill = PARTS == 2 ? fills[slot]++ : j / NS;
             mbar_wait(&aempty_bar[slot], (fill & 1) ^ 1);
             mbar_expect_tx(&afull_bar[slot], STG_BYTES);
-            if (kind == 0) tma_load_4d(aux + slot * STG_BYTES, &tmR, &afull_bar[slot], n0 + c * 64, x0 - fo + P.residOx, y0 - fo + P.residOy, b);
-            else tma_load_4d(aux + slot * STG_BYTES, &tmM, &afull_bar[slot], n0 + c * 64, x0 - fo + P.maskOx, y0 - fo + P.maskOy, b);
+            if (kind == 0) tma_load_4d(aux + slot * STG_BYTES, tmRr, &afull_bar[slot], n0 + c * 64, x0 - fo + P.residOx, y0 - fo + P.residOy, b);
+            else tma_load_4d(aux + slot * STG_BYTES, tmMm, &afull_bar[slot], n0 + c * 64, x0 - fo + P.maskOx, y0 - fo + P.maskOy, b);
           }
         }
       }
@@ -249,7 +275,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int part = (PARTS == 2 && warp >= 7) ? 1 : 0;   // epilogue group: takes the 64-channel chunks c with c % PARTS == part
     const int row = quad * 32 + lane;      // accumulator row == pixel index inside the tile
-    const int py = row / TILE_W, px = row % TILE_W;
     const bool issuer = ((warp == 2 || warp == 7) && lane == 0);
     auto group_sync = [&]() {
       if (part == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -296,11 +321,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     };
     int it = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
-      const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
-        const int nt = te % P.n_tiles, mt = te / P.n_tiles;
-      const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, b = mt / (P.tiles_x * P.tiles_y);
-      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-      const int x = x0 + px, y = y0 + py, n0 = nt * BN;
+      const TileXY tl = decode_tile(P, tile);
+      const int b = tl.b, x0 = tl.x0, y0 = tl.y0;
+      const int tw = tl.strip ? 64 : TILE_W;               // tile width in pixels (rows of the tile are tw pixels apart)
+      const int py = tl.strip ? (row >> 6) : row / TILE_W, px = tl.strip ? (row & 63) : row % TILE_W;
+      const CUtensorMap* tmOut1 = tl.strip ? &tmO1s : &tmO1;
+      const CUtensorMap* tmOut2 = tl.strip ? &tmO2s : &tmO2;
+      const int x = x0 + px, y = y0 + py, n0 = tl.nt * BN;
       const bool valid = x < P.Wo && y < P.Ho;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -353,9 +380,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
               }
             };
-            if (ey) add_row(row + ey * TILE_W);
+            if (ey) add_row(row + ey * tw);
             if (ex) add_row(row + ex);
-            if (ey && ex) add_row(row + ey * TILE_W + ex);
+            if (ey && ex) add_row(row + ey * tw + ex);
           }
         }
         if (AUX && (P.flags & PHT_EPI_RESID_PRE)) aux_apply(v, n0 + c0, false);
@@ -372,13 +399,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               for (int j = 0; j < 64; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           } else {
-            stage_and_store(v, &tmO1, n0 + c0, x0 + P.out1Ox, y0 + P.out1Oy, b);
+            stage_and_store(v, tmOut1, n0 + c0, x0 + P.out1Ox, y0 + P.out1Oy, b);
           }
         }
         if (P.has_out2) {   // (the host clears RESID_POST / MASK when there is no out2)
           if (AUX && (P.flags & PHT_EPI_RESID_POST)) aux_apply(v, n0 + c0, false);
           if (AUX && (P.flags & PHT_EPI_MASK)) aux_apply(v, n0 + c0, true);
-          stage_and_store(v, &tmO2, n0 + c0, x0 + P.out2Ox, y0 + P.out2Oy, b);
+          stage_and_store(v, tmOut2, n0 + c0, x0 + P.out2Ox, y0 + P.out2Oy, b);
         }
       }
     }
@@ -449,15 +476,16 @@ static bool view_tma_ok(const pht_view& v) {
   return true;
 }
 
-static int make_src_tmap(CUtensorMap* tm, const pht_view& v, int B) {
+static int make_src_tmap(CUtensorMap* tm, const pht_view& v, int B, bool strip = false) {
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)v.sx * 2, (uint64_t)v.sy * 2, (uint64_t)v.sb * 2};
-  uint32_t box[4] = {BK, TILE_W, TILE_H, 1};
+  uint32_t box[4] = {BK, strip ? 64u : (uint32_t)TILE_W, strip ? 2u : (uint32_t)TILE_H, 1};
   return make_tmap_bf16(tm, v.ptr, 4, dims, strides, box);
 }
 
 struct TcMaps {
   CUtensorMap A[3], W, O[2], R, M;
+  CUtensorMap As, Os[2], Rs, Ms;   // 2 x 64-pixel strip boxes (pad-fold domain only)
 };
 
 template <int BN, int MODE>
@@ -473,13 +501,15 @@ static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
   PHT_CUDA(launch_pdl(conv_gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1], m.A[2], m.W,
-                      m.O[0], m.O[1], m.R, m.M, P));
+                      m.O[0], m.O[1], m.R, m.M, m.As, m.Os[0], m.Os[1], m.Rs, m.Ms, P));
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
 
 static std::atomic<int> g_tc_cfg{0};  // 0 = auto, 1 = force "deep" where legal, 2 = force "wide"
 static std::atomic<int> g_serpentine{1};
+static std::atomic<int> g_strips{1};
+void set_strips(int v) { g_strips.store(v, std::memory_order_relaxed); }
 void set_serpentine(int v) { g_serpentine.store(v, std::memory_order_relaxed); }
 void set_tc_cfg(int v) { g_tc_cfg.store(v, std::memory_order_relaxed); }
 
@@ -543,7 +573,13 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   P.tiles_x = ceil_div(a->Wo, TILE_W);
   P.tiles_y = ceil_div(a->Ho, TILE_H);
   P.n_tiles = a->N / BN;
-  P.num_tiles = a->B * P.tiles_x * P.tiles_y * P.n_tiles;
+  // pad-fold domain (H+2 rows, (H+2) % 8 == 2): the last two rows as 2 x 64 strips instead of a ninth/seventeenth
+  // row of 8 x 16 tiles that would be 3/4 empty
+  const bool strips = padfold && a->n_src == 1 && g_strips.load(std::memory_order_relaxed) != 0;
+  P.strip_rows = strips ? 2 : 0;
+  P.reg_tiles_y = strips ? (a->Ho - 2) / TILE_H : P.tiles_y;
+  P.n_strip = strips ? ceil_div(a->Wo, 64) : 0;
+  P.num_tiles = a->B * (P.tiles_x * P.reg_tiles_y + P.n_strip) * P.n_tiles;
   P.bias = a->bias; P.slope = a->slope; P.mslope = a->mslope;
   P.out1 = a->out1.ptr ? make_view(a->out1) : null_view();
   P.has_out1 = a->out1.ptr ? 1 : 0; P.has_out2 = a->out2.ptr ? 1 : 0;
@@ -557,6 +593,14 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   if (!rc && a->out2.ptr) rc = make_src_tmap(&m.O[1], a->out2, a->B);
   if (!rc && has_resid) rc = make_src_tmap(&m.R, a->resid, a->B);
   if (!rc && has_mask) rc = make_src_tmap(&m.M, a->mask, a->B);
+  m.As = m.Os[0] = m.Os[1] = m.Rs = m.Ms = m.W;
+  if (!rc && strips) {
+    rc = make_src_tmap(&m.As, a->src[0], a->B, true);
+    if (!rc && a->out1.ptr && !out1_f32) rc = make_src_tmap(&m.Os[0], a->out1, a->B, true);
+    if (!rc && a->out2.ptr) rc = make_src_tmap(&m.Os[1], a->out2, a->B, true);
+    if (!rc && has_resid) rc = make_src_tmap(&m.Rs, a->resid, a->B, true);
+    if (!rc && has_mask) rc = make_src_tmap(&m.Ms, a->mask, a->B, true);
+  }
   if (rc) return rc;
   // 1x1 GEMMs are HBM-bound: wide epilogue.  3x3: deep ring; with a fused epilogue (inputs, second output, fold) the
   // deep+aux variant.

@@ -22,6 +22,7 @@ void count_launch(int slot, uint64_t n) { g_counters[slot & 7].fetch_add(n, std:
 void set_tc_cfg(int v);  // igemm_tc.cu
 void set_wgrad_split_div(int v);  // wgrad_tc.cu
 void set_serpentine(int v);  // igemm_tc.cu
+void set_strips(int v);  // igemm_tc.cu
 void set_attn_trace(int v);  // attention_tc.cu
 int read_attn_trace(long long* host, int n);  // attention_tc.cu
 bool force_simple() { return g_force_simple.load(std::memory_order_relaxed) != 0; }
@@ -42,6 +43,7 @@ void pht_reset_counters(void) {
 int pht_set_option(const char* name, int value) {
   if (name && !strcmp(name, "tc_cfg")) { pht::set_tc_cfg(value); return PHT_OK; }
   if (name && !strcmp(name, "wgrad_split_div")) { pht::set_wgrad_split_div(value); return PHT_OK; }
+  if (name && !strcmp(name, "strips")) { pht::set_strips(value); return PHT_OK; }
   if (name && !strcmp(name, "serpentine")) { pht::set_serpentine(value); return PHT_OK; }
   if (name && !strcmp(name, "pdl")) { pht::g_pdl.store(value ? 1 : 0, std::memory_order_relaxed); return PHT_OK; }
   if (name && !strcmp(name, "attn_trace")) { pht::set_attn_trace(value); return PHT_OK; }
