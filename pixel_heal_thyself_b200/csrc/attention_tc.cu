@@ -24,6 +24,8 @@ namespace pht {
 
 using namespace tc;
 
+void walk_dir_set(const void* p, int dir);   // igemm_tc.cu: tile-walk direction bookkeeping (serpentine order)
+
 constexpr int AF_THREADS = 352;                                // forward kernel (11 warps)
 constexpr int AT_NK = 196, AT_NKP = 208, AT_NS = 200;          // keys, keys padded to 16 (P / V), S columns = K-tile rows
 constexpr int AT_Q_BYTES = 64 * 128;                           // 8 KB per head
@@ -490,6 +492,7 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   int grid = P.nblocks < sms ? P.nblocks : sms;
   PHT_CUDA(launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(AF_THREADS), AT_SMEM, st, tmQ, tmK, tmV, tmR, tmO, P));
   PHT_LAUNCH_CHECK();
+  walk_dir_set(a->out.ptr, 0);   // written first-to-last
   count_launch(CNT_ATTN_TC);
   *handled = true;
   return PHT_OK;
@@ -1077,6 +1080,9 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
                                              P.nby, P.nbx);
   attn_bwd_rel_reduce_kernel<<<896, 64, 0, st>>>(P.rel_part, grid, a->d_rel_h, a->d_rel_w);
   PHT_LAUNCH_CHECK();
+  walk_dir_set(a->dq.ptr, 0);
+  walk_dir_set(a->dk.ptr, 0);
+  walk_dir_set(a->dv.ptr, 0);
   count_launch(CNT_ATTN_TC);
   count_launch(CNT_OTHER, 2);
   *handled = true;

@@ -508,6 +508,18 @@ static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
 
 static std::atomic<int> g_tc_cfg{0};  // 0 = auto, 1 = force "deep" where legal, 2 = force "wide"
 static std::atomic<int> g_serpentine{1};
+// direction (0 = first-to-last tile, 1 = last-to-first) in which a buffer was most recently written; small direct-mapped
+// table keyed by the base pointer (host-side bookkeeping only; a wrong entry costs L2 hits, never correctness)
+static struct { const void* ptr; int dir; } g_walk[256];
+static inline unsigned walk_slot(const void* p) { return (unsigned)(((uintptr_t)p >> 8) * 2654435761u) >> 24; }
+int walk_dir_get(const void* p) {
+  const auto& e = g_walk[walk_slot(p)];
+  return e.ptr == p ? e.dir : 0;
+}
+void walk_dir_set(const void* p, int dir) {
+  auto& e = g_walk[walk_slot(p)];
+  e.ptr = p; e.dir = dir;
+}
 static std::atomic<int> g_strips{1};
 void set_strips(int v) { g_strips.store(v, std::memory_order_relaxed); }
 void set_serpentine(int v) { g_serpentine.store(v, std::memory_order_relaxed); }
@@ -568,8 +580,11 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   // Serpentine tile order: consecutive launches walk their tiles in opposite directions, so a kernel starts on the
   // part of its input that the previous kernel wrote LAST and that is still resident in the 126 MB L2
   // (the activations are 67-134 MB each; walking them in the same direction every time always misses).
-  static std::atomic<unsigned> launch_parity{0};
-  P.rev = (g_serpentine.load(std::memory_order_relaxed) && (launch_parity.fetch_add(1, std::memory_order_relaxed) & 1)) ? 1 : 0;
+  // The direction every buffer was last written in is remembered (walk_dir_*); a consumer walks opposite to its
+  // producer.  Buffers written by other kernels (attention, elementwise) count as first-to-last.
+  P.rev = g_serpentine.load(std::memory_order_relaxed) ? (walk_dir_get(a->src[0].ptr) ^ 1) : 0;
+  if (a->out1.ptr) walk_dir_set(a->out1.ptr, P.rev);
+  if (a->out2.ptr) walk_dir_set(a->out2.ptr, P.rev);
   P.tiles_x = ceil_div(a->Wo, TILE_W);
   P.tiles_y = ceil_div(a->Ho, TILE_H);
   P.n_tiles = a->N / BN;
