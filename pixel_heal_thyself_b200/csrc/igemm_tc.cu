@@ -211,7 +211,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    {   // all 32 lanes run the loop (warp-converged); one elected lane issues each tcgen05 instruction
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -234,12 +234,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in the (>>4) address field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) ? 1u : 0u);
+            umma_bf16_elect(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
+          umma_commit_elect(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        umma_commit_elect(&tfull_bar[acc]);      // accumulator complete -> epilogue
       }
     }
   } else if (warp == 6) {
