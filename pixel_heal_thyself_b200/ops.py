@@ -101,14 +101,13 @@ class WgradBucket:
     ``wgrad()`` launches only the split GEMM (``pht_wgrad_partial``) into this bucket's private workspace;
     ``unpack()`` queues a packed -> OIHW scatter; ``flush()`` then finishes every pending reduction in ONE launch
     (``pht_wgrad_reduce_batched``) and every scatter in one more (``pht_unpack_wgrads_batched``).  The descriptor
-    tables are cached on the device and only re-uploaded when a pointer or shape changes (the first step)."""
+    tables are cached on the device by content and only uploaded the first time a job list is seen."""
 
     def __init__(self, device, workspace_bytes=320 << 20):
         self.ws = torch.empty(workspace_bytes // 4, dtype=torch.float32, device=device)
         self.cursor = 0
         self.jobs, self.unpacks = [], []
-        self._rsig = self._usig = None
-        self._rarr = self._uarr = self._rtab = self._utab = None
+        self._tables = {}
 
     def wgrad(self, dy, srcs, dw, *, ksize=1, dbias=None, src_offsets=None):
         L.require_cuda(dy, *srcs, dw)
@@ -132,29 +131,34 @@ class WgradBucket:
         assert w_grad.is_contiguous() and w_grad.dtype == torch.float32 and packed.dtype == torch.float32
         self.unpacks.append(_pack_args(w_grad, packed, **kw))
 
-    @staticmethod
-    def _table(items, ctype, sig_old, arr_old, tab_old, device, key, nbytes):
-        sig = tuple(key(x) for x in items)
-        if sig == sig_old:
-            return sig, arr_old, tab_old, 0
+    def _table(self, kind, items, ctype, key, nbytes):
+        """Descriptor table of this exact job list on the device: (host array, device table, upload?).  A step flushes
+        several different buckets (and the gradient arenas alternate between steps), so tables are cached by content."""
+        sig = (kind,) + tuple(key(x) for x in items)
+        hit = self._tables.get(sig)
+        if hit is not None:
+            return hit[0], hit[1], 0
+        if len(self._tables) > 256:
+            self._tables.clear()
         arr = (ctype * len(items))(*items)
-        tab = torch.empty(nbytes + 64, dtype=torch.uint8, device=device)
-        return sig, arr, tab, 1
+        tab = torch.empty(nbytes + 64, dtype=torch.uint8, device=self.ws.device)
+        self._tables[sig] = (arr, tab)
+        return arr, tab, 1
 
     def flush(self):
         if self.jobs:
-            self._rsig, self._rarr, self._rtab, up = self._table(
-                self.jobs, L.WgradReduceJob, self._rsig, self._rarr, self._rtab, self.ws.device,
+            arr, tab, up = self._table(
+                "r", self.jobs, L.WgradReduceJob,
                 lambda j: (j.partials, j.dw, j.bias_partials, j.dbias, j.elems, j.splits, j.bias_rows, j.N),
                 C.sizeof(L.WgradReduceJob) * len(self.jobs))
-            L.check(lib.pht_wgrad_reduce_batched(self._rarr, len(self.jobs), self._rtab.data_ptr(), self._rtab.numel(), up,
+            L.check(lib.pht_wgrad_reduce_batched(arr, len(self.jobs), tab.data_ptr(), tab.numel(), up,
                                                  L.stream_ptr()), "pht_wgrad_reduce_batched")
         if self.unpacks:
-            self._usig, self._uarr, self._utab, up = self._table(
-                self.unpacks, L.PackArgs, self._usig, self._uarr, self._utab, self.ws.device,
+            arr, tab, up = self._table(
+                "u", self.unpacks, L.PackArgs,
                 lambda a: (a.w, a.packed, a.O, a.I, a.ksize, a.Ntot, a.Ktot, a.n_off, a.k_off, a.transpose, a.grid,
                            a.i_begin, a.i_count, a.scale), int(lib.pht_pack_table_bytes(len(self.unpacks))))
-            L.check(lib.pht_unpack_wgrads_batched(self._uarr, len(self.unpacks), self._utab.data_ptr(), self._utab.numel(),
+            L.check(lib.pht_unpack_wgrads_batched(arr, len(self.unpacks), tab.data_ptr(), tab.numel(),
                                                   up, L.stream_ptr()), "pht_unpack_wgrads_batched")
         self.jobs, self.unpacks, self.cursor = [], [], 0
 
