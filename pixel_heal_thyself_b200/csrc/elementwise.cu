@@ -693,14 +693,9 @@ __global__ void tail_finish_kernel(const float* __restrict__ y, int ldy, const f
     out[i] = y[(((long long)b * H + py) * W + px) * ldy + co] + bias[co] + x[i];
   }
 }
-// a[p][t*3+co] = dout[p - tap_t][co] (zero outside the image), columns 27..63 zero; dbias[co] = sum_p dout[p][co]
-__global__ void tail_im2col_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ a, float* __restrict__ dbias, int B,
-                                       int H, int W) {
-  __shared__ float sb[3];
-  if (threadIdx.x < 3) sb[threadIdx.x] = 0.f;
-  __syncthreads();
+// a[p][t*3+co] = dout[p - tap_t][co] (zero outside the image), columns 27..63 zero (the bias gradient is tail_dbias_kernel)
+__global__ void tail_im2col_bwd_kernel(const float* __restrict__ dout, bf16* __restrict__ a, int B, int H, int W) {
   const long long npx = (long long)B * H * W;
-  float acc[3] = {0.f, 0.f, 0.f};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npx * 8; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i & 7);          // 8-column group of the 64-wide row
     const long long p = i >> 3;
@@ -718,18 +713,26 @@ __global__ void tail_im2col_bwd_kernel(const float* __restrict__ dout, bf16* __r
         if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) v[j] = dout[(((long long)b * 3 + co) * H + yy) * W + xx];
       }
     }
-    if (g == 1) {  // columns 12..14 are the centre tap (t = 4): dout[p][0..2]
-      acc[0] += v[4]; acc[1] += v[5]; acc[2] += v[6];
-    }
     Vec<bf16>::st(a + p * 64 + g * 8, v);
   }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float s = warp_sum(acc[c]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&sb[c], s);
+}
+// dbias[co] = sum over the batch of dout[b][co][:, :]; one block per channel, fixed summation order (deterministic)
+__global__ void __launch_bounds__(1024) tail_dbias_kernel(const float* __restrict__ dout, float* __restrict__ dbias, int B, int HW) {
+  const int co = blockIdx.x;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* src = dout + ((long long)b * 3 + co) * HW;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) s += src[i];
   }
+  __shared__ float ws[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x < 3) atomicAdd(dbias + threadIdx.x, sb[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += ws[w];
+    dbias[co] = t;
+  }
 }
 
 template <typename S, typename D>
@@ -1060,10 +1063,10 @@ int pht_tail_finish(const float* y, int32_t ldy, const float* bias, const float*
 int pht_tail_im2col_bwd(const float* dout_nchw, void* a_bf16, float* dbias, int32_t B, int32_t H, int32_t W, void* stream) {
   PHT_CHECK_ARG(dout_nchw && a_bf16 && dbias, "tail_im2col_bwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  PHT_CUDA(cudaMemsetAsync(dbias, 0, 3 * sizeof(float), st));
   long long n = (long long)B * H * W * 8;
-  tail_im2col_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dout_nchw, (bf16*)a_bf16, dbias, B, H, W);
-  count_launch(CNT_OTHER);
+  tail_im2col_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dout_nchw, (bf16*)a_bf16, B, H, W);
+  tail_dbias_kernel<<<3, 1024, 0, st>>>(dout_nchw, dbias, B, H * W);
+  count_launch(CNT_OTHER, 2);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }

@@ -226,3 +226,34 @@ def test_trainer_gan_step_runs_and_learns():
     tr2.setup(g_only=True)
     losses = [float(tr2.train_step(noisy, gt, aux)[0]) for _ in range(6)]
     assert losses[-1] < losses[0]
+
+
+def test_launch_options_are_bitwise_neutral():
+    """Programmatic dependent launch, the serpentine tile order and the strip tiles of the fused pad-fold
+    data-gradient only change WHEN and WHERE a tile is computed, never its arithmetic: output, loss and every
+    gradient must be bit-identical with the options on and off (bf16 production path, 2 blocks, 64x64)."""
+    from pixel_heal_thyself_b200 import _lib
+    from pixel_heal_thyself_b200.models.losses import L1ReconstructionLoss
+    torch.manual_seed(7)
+    x = (torch.randn(2, 3, 64, 64) * 0.5).to(DEV)
+    aux = torch.rand(2, 7, 64, 64).to(DEV)
+    gt = (torch.randn(2, 3, 64, 64) * 0.5).to(DEV)
+    results = []
+    try:
+        for on in (1, 0, 1):
+            for name in (b"pdl", b"serpentine", b"strips"):
+                assert _lib.lib.pht_set_option(name, on) == 0
+            net = make_net("replicate", "bf16", num_sa=2)
+            out = net(x, aux)
+            loss = L1ReconstructionLoss()(out, gt)
+            loss.backward()
+            torch.cuda.synchronize()
+            results.append((out.detach().clone(), float(loss), [p.grad.detach().clone() for p in net.parameters()]))
+    finally:
+        for name in (b"pdl", b"serpentine", b"strips"):
+            _lib.lib.pht_set_option(name, 1)
+    for other in results[1:]:
+        assert torch.equal(results[0][0], other[0])
+        assert results[0][1] == other[1]
+        for a, b in zip(results[0][2], other[2]):
+            assert torch.equal(a, b)
