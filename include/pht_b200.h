@@ -145,6 +145,17 @@ int pht_wgrad_reduce_batched(const pht_wgrad_reduce_job* jobs, int32_t n, void* 
  * 690-706; mode chosen at base_trainer.py:334). */
 int pht_border_fill(void* buf, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode, void* stream);
 
+/* FiLM modulation of the AFGSA layer's FiLM variant (use_film=True): replaces FiLM.forward's
+ * `gamma, beta = torch.chunk(gamma_beta, 2, dim=1); return gamma * x + beta` (pht/models/afgsa/film.py:36-45, spatial
+ * gamma/beta as built by AFGSA, model.py:443-449) and its autograd.  gb holds [gamma | beta] (2C channels), x / out C
+ * channels, all views of one dtype.
+ *   fwd: out = gb[..., :C] * x + gb[..., C:]
+ *   bwd: dgb[..., :C] = dout * x, dgb[..., C:] = dout, and (dx non-null) dx = (dx_in ? dx_in : 0) + gb[..., :C] * dout
+ *        (dx may alias dx_in). */
+int pht_film_fwd(const pht_view* gb, const pht_view* x, const pht_view* out, int32_t B, int32_t C, void* stream);
+int pht_film_bwd(const pht_view* gb, const pht_view* x, const pht_view* dout, const pht_view* dgb, const pht_view* dx_in,
+                 const pht_view* dx, int32_t B, int32_t C, void* stream);
+
 /* Backward of the padding: fold the border of a padded-domain gradient
  * gpad[B][H+2][W+2][C] into the interior, then
  *   out1 = fold(gpad) (+ resid)          (if out1.ptr)

@@ -94,13 +94,26 @@ def attention_core(q, k, v, rel_h, rel_w, block=8, halo=3, heads=4):
     return out.reshape(B, C, H, W)
 
 
+def film(x, cond, sd, prefix):
+    """FiLM.forward with use_spatial=True (the only way AFGSA builds it, model.py:443-449), film.py:36-45:
+    gamma, beta = chunk(conv1x1(relu(conv1x1(cond))), 2, dim=1);  x' = gamma * x + beta."""
+    h = conv_block(cond, sd[prefix + "affine.0.weight"], sd[prefix + "affine.0.bias"], "relu")
+    gb = conv_block(h, sd[prefix + "affine.2.weight"], sd[prefix + "affine.2.bias"], None)
+    gamma, beta = torch.chunk(gb, 2, dim=1)
+    return gamma * x + beta
+
+
 def afgsa(noisy, aux, sd, prefix, block=8, halo=3, heads=4):
-    """AFGSA.forward (non-FiLM), pht/models/afgsa/model.py:456-516."""
+    """AFGSA.forward, pht/models/afgsa/model.py:456-516 (conv_map variant, or the FiLM variant :458-460 when the
+    state dict holds ``film.affine.*`` -- ``alpha`` is registered by the reference but unused in its forward)."""
     B, C, H, W = noisy.shape
     assert H % block == 0 and W % block == 0  # model.py:469-471
     d = C // heads
-    n_aux = conv_block(torch.cat([noisy, aux], 1), sd[prefix + "conv_map.0.weight"],
-                       sd[prefix + "conv_map.0.bias"], "relu")
+    if prefix + "film.affine.0.weight" in sd:
+        n_aux = film(noisy, aux, sd, prefix + "film.")
+    else:
+        n_aux = conv_block(torch.cat([noisy, aux], 1), sd[prefix + "conv_map.0.weight"],
+                           sd[prefix + "conv_map.0.bias"], "relu")
     q = F.conv2d(n_aux, sd[prefix + "q_conv.weight"]) * d ** -0.5
     k = F.conv2d(n_aux, sd[prefix + "k_conv.weight"])
     v = F.conv2d(noisy, sd[prefix + "v_conv.weight"])
@@ -164,4 +177,5 @@ def g_only_train_step(x, aux, gt, sd, padding_mode="replicate", num_sa=5):
     out = afgsa_net_forward(x, aux, params, padding_mode, num_sa=num_sa)
     loss = l1_loss(out, gt)
     loss.backward()
-    return out.detach(), loss.detach(), {k: p.grad for k, p in params.items()}
+    # (parameters the forward never touches, i.e. FiLM's ``alpha``, have no gradient: reported as zeros)
+    return out.detach(), loss.detach(), {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}

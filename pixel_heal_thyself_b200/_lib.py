@@ -75,6 +75,9 @@ SYMBOLS = {
     "pht_wgrad_workspace_bytes": (_sz, [C.POINTER(WgradArgs)]),
     "pht_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
     "pht_border_fill": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "pht_film_fwd": (C.c_int, [C.POINTER(PhtView), C.POINTER(PhtView), C.POINTER(PhtView), _i32, _i32, _vp]),
+    "pht_film_bwd": (C.c_int, [C.POINTER(PhtView), C.POINTER(PhtView), C.POINTER(PhtView), C.POINTER(PhtView), C.POINTER(PhtView),
+                               C.POINTER(PhtView), _i32, _i32, _vp]),
     "pht_pad_fold": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _PV, _PV, _vp, _PV, _PV, _vp]),
     "pht_im2col5": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "pht_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _vp]),

@@ -753,11 +753,108 @@ static int grid_for(long long work_items, int threads) {
   return (int)blocks;
 }
 
+// ---------------------------------------------------------------------------------------------
+// FiLM modulation (reference: pht/models/afgsa/film.py:36-45, spatial gamma / beta):
+//   forward   out = gb[..., :C] * x + gb[..., C:]
+//   backward  dgb[..., :C] = dout * x,  dgb[..., C:] = dout,  dx = dx_in + gb[..., :C] * dout
+// one thread per (pixel, vector of channels); HBM-bound
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void film_fwd_kernel(View gb, View x, View out, int B, int H, int W, int C) {
+  constexpr int V = Vec<T>::N;
+  const int cv = C / V;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * V;
+    long long p = i / cv;
+    const int px = (int)(p % W);
+    p /= W;
+    const int py = (int)(p % H), b = (int)(p / H);
+    float g[V], be[V], xv[V], o[V];
+    Vec<T>::ld((const T*)gb.ptr + view_off(gb, b, py + gb.oy, px + gb.ox) + c, g);
+    Vec<T>::ld((const T*)gb.ptr + view_off(gb, b, py + gb.oy, px + gb.ox) + C + c, be);
+    Vec<T>::ld((const T*)x.ptr + view_off(x, b, py + x.oy, px + x.ox) + c, xv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) o[j] = fmaf(g[j], xv[j], be[j]);
+    Vec<T>::st((T*)out.ptr + view_off(out, b, py + out.oy, px + out.ox) + c, o);
+  }
+}
+template <typename T>
+__global__ void film_bwd_kernel(View gb, View x, View dout, View dgb, View dx_in, View dx, int B, int H, int W, int C) {
+  constexpr int V = Vec<T>::N;
+  const int cv = C / V;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * V;
+    long long p = i / cv;
+    const int px = (int)(p % W);
+    p /= W;
+    const int py = (int)(p % H), b = (int)(p / H);
+    float g[V], xv[V], d[V], t[V];
+    Vec<T>::ld((const T*)gb.ptr + view_off(gb, b, py + gb.oy, px + gb.ox) + c, g);
+    Vec<T>::ld((const T*)x.ptr + view_off(x, b, py + x.oy, px + x.ox) + c, xv);
+    Vec<T>::ld((const T*)dout.ptr + view_off(dout, b, py + dout.oy, px + dout.ox) + c, d);
+#pragma unroll
+    for (int j = 0; j < V; ++j) t[j] = d[j] * xv[j];
+    T* dg = (T*)dgb.ptr + view_off(dgb, b, py + dgb.oy, px + dgb.ox);
+    Vec<T>::st(dg + c, t);
+    Vec<T>::st(dg + C + c, d);
+    if (dx.ptr) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) t[j] = 0.f;
+      if (dx_in.ptr) Vec<T>::ld((const T*)dx_in.ptr + view_off(dx_in, b, py + dx_in.oy, px + dx_in.ox) + c, t);
+#pragma unroll
+      for (int j = 0; j < V; ++j) t[j] = fmaf(g[j], d[j], t[j]);
+      Vec<T>::st((T*)dx.ptr + view_off(dx, b, py + dx.oy, px + dx.ox) + c, t);
+    }
+  }
+}
+
 }  // namespace pht
 
 using namespace pht;
 
 extern "C" {
+
+static bool film_view_ok(const pht_view* v, int dtype, int C, int vec) {
+  return v && v->ptr && v->dtype == dtype && v->C >= C && v->sx % vec == 0 && v->sy % vec == 0 && v->sb % vec == 0 &&
+         ((uintptr_t)v->ptr & 15) == 0;
+}
+int pht_film_fwd(const pht_view* gb, const pht_view* x, const pht_view* out, int32_t B, int32_t C, void* stream) {
+  PHT_CHECK_ARG(gb && x && out && B > 0 && C > 0, "film_fwd: bad args");
+  const int dt = x->dtype, vec = dt == PHT_F32 ? 4 : 8;
+  PHT_CHECK_ARG(C % vec == 0 && film_view_ok(gb, dt, 2 * C, vec) && film_view_ok(x, dt, C, vec) && film_view_ok(out, dt, C, vec),
+                "film_fwd: views must share the dtype, be 16-byte aligned and hold 2C / C / C channels");
+  const int H = x->H, W = x->W;
+  const long long items = (long long)B * H * W * (C / vec);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == PHT_F32) film_fwd_kernel<float><<<grid_for(items, 256), 256, 0, st>>>(make_view(gb), make_view(x), make_view(out), B, H, W, C);
+  else film_fwd_kernel<bf16><<<grid_for(items, 256), 256, 0, st>>>(make_view(gb), make_view(x), make_view(out), B, H, W, C);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+int pht_film_bwd(const pht_view* gb, const pht_view* x, const pht_view* dout, const pht_view* dgb, const pht_view* dx_in,
+                 const pht_view* dx, int32_t B, int32_t C, void* stream) {
+  PHT_CHECK_ARG(gb && x && dout && dgb && B > 0 && C > 0, "film_bwd: bad args");
+  const int dt = x->dtype, vec = dt == PHT_F32 ? 4 : 8;
+  PHT_CHECK_ARG(C % vec == 0 && film_view_ok(gb, dt, 2 * C, vec) && film_view_ok(x, dt, C, vec) && film_view_ok(dout, dt, C, vec) &&
+                    film_view_ok(dgb, dt, 2 * C, vec), "film_bwd: bad views");
+  PHT_CHECK_ARG(!(dx && dx->ptr) || film_view_ok(dx, dt, C, vec), "film_bwd: bad dx view");
+  PHT_CHECK_ARG(!(dx_in && dx_in->ptr) || film_view_ok(dx_in, dt, C, vec), "film_bwd: bad dx_in view");
+  const int H = x->H, W = x->W;
+  const long long items = (long long)B * H * W * (C / vec);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == PHT_F32)
+    film_bwd_kernel<float><<<grid_for(items, 256), 256, 0, st>>>(make_view(gb), make_view(x), make_view(dout), make_view(dgb),
+                                                                 make_view(dx_in), make_view(dx), B, H, W, C);
+  else
+    film_bwd_kernel<bf16><<<grid_for(items, 256), 256, 0, st>>>(make_view(gb), make_view(x), make_view(dout), make_view(dgb),
+                                                                make_view(dx_in), make_view(dx), B, H, W, C);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
 
 int pht_border_fill(void* buf, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode, void* stream) {
   PHT_CHECK_ARG(buf && B > 0 && H > 0 && W > 0, "border_fill: bad args");

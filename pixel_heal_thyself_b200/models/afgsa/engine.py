@@ -139,9 +139,17 @@ class AfgsaEngine:
                 pw(P[f"{nm}.0.weight"], self._pk(nm + ".T", (1, I, C)), ksize=1, Ntot=I, Ktot=C, transpose=1)
         for i in range(self.num_sa):
             pre = f"transformer_blocks.{i}."
-            wmap, wq, wk, wv = (P[pre + "attention.conv_map.0.weight"], P[pre + "attention.q_conv.weight"],
-                                P[pre + "attention.k_conv.weight"], P[pre + "attention.v_conv.weight"])
-            pw(wmap, self._pk(f"b{i}.map", (1, C, 2 * C)), ksize=1, Ntot=C, Ktot=2 * C)
+            film = getattr(net, "use_film", False)
+            wq, wk, wv = (P[pre + "attention.q_conv.weight"], P[pre + "attention.k_conv.weight"],
+                          P[pre + "attention.v_conv.weight"])
+            if film:   # FiLM variant: gamma_beta = W2 relu(W0 a + b0) + b2 (film.py:28-38)
+                w0, w2 = P[pre + "attention.film.affine.0.weight"], P[pre + "attention.film.affine.2.weight"]
+                FH = w0.shape[0]
+                pw(w0, self._pk(f"b{i}.film0", (1, FH, C)), ksize=1, Ntot=FH, Ktot=C)
+                pw(w2, self._pk(f"b{i}.film2", (1, 2 * C, FH)), ksize=1, Ntot=2 * C, Ktot=FH)
+            else:
+                wmap = P[pre + "attention.conv_map.0.weight"]
+                pw(wmap, self._pk(f"b{i}.map", (1, C, 2 * C)), ksize=1, Ntot=C, Ktot=2 * C)
             wqk = self._pk(f"b{i}.qk", (1, 2 * C, C))
             pw(wq, wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=0, scale=self.scale)
             pw(wk, wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=C)
@@ -155,10 +163,15 @@ class AfgsaEngine:
                 wqkT = self._pk(f"b{i}.qk.T", (1, C, 2 * C))       # dM = [dQ | dK] @ [s*Wq ; Wk]
                 pw(wq, wqkT, ksize=1, Ntot=C, Ktot=2 * C, k_off=0, transpose=1, scale=self.scale)
                 pw(wk, wqkT, ksize=1, Ntot=C, Ktot=2 * C, k_off=C, transpose=1)
-                wx = self._pk(f"b{i}.x.T", (1, C, 2 * C))          # dX = [dV | dMpre] @ [Wv ; Wmap[:, :C]]
-                pw(wv, wx, ksize=1, Ntot=C, Ktot=2 * C, k_off=0, transpose=1)
-                pw(wmap, wx, ksize=1, Ntot=C, Ktot=2 * C, k_off=C, transpose=1, i_begin=0, i_count=C)
-                pw(wmap, self._pk(f"b{i}.a.T", (1, C, C)), ksize=1, Ntot=C, Ktot=C, transpose=1, i_begin=C, i_count=C)
+                if film:
+                    pw(wv, self._pk(f"b{i}.v.T", (1, C, C)), ksize=1, Ntot=C, Ktot=C, transpose=1)          # dX += dV @ Wv
+                    pw(w2, self._pk(f"b{i}.film2.T", (1, FH, 2 * C)), ksize=1, Ntot=FH, Ktot=2 * C, transpose=1)
+                    pw(w0, self._pk(f"b{i}.a.T", (1, C, FH)), ksize=1, Ntot=C, Ktot=FH, transpose=1)        # dA += dH @ W0
+                else:
+                    wx = self._pk(f"b{i}.x.T", (1, C, 2 * C))          # dX = [dV | dMpre] @ [Wv ; Wmap[:, :C]]
+                    pw(wv, wx, ksize=1, Ntot=C, Ktot=2 * C, k_off=0, transpose=1)
+                    pw(wmap, wx, ksize=1, Ntot=C, Ktot=2 * C, k_off=C, transpose=1, i_begin=0, i_count=C)
+                    pw(wmap, self._pk(f"b{i}.a.T", (1, C, C)), ksize=1, Ntot=C, Ktot=C, transpose=1, i_begin=C, i_count=C)
         for j in (0, 1):
             w = P[f"decoder.{j}.0.weight"]
             pw(w, self._pk(f"dec{j}", (9, C, C)), ksize=3, Ntot=C, Ktot=C)
@@ -231,7 +244,17 @@ class AfgsaEngine:
             lse = g(f"lse{j}", (B, H, W, self.heads), torch.float32)
             Xn = g(f"Xp{(i + 1) if save else (i + 1) % 2}", (B, H + 2, W + 2, C), T)
             X1 = X1p[:, 1:-1, 1:-1, :]
-            ops.conv_gemm([X, Af], pk[f"b{i}.map"], C, bias=P[pre + "attention.conv_map.0.bias"], slope=relu, out1=M)
+            if net.use_film:
+                # n_aux = gamma * x + beta with [gamma | beta] = W2 relu(W0 a + b0) + b2 (film.py:36-45, model.py:458-460)
+                FH = pk[f"b{i}.film0"].shape[1]
+                Fh = g(f"Fh{j}", (B, H, W, FH), T)
+                GB = g(f"GB{j}", (B, H, W, 2 * C), T)
+                ops.conv_gemm([Af], pk[f"b{i}.film0"], FH, bias=P[pre + "attention.film.affine.0.bias"],
+                              slope=self._const("reluF", [0.0] * FH), out1=Fh)
+                ops.conv_gemm([Fh], pk[f"b{i}.film2"], 2 * C, bias=P[pre + "attention.film.affine.2.bias"], out1=GB)
+                ops.film_fwd(GB, X, M)
+            else:
+                ops.conv_gemm([X, Af], pk[f"b{i}.map"], C, bias=P[pre + "attention.conv_map.0.bias"], slope=relu, out1=M)
             ops.conv_gemm([M], pk[f"b{i}.qk"], 2 * C, out1=QK)
             ops.conv_gemm([X], pk[f"b{i}.v"], C, out1=V)
             ops.attn_fwd(QK[..., :C], QK[..., C:], V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], X1,
@@ -408,21 +431,44 @@ class AfgsaEngine:
             unpack(G[pre + "attention.q_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=0, scale=self.scale)
             unpack(G[pre + "attention.k_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=C)
             wgrad(dV, [X], G[pre + "attention.v_conv.weight"])
-            ops.conv_gemm([dQK], pk[f"b{i}.qk.T"], C, mask=M, mslope=relu0, out2=G1)       # G1 = d(M pre-act)
-            wgrad(G1, [X, Af], G[pre + "attention.conv_map.0.weight"], dbias=G[pre + "attention.conv_map.0.bias"])
-            ready(f"block{i}")
-            # d(block input) = dX1 + dV Wv + dMpre Wmap[:, :C]; also emit the next layer's masked gradient
-            if i > 0:
-                ops.conv_gemm([dV, G1], pk[f"b{i}.x.T"], C, resid=G2, resid_mode="pre",
-                              mask=g(f"H2{i - 1}", (B, H, W, C), T), mslope=relu0, out1=GX, out2=G0)
-            else:
-                ops.conv_gemm([dV, G1], pk[f"b{i}.x.T"], C, resid=G2, resid_mode="pre", mask=X, mslope=relu0, out2=G0)
-            # dA accumulates over blocks; the last accumulation applies LeakyReLU' of conv_aenc2
             first = i == self.num_sa - 1
-            if i > 0:
-                ops.conv_gemm([G1], pk[f"b{i}.a.T"], C, resid=None if first else GA, resid_mode="pre", out1=GA)
+            if net.use_film:
+                FH = pk[f"b{i}.film0"].shape[1]
+                Fh, GB = g(f"Fh{i}", (B, H, W, FH), T), g(f"GB{i}", (B, H, W, 2 * C), T)
+                dGB = g("dGB", (B, H, W, 2 * C), T)
+                dFh = g("dFh", (B, H, W, FH), T)
+                reluF = self._const("reluF", [0.0] * FH)
+                ops.conv_gemm([dQK], pk[f"b{i}.qk.T"], C, out1=G1)                         # G1 = dM (no activation on M)
+                # dGB = [dM * x | dM];  G2 = dX1 + gamma * dM
+                ops.film_bwd(GB, X, G1, dGB, dx_in=G2, dx=G2)
+                wgrad(dGB, [Fh], G[pre + "attention.film.affine.2.weight"], dbias=G[pre + "attention.film.affine.2.bias"])
+                ops.conv_gemm([dGB], pk[f"b{i}.film2.T"], FH, mask=Fh, mslope=reluF, out2=dFh)   # d(hidden pre-act)
+                wgrad(dFh, [Af], G[pre + "attention.film.affine.0.weight"], dbias=G[pre + "attention.film.affine.0.bias"])
+                G[pre + "attention.alpha"].zero_()      # registered by the reference, unused by its forward
+                ready(f"block{i}")
+                # d(block input) = (dX1 + gamma dM) + dV Wv; also emit the next layer's masked gradient
+                if i > 0:
+                    ops.conv_gemm([dV], pk[f"b{i}.v.T"], C, resid=G2, resid_mode="pre",
+                                  mask=g(f"H2{i - 1}", (B, H, W, C), T), mslope=relu0, out1=GX, out2=G0)
+                else:
+                    ops.conv_gemm([dV], pk[f"b{i}.v.T"], C, resid=G2, resid_mode="pre", mask=X, mslope=relu0, out2=G0)
+                dA_src = dFh
             else:
-                ops.conv_gemm([G1], pk[f"b{i}.a.T"], C, resid=None if first else GA, resid_mode="pre",
+                ops.conv_gemm([dQK], pk[f"b{i}.qk.T"], C, mask=M, mslope=relu0, out2=G1)       # G1 = d(M pre-act)
+                wgrad(G1, [X, Af], G[pre + "attention.conv_map.0.weight"], dbias=G[pre + "attention.conv_map.0.bias"])
+                ready(f"block{i}")
+                # d(block input) = dX1 + dV Wv + dMpre Wmap[:, :C]; also emit the next layer's masked gradient
+                if i > 0:
+                    ops.conv_gemm([dV, G1], pk[f"b{i}.x.T"], C, resid=G2, resid_mode="pre",
+                                  mask=g(f"H2{i - 1}", (B, H, W, C), T), mslope=relu0, out1=GX, out2=G0)
+                else:
+                    ops.conv_gemm([dV, G1], pk[f"b{i}.x.T"], C, resid=G2, resid_mode="pre", mask=X, mslope=relu0, out2=G0)
+                dA_src = G1
+            # dA accumulates over blocks; the last accumulation applies LeakyReLU' of conv_aenc2
+            if i > 0:
+                ops.conv_gemm([dA_src], pk[f"b{i}.a.T"], C, resid=None if first else GA, resid_mode="pre", out1=GA)
+            else:
+                ops.conv_gemm([dA_src], pk[f"b{i}.a.T"], C, resid=None if first else GA, resid_mode="pre",
                               mask=Af, mslope=leaky, out2=G2)                              # G2 = d(A pre-act)
 
         # ---- noisy encoder: G0 = d(conv_map pre-act) -----------------------------------------------

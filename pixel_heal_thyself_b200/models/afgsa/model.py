@@ -78,10 +78,18 @@ def _conv(cin, cout, k, act, padding_mode="zeros"):
     return nn.Sequential(*mods)
 
 
+class _FiLMParams(nn.Module):
+    """Parameters of FiLM (reference: film.py:20-34): affine = Conv1x1(cond_ch, hidden) - ReLU - Conv1x1(hidden, 2 C)."""
+
+    def __init__(self, ch, cond_ch, hidden=128):
+        super().__init__()
+        self.affine = nn.Sequential(nn.Conv2d(cond_ch, hidden, 1), nn.ReLU(True), nn.Conv2d(hidden, 2 * ch, 1))
+
+
 class _AttentionParams(nn.Module):
     """Parameters of one AFGSA layer (reference: model.py:401-454, 518-524)."""
 
-    def __init__(self, ch, block_size, halo_size, num_heads, curve_order):
+    def __init__(self, ch, block_size, halo_size, num_heads, curve_order, use_film=False):
         super().__init__()
         assert ch % num_heads == 0, "ch should be divided by # heads"
         head_ch = ch // num_heads
@@ -90,7 +98,12 @@ class _AttentionParams(nn.Module):
         self.register_buffer("inv_curve_indices", torch.argsort(self.curve_indices))
         self.rel_h = nn.Parameter(torch.randn(1, win, 1, head_ch // 2))
         self.rel_w = nn.Parameter(torch.randn(1, 1, win, head_ch // 2))
-        self.conv_map = _conv(ch * 2, ch, 1, "relu")
+        self.use_film = use_film
+        if use_film:   # model.py:443-449 (alpha is registered by the reference but not used by its forward)
+            self.alpha = nn.Parameter(torch.zeros(1))
+            self.film = _FiLMParams(ch, ch, hidden=128)
+        else:
+            self.conv_map = _conv(ch * 2, ch, 1, "relu")
         self.q_conv = nn.Conv2d(ch, ch, kernel_size=1, bias=False)
         self.k_conv = nn.Conv2d(ch, ch, kernel_size=1, bias=False)
         self.v_conv = nn.Conv2d(ch, ch, kernel_size=1, bias=False)
@@ -101,9 +114,9 @@ class _AttentionParams(nn.Module):
 
 
 class _BlockParams(nn.Module):
-    def __init__(self, ch, block_size, halo_size, num_heads, padding_mode, curve_order):
+    def __init__(self, ch, block_size, halo_size, num_heads, padding_mode, curve_order, use_film=False):
         super().__init__()
-        self.attention = _AttentionParams(ch, block_size, halo_size, num_heads, curve_order)
+        self.attention = _AttentionParams(ch, block_size, halo_size, num_heads, curve_order, use_film)
         self.feed_forward = nn.Sequential(_conv(ch, ch, 3, "relu", padding_mode), _conv(ch, ch, 3, "relu", padding_mode))
 
 
@@ -145,8 +158,7 @@ class AFGSANet(nn.Module):
                  compute_dtype: str | torch.dtype = "bf16") -> None:
         super().__init__()
         assert num_gcp <= num_sa
-        if use_film:
-            raise NotImplementedError("use_film=True (FiLM conditioning) is not built yet on the B200 path")
+        self.use_film = bool(use_film)
         if base_ch != 256 or base_ch // num_heads != 64:
             # the reference hard-codes 256-wide encoder branches (model.py:606-652); smaller widths are
             # supported by the fp32/CUDA-core kernels only
@@ -170,7 +182,7 @@ class AFGSANet(nn.Module):
         self.conv_aenc1 = _conv(256 * 3, base_ch, 1, "leakyrelu")
         self.conv_aenc2 = _conv(base_ch, base_ch, 1, "leakyrelu")
         self.transformer_blocks = nn.Sequential(*[
-            _BlockParams(base_ch, block_size, halo_size, num_heads, padding_mode, self.curve_order)
+            _BlockParams(base_ch, block_size, halo_size, num_heads, padding_mode, self.curve_order, self.use_film)
             for _ in range(num_sa)])
         self.decoder = nn.Sequential(_conv(base_ch, base_ch, 3, "relu", padding_mode),
                                      _conv(base_ch, base_ch, 3, "relu", padding_mode),

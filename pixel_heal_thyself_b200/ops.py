@@ -182,6 +182,24 @@ def pad_fold(gpad, mode, *, resid=None, mask=None, mslope=None, out1=None, out2=
                              L.ptr(mslope), refs[2], refs[3], L.stream_ptr()), "pht_pad_fold")
 
 
+def film_fwd(gb, x, out):
+    """FiLM modulation (film.py:36-45): out = gb[..., :C] * x + gb[..., C:]; gb [B,H,W,2C], x / out [B,H,W,C] views."""
+    L.require_cuda(gb, x, out)
+    vg, vx, vo = L.view(gb), L.view(x), L.view(out)
+    L.check(lib.pht_film_fwd(C.byref(vg), C.byref(vx), C.byref(vo), x.shape[0], x.shape[3], L.stream_ptr()), "pht_film_fwd")
+
+
+def film_bwd(gb, x, dout, dgb, dx_in=None, dx=None):
+    """dgb = [dout * x | dout]; dx = (dx_in or 0) + gamma * dout (dx may alias dx_in)."""
+    L.require_cuda(gb, x, dout, dgb)
+    vs = [L.view(t) for t in (gb, x, dout, dgb)]
+    vi = L.view(dx_in) if dx_in is not None else None
+    vd = L.view(dx) if dx is not None else None
+    L.check(lib.pht_film_bwd(C.byref(vs[0]), C.byref(vs[1]), C.byref(vs[2]), C.byref(vs[3]),
+                             C.byref(vi) if vi is not None else None, C.byref(vd) if vd is not None else None,
+                             x.shape[0], x.shape[3], L.stream_ptr()), "pht_film_bwd")
+
+
 def im2col5(x_nchw, col, mode):
     """x_nchw fp32 [B,Cin,H,W] -> col [B,H,W,Kpad] (dtype of col)."""
     L.require_cuda(x_nchw, col)

@@ -85,8 +85,10 @@ def test_generator_needs_cuda():
     net = AFGSANet(3, 7, 256, num_sa=1, num_gcp=0, padding_mode="replicate")
     with pytest.raises(RuntimeError, match="CUDA"):
         net(torch.zeros(1, 3, 8, 8), torch.zeros(1, 7, 8, 8))
-    with pytest.raises(NotImplementedError):
-        AFGSANet(3, 7, 256, num_gcp=0, use_film=True)
+    film = AFGSANet(3, 7, 256, num_sa=1, num_gcp=0, padding_mode="replicate", use_film=True)   # FiLM variant: same rule
+    assert "transformer_blocks.0.attention.film.affine.2.weight" in dict(film.named_parameters())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        film(torch.zeros(1, 3, 8, 8), torch.zeros(1, 7, 8, 8))
 
 
 def test_config_presets_and_overrides():

@@ -257,3 +257,36 @@ def test_launch_options_are_bitwise_neutral():
         assert results[0][1] == other[1]
         for a, b in zip(results[0][2], other[2]):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_film_variant_matches_reference_golden(dtype):
+    """use_film=True: the FiLM branch of the AFGSA layer (two 1x1 GEMMs + pht_film_fwd / pht_film_bwd) against the real
+    reference's output / loss / gradients (tests/golden/make_golden_film.py).  fp32 mode: 1e-5 output, flip-tolerant
+    gradients; bf16: the production tolerances."""
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    from pixel_heal_thyself_b200.models.losses import L1ReconstructionLoss
+    g = load_npz("net_film.npz")
+    gref = load_json("net_film_grads.json")
+    torch.manual_seed(990819)
+    net = AFGSANet(3, 7, 256, num_sa=2, num_gcp=0, padding_mode="replicate", use_film=True, compute_dtype=dtype).to(DEV)
+    x, aux, gt = (torch.from_numpy(g[k]).to(DEV) for k in ("x", "aux", "gt"))
+    out = net(x, aux)
+    ref = torch.from_numpy(g["out"]).to(DEV)
+    err = float((out - ref).abs().max() / ref.abs().max())
+    assert err < (1e-5 if dtype == "fp32" else 3e-2), err
+    loss = L1ReconstructionLoss()(out, gt)
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < (1e-5 if dtype == "fp32" else 2e-2)
+    loss.backward()
+    tol = FLIP_TOL if dtype == "fp32" else 8e-2
+    for name, p in net.named_parameters():
+        r = gref[name]
+        gr = p.grad.flatten()
+        if r["absmax"] == 0.0:                     # alpha: registered by the reference, unused by its forward
+            assert float(gr.abs().max()) == 0.0, name
+            continue
+        e = abs(float(gr.double().abs().sum()) - r["abssum"]) / (r["abssum"] + 1e-30)
+        if dtype == "fp32":
+            probe = torch.tensor([float(gr[i]) for i in r["probe_idx"]])
+            e = max(e, float((probe - torch.tensor(r["probe"])).abs().max() / (r["absmax"] + 1e-30)))
+        assert e < tol, (name, e)

@@ -125,3 +125,29 @@ def test_uniform_filter_restatement_matches_scipy():
     a = rs.standard_normal((37, 53, 3)).astype(np.float32)
     for size in (1, 2, 5, 8, 32):
         assert np.array_equal(S.uniform_filter_pp1(a, size), ndimage.uniform_filter(a, size=(size, size, 1))), size
+
+
+def test_film_variant_matches_reference_golden():
+    """use_film=True (AFGSA.forward's FiLM branch, model.py:458-460, film.py:36-45): parameter names / shapes / seeded
+    init of the product containers and the oracle's forward + gradients against the fixture generated from the real
+    reference (tests/golden/make_golden_film.py)."""
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    meta = load_json("net_film_meta.json")
+    g = load_npz("net_film.npz")
+    gref = load_json("net_film_grads.json")
+    torch.manual_seed(990819)
+    net = AFGSANet(3, 7, 256, num_sa=2, num_gcp=0, padding_mode="replicate", use_film=True)
+    assert [k for k, _ in net.named_parameters()] == meta["param_order"]
+    for k, p in net.named_parameters():
+        assert list(p.shape) == meta["param_shapes"][k]
+        assert abs(float(p.detach().double().sum()) - meta["param_checksums"][k][0]) <= 1e-6 * max(1.0, abs(meta["param_checksums"][k][0]))
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x, aux, gt = (torch.from_numpy(g[k]) for k in ("x", "aux", "gt"))
+    out, loss, grads = O.g_only_train_step(x, aux, gt, sd, "replicate", num_sa=2)
+    assert float((out - torch.from_numpy(g["out"])).abs().max()) < 2e-6
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    for name, r in gref.items():
+        gr = grads[name].flatten()
+        probe = torch.tensor([float(gr[i]) for i in r["probe_idx"]])
+        assert float((probe - torch.tensor(r["probe"])).abs().max()) <= 1e-5 * (r["absmax"] + 1e-30) + 1e-12, name
+        assert abs(float(gr.double().abs().sum()) - r["abssum"]) <= 1e-5 * (r["abssum"] + 1e-30) + 1e-12, name
