@@ -335,6 +335,24 @@ int pht_importance_map(const float* noisy_f, const float* aux_f, int32_t n_img, 
 int pht_importance_sample(const int64_t* seeds, int32_t n_img, int32_t Hf, int32_t Wf, int32_t P, int32_t n,
                           int32_t max_iter, const float* imp, int32_t* out_centres, int32_t* out_counts, void* stream);
 
+/* ---- validation metrics (pht/models/base_trainer.py:549-571) ----
+ * pht_tonemap_u8: tensor2img (pht/models/afgsa/util.py:77-119): NCHW fp32 -> uint8 NHWC;
+ *   v = post_spec ? exp(x) - 1 (postprocess_specular, preprocessing.py:46-48) : x;
+ *   out = uint8(clip(clip(v ** (1/2.2), 0, 1) * 255, 0, 255)), NaN -> 0.
+ * pht_image_metrics_u8: per image of the batch, on uint8 NHWC pairs:
+ *   sqdiff[b] = sum (a - b)^2 (exact integer; calculate_psnr = 20 log10(255 / sqrt(sqdiff / (H W C))), metric.py:9-24);
+ *   ssim_sum[b] = sum of the SSIM map over the valid (H-10) x (W-10) x C region, 11x11 gaussian (sigma 1.5) window,
+ *   fp64 (metric.py:27-48; calculate_ssim = ssim_sum / ((H-10)(W-10)C), :51-73).
+ * pht_mrse: out_sum[b] = sum (a - b)^2 / (b^2 + 0.01) with a = a_is_log ? exp(a) - 1 : a (calculate_rmse = 0.5 * mean,
+ *   metric.py:76-94).  workspace: pht_image_metrics_ws_bytes(B) bytes, 8-byte aligned.  Deterministic reductions. */
+int pht_tonemap_u8(const float* x_nchw, uint8_t* out_nhwc, int32_t B, int32_t C, int32_t H, int32_t W, int32_t post_spec,
+                   void* stream);
+size_t pht_image_metrics_ws_bytes(int32_t B);
+int pht_image_metrics_u8(const uint8_t* a, const uint8_t* b, int32_t B, int32_t H, int32_t W, int32_t C, uint64_t* sqdiff,
+                         double* ssim_sum, void* workspace, size_t workspace_bytes, void* stream);
+int pht_mrse(const float* a, const float* b, int32_t B, int64_t n_per_image, int32_t a_is_log, double* out_sum, void* workspace,
+             size_t workspace_bytes, void* stream);
+
 /* Introspection */
 int pht_abi_version(void);
 const char* pht_last_error(void);

@@ -75,6 +75,10 @@ SYMBOLS = {
     "pht_wgrad_workspace_bytes": (_sz, [C.POINTER(WgradArgs)]),
     "pht_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
     "pht_border_fill": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "pht_tonemap_u8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "pht_image_metrics_ws_bytes": (C.c_size_t, [_i32]),
+    "pht_image_metrics_u8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "pht_mrse": (C.c_int, [_vp, _vp, _i32, C.c_int64, _i32, _vp, _vp, C.c_size_t, _vp]),
     "pht_film_fwd": (C.c_int, [C.POINTER(PhtView), C.POINTER(PhtView), C.POINTER(PhtView), _i32, _i32, _vp]),
     "pht_film_bwd": (C.c_int, [C.POINTER(PhtView), C.POINTER(PhtView), C.POINTER(PhtView), C.POINTER(PhtView), C.POINTER(PhtView),
                                C.POINTER(PhtView), _i32, _i32, _vp]),

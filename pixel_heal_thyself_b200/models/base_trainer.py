@@ -192,23 +192,33 @@ class BaseTrainer(ABC):
                 self._validate_and_save(epoch, ds, n_train, n_val, out_dir)
 
     def _validate_and_save(self, epoch, ds, n_train, n_val, out_dir) -> None:
-        """Checkpoint (same file names / state_dict keys as base_trainer.py:521-533) and a patch-level
-        validation pass (mean relative-MSE and PSNR on the log-domain output)."""
+        """Checkpoint (same file names / state_dict keys as base_trainer.py:521-533) and the validation pass of
+        base_trainer.py:535-595 on the GPU: tone-mapped uint8 images (tensor2img), MRSE on the linear radiance, PSNR and
+        SSIM on the images (``pixel_heal_thyself_b200.metrics``), and the reference's ``evaluation.txt`` line."""
+        from .. import metrics as M
         path = os.path.join(out_dir, f"model_epoch{epoch + 1}")
         os.makedirs(path, exist_ok=True)
         torch.save(self.G.state_dict(), os.path.join(path, "G.pt"))
         if self.D is not None:
             torch.save(self.D.state_dict(), os.path.join(path, "D.pt"))
         self.G.eval()
-        mse, cnt = 0.0, 0
+        avg_mrse = avg_psnr = avg_ssim = 0.0
+        cnt = 0
         with torch.no_grad():
             for k in range(n_train, n_train + n_val):
-                noisy, gt, aux = ds.batch_device(torch.tensor([k], device=self.device))
+                noisy, gt_log, aux = ds.batch_device(torch.tensor([k], device=self.device))
                 out = self.G(noisy, aux)
-                mse += float(((out - gt) ** 2).mean())
+                gt = torch.expm1(gt_log)                     # the reference validates against the un-preprocessed gt
+                avg_mrse += M.calculate_rmse(out, gt, output_is_log=True)                    # base_trainer.py:566
+                psnr, ssim = M.image_metrics(M.tensor2img(out, post_spec=True), M.tensor2img(gt))   # :567-568
+                avg_psnr += psnr
+                avg_ssim += ssim
                 cnt += 1
         self.G.train()
-        psnr = 10 * math.log10(1.0 / max(mse / max(cnt, 1), 1e-12))
-        logger.info(f"[Val] epoch={epoch + 1} summary: log-domain mse={mse / max(cnt, 1):.6f} psnr={psnr:.3f}")
-        with open(os.path.join(out_dir, "evaluation.txt"), "a") as f:
-            f.write(f"Validation: {epoch + 1} \tAvg MSE(log): {mse / max(cnt, 1):.6f} \tAvg PSNR(log): {psnr:.4f}\n")
+        cnt = max(cnt, 1)
+        avg_mrse, avg_psnr, avg_ssim = avg_mrse / cnt, avg_psnr / cnt, avg_ssim / cnt
+        logger.info(f"[Val] epoch={epoch + 1} summary: avg_mrse={avg_mrse:.4f} avg_psnr={avg_psnr:.4f} "
+                    f"avg_1-ssim={1 - avg_ssim:.4f}")
+        with open(os.path.join(out_dir, "evaluation.txt"), "a") as f:   # format: base_trainer.py:591-595
+            f.write(f"Validation: {epoch + 1} \tAvg MRSE: {avg_mrse:.4f} \tAvg PSNR: {avg_psnr:.4f} "
+                    f"\tAvg 1-SSIM: {1 - avg_ssim:.4f}\n")

@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import load_npz
+from conftest import load_json, load_npz
 from oracle import afgsa_oracle as O
 from oracle import sampler_oracle as S
 
@@ -485,3 +485,35 @@ def test_importance_map_cleans_nan_normals_and_negative_radiance():
     imp = ops.importance_map(torch.from_numpy(noisy[None]).to(DEV), torch.from_numpy(aux[None]).to(DEV), p)
     ref = S.importance_map(np.clip(np.nan_to_num(noisy), 0, None), np.nan_to_num(aux[..., :3]), p)
     assert float((imp[0].cpu() - torch.from_numpy(ref)).abs().max()) < 2e-6
+
+
+def test_validation_metrics_match_reference_golden():
+    """pht_tonemap_u8 / pht_image_metrics_u8 / pht_mrse against the real reference's tensor2img, calculate_psnr,
+    calculate_ssim, calculate_rmse (fixture: tests/golden/make_golden_metrics.py).  The uint8 images may differ by one
+    level where powf rounds differently next to a truncation boundary (a handful of pixels); the integer MSE and the fp64
+    SSIM are exact given the same images."""
+    from pixel_heal_thyself_b200 import metrics as M
+    from oracle import metrics_oracle as MO
+    g, r = load_npz("metrics.npz"), load_json("metrics.json")
+    out_log, gt, noisy_log = (torch.from_numpy(g[k]).to(DEV) for k in ("out_log", "gt", "noisy_log"))
+    imgs = {}
+    for name, t, spec in (("out_img", out_log, True), ("gt_img", gt, False), ("noisy_img", noisy_log, True)):
+        img = M.tensor2img(t, post_spec=spec)
+        d = (img.cpu().numpy().astype(int) - g[name].astype(int))
+        assert np.abs(d).max() <= 1 and (d != 0).mean() < 1e-3, (name, np.abs(d).max(), (d != 0).mean())
+        imgs[name] = img
+    # metrics on the REFERENCE's own uint8 images: exact integer MSE, fp64 SSIM
+    ref_out, ref_gt, ref_noisy = (torch.from_numpy(g[k]).to(DEV) for k in ("out_img", "gt_img", "noisy_img"))
+    psnr, ssim = M.image_metrics(ref_out, ref_gt)
+    assert abs(psnr - r["psnr_out"]) < 1e-9 and abs(ssim - r["ssim_out"]) < 1e-9
+    psnr_n, ssim_n = M.image_metrics(ref_noisy, ref_gt)
+    assert abs(psnr_n - r["psnr_noisy"]) < 1e-9 and abs(ssim_n - r["ssim_noisy"]) < 1e-9
+    # end to end (our tone mapping): within what a one-level flip of a few pixels can move
+    psnr2, ssim2 = M.image_metrics(imgs["out_img"], imgs["gt_img"])
+    assert abs(psnr2 - r["psnr_out"]) < 1e-2 and abs(ssim2 - r["ssim_out"]) < 1e-4
+    mrse = M.calculate_rmse(out_log, gt, output_is_log=True)
+    assert abs(mrse - r["mrse_out"]) < 1e-5 * r["mrse_out"]
+    assert abs(mrse - MO.rmse(np.exp(g["out_log"]) - 1, g["gt"])) < 1e-5 * r["mrse_out"]
+    assert M.image_metrics(ref_gt, ref_gt)[0] == 0.0          # mse == 0 -> 0.0 (metric.py:22-23)
+    with pytest.raises(ValueError):
+        M.image_metrics(ref_out, ref_gt[:, :-1])

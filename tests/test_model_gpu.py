@@ -290,3 +290,25 @@ def test_film_variant_matches_reference_golden(dtype):
             probe = torch.tensor([float(gr[i]) for i in r["probe_idx"]])
             e = max(e, float((probe - torch.tensor(r["probe"])).abs().max() / (r["absmax"] + 1e-30)))
         assert e < tol, (name, e)
+
+
+def test_validation_pass_writes_the_reference_evaluation_line(tmp_path):
+    """BaseTrainer._validate_and_save: checkpoint names (base_trainer.py:521-533) and the evaluation.txt line of
+    base_trainer.py:591-595 with MRSE / PSNR / 1-SSIM from the GPU metrics."""
+    import os
+    import re
+    from pixel_heal_thyself_b200.config import load_config
+    from pixel_heal_thyself_b200.models.afgsa.train import AFGSATrainer
+    cfg = load_config("ci", ["data.synthetic.num_images=1", "data.synthetic.height=128", "data.synthetic.width=128",
+                             "data.patches.num_patches=16"])
+    tr = AFGSATrainer(cfg)
+    tr.setup(g_only=True)
+    ds = tr.setup_data()
+    n = len(ds)
+    tr._validate_and_save(0, ds, n - 2, 2, str(tmp_path))
+    assert os.path.exists(tmp_path / "model_epoch1" / "G.pt")
+    line = open(tmp_path / "evaluation.txt").read()
+    m = re.fullmatch(r"Validation: 1 \tAvg MRSE: (\d+\.\d{4}) \tAvg PSNR: (\d+\.\d{4}) \tAvg 1-SSIM: (-?\d+\.\d{4})\n", line)
+    assert m, line
+    mrse, psnr, one_minus_ssim = (float(v) for v in m.groups())
+    assert mrse > 0 and 0 < psnr < 100 and 0 <= one_minus_ssim <= 2

@@ -151,3 +151,17 @@ def test_film_variant_matches_reference_golden():
         probe = torch.tensor([float(gr[i]) for i in r["probe_idx"]])
         assert float((probe - torch.tensor(r["probe"])).abs().max()) <= 1e-5 * (r["absmax"] + 1e-30) + 1e-12, name
         assert abs(float(gr.double().abs().sum()) - r["abssum"]) <= 1e-5 * (r["abssum"] + 1e-30) + 1e-12, name
+
+
+def test_metrics_oracle_matches_reference_golden():
+    """tensor2img / PSNR / SSIM / MRSE restatements (oracle/metrics_oracle.py) against the values the real reference
+    functions produced (tests/golden/make_golden_metrics.py)."""
+    from oracle import metrics_oracle as MO
+    g, r = load_npz("metrics.npz"), load_json("metrics.json")
+    out_img, gt_img = MO.tensor2img(g["out_log"], True), MO.tensor2img(g["gt"])
+    assert np.array_equal(out_img, g["out_img"]) and np.array_equal(gt_img, g["gt_img"])
+    assert np.array_equal(MO.tensor2img(g["noisy_log"], True), g["noisy_img"])
+    assert abs(MO.psnr(out_img, gt_img) - r["psnr_out"]) < 1e-9
+    assert abs(MO.ssim(out_img, gt_img) - r["ssim_out"]) < 1e-9
+    assert abs(MO.ssim(g["noisy_img"], gt_img) - r["ssim_noisy"]) < 1e-9
+    assert abs(MO.rmse(np.exp(g["out_log"]) - 1, g["gt"]) - r["mrse_out"]) < 1e-6 * r["mrse_out"]
