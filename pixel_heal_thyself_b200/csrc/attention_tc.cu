@@ -96,7 +96,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* s_full = bars + 5;     // [2]
   uint64_t* o_free = bars + 7;     // O read out of TMEM (256 arrivals)
   uint64_t* ro_in = bars + 9;      // residual tile of the iteration has landed / the staging tile is free
-  uint64_t* ro_out = bars + 10;    // output tile complete (128 arrivals)
+  uint64_t* ro_out = bars + 10;    // output tile complete (256 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 

@@ -281,7 +281,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       else asm volatile("bar.sync 2, 128;" ::: "memory");
     };
     const int rsw = row & 7;
-    int n_store = 0;                       // output tiles stored so far (selects the staging buffer)
     int j_aux = 0;                         // epilogue-input tiles consumed so far
     auto stage_and_store = [&](const float* v, const CUtensorMap* tm, int c_glob, int x0, int y0, int b) {
       uint8_t* buf = stg + part * STG_BYTES;   // one staging tile per epilogue group
@@ -294,7 +293,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       fence_proxy_async();
       group_sync();
       if (issuer) tma_store_4d(tm, buf, c_glob, x0, y0, b);
-      ++n_store;
     };
     // v[64] (op)= the epilogue-input tile that is next in the stream; releases its slot
     auto aux_apply = [&](float* v, int c_abs, bool is_mask) {
