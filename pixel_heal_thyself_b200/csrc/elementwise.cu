@@ -716,22 +716,37 @@ __global__ void tail_im2col_bwd_kernel(const float* __restrict__ dout, bf16* __r
     Vec<bf16>::st(a + p * 64 + g * 8, v);
   }
 }
-// dbias[co] = sum over the batch of dout[b][co][:, :]; one block per channel, fixed summation order (deterministic)
-__global__ void __launch_bounds__(1024) tail_dbias_kernel(const float* __restrict__ dout, float* __restrict__ dbias, int B, int HW) {
-  const int co = blockIdx.x;
+// dbias[co] = sum over the batch of dout[b][co][:, :].  grid (TAIL_DB_BLOCKS, 3): every block sums a fixed slice, the
+// last block to finish (ticket) adds the block partials in block order -> deterministic regardless of scheduling.
+constexpr int TAIL_DB_BLOCKS = 48;
+__device__ float g_tail_db_part[3 * TAIL_DB_BLOCKS];
+__device__ unsigned int g_tail_db_ticket[3] = {0, 0, 0};
+__global__ void __launch_bounds__(256) tail_dbias_kernel(const float* __restrict__ dout, float* __restrict__ dbias, int B, int HW) {
+  const int co = blockIdx.y;
   float s = 0.f;
   for (int b = 0; b < B; ++b) {
     const float* src = dout + ((long long)b * 3 + co) * HW;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) s += src[i];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) s += src[i];
   }
-  __shared__ float ws[32];
+  __shared__ float ws[8];
+  __shared__ bool last;
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += ws[w];
+    g_tail_db_part[co * TAIL_DB_BLOCKS + blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(&g_tail_db_ticket[co], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = 0; i < (int)gridDim.x; ++i) t += ((volatile float*)g_tail_db_part)[co * TAIL_DB_BLOCKS + i];
     dbias[co] = t;
+    g_tail_db_ticket[co] = 0;
   }
 }
 
@@ -1162,7 +1177,7 @@ int pht_tail_im2col_bwd(const float* dout_nchw, void* a_bf16, float* dbias, int3
   cudaStream_t st = (cudaStream_t)stream;
   long long n = (long long)B * H * W * 8;
   tail_im2col_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dout_nchw, (bf16*)a_bf16, B, H, W);
-  tail_dbias_kernel<<<3, 1024, 0, st>>>(dout_nchw, dbias, B, H * W);
+  tail_dbias_kernel<<<dim3(TAIL_DB_BLOCKS, 3), 256, 0, st>>>(dout_nchw, dbias, B, H * W);
   count_launch(CNT_OTHER, 2);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
