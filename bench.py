@@ -263,6 +263,23 @@ def run_ours(args):
         tr.G.train()
         inf_cfg = {"frame": f"{side}x{side}", "tiles": f"{rows}x{cols} 8-aligned, {EXACT_HALO}-px halo (exact)", "frames_timed": n_frames}
 
+    # ---------------- full GAN iteration (G step above + the PyTorch critic step), single GPU, informational ----------
+    gan_ms = None
+    if world == 1 and not args.gan and not args.no_gan_extra:
+        trg = AFGSATrainer(cfg)
+        trg.setup(g_only=False)
+        for i in range(args.warmup + 1):
+            trg.train_step(*batches[i % total])
+        sync_all()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(args.steps):
+            trg.train_step(*batches[i % total])
+        g1.record()
+        sync_all()
+        gan_ms = g0.elapsed_time(g1) / args.steps
+        del trg
+
     t = torch.tensor([ms, ms_e2e, ms_inf or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -297,6 +314,10 @@ def run_ours(args):
         "clocks": clk,
         "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+        "gan_step": ({"value": batch / (gan_ms * 1e-3), "unit": "patches/s", "ms_per_step": gan_ms,
+                      "note": "full iteration of base_trainer.py:388-457: the G step above + the critic step, which stays "
+                              "PyTorch/cuDNN (channels-last, cuDNN-friendly gradient-penalty backward, replayed as a CUDA graph)"}
+                     if gan_ms is not None else None),
         "gpu_launches": launches,
         "launch_counters": counters,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm 3x3 256->256 (forward + data-grad launches)",
@@ -330,6 +351,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gan", action="store_true", help="time the full GAN iteration (adds the PyTorch critic step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gan-extra", action="store_true", help="skip the informational full-GAN-iteration timing")
     ap.add_argument("--no-inference", action="store_true", help="skip the full-frame tiled inference measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -86,7 +86,9 @@ class BaseTrainer(ABC):
         milestones = [i * t.lr_milestone - 1 for i in range(1, t.epochs // t.lr_milestone)]
         opt_g = FlatAdam(G, lr=t.lr_g, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0 / self.world)
         sch_g = lr_scheduler.MultiStepLR(opt_g, milestones=milestones, gamma=0.5)
-        opt_d = optim.Adam(D.parameters(), lr=t.lr_d, betas=(0.9, 0.999), eps=1e-8)
+        # capturable: the critic step is replayed as one CUDA graph on a single GPU (same update rule, device-side step count)
+        opt_d = optim.Adam(D.parameters(), lr=t.lr_d, betas=(0.9, 0.999), eps=1e-8,
+                           capturable=self.device.type == "cuda" and self.world == 1)
         sch_d = lr_scheduler.MultiStepLR(opt_d, milestones=milestones, gamma=0.5)
         return opt_g, sch_g, opt_d, sch_d
 
@@ -130,23 +132,73 @@ class BaseTrainer(ABC):
         output = self.G(noisy, aux)
         d_loss = None
         if not self.g_only:
-            self.opt_d.zero_grad()
-            pred_fake = self.D(output.detach())
-            pred_real = self.D(gt)
-            d_loss = (self.gan_loss(pred_fake, False) + self.gan_loss(pred_real, True)) / 2 \
-                + lw.gp_loss_w * self.gp_loss(self.D, gt, output.detach())
-            d_loss.backward()
-            parallel.allreduce_module_grads(self.D, self.world)
-            self.opt_d.step()
+            d_loss = self._critic_step(output.detach(), gt)
         self.opt_g.zero_grad()
         g_loss = lw.l1_loss_w * self.l1_loss(output, gt)
         if not self.g_only:
+            # the generator's adversarial term only needs d D / d input: skip the critic's weight gradients (the reference
+            # computes and then discards them at the next opt_d.zero_grad())
+            d_params = list(self.D.parameters())
+            for p in d_params:
+                p.requires_grad_(False)
             g_loss = lw.gan_loss_w * self.gan_loss(self.D(output), True) + g_loss
+            for p in d_params:
+                p.requires_grad_(True)
         g_loss.backward()
         if self.bucketer is not None:
             self.bucketer.finish()
         self.opt_g.step()
         return g_loss.detach(), (d_loss.detach() if d_loss is not None else None)
+
+    # ------------------------------------------------------------------ critic step (base_trainer.py:391-412)
+    def _critic_eager(self, fake, gt):
+        lw = self.cfg.model.losses
+        self.opt_d.zero_grad()
+        pred_fake = self.D(fake)
+        pred_real = self.D(gt)
+        d_loss = (self.gan_loss(pred_fake, False) + self.gan_loss(pred_real, True)) / 2 \
+            + lw.gp_loss_w * self.gp_loss(self.D, gt, fake)
+        d_loss.backward()
+        parallel.allreduce_module_grads(self.D, self.world)
+        self.opt_d.step()
+        return d_loss.detach()
+
+    def _critic_step(self, fake, gt):
+        """The PyTorch critic step.  On one GPU it is captured once per (shape, learning rate) as a CUDA graph and
+        replayed: the step is ~2,000 small eager launches (BatchNorm / LeakyReLU double backward of the gradient
+        penalty), i.e. bound by the host's launch rate, not by the GPU."""
+        use_graph = (self.world == 1 and fake.is_cuda and os.environ.get("PHT_CRITIC_GRAPH", "1") != "0"
+                     and not getattr(self, "_critic_graph_failed", False))
+        if not use_graph:
+            return self._critic_eager(fake, gt)
+        key = (tuple(fake.shape), tuple(float(g["lr"]) for g in self.opt_d.param_groups))
+        st = getattr(self, "_critic_graph", None)
+        if st is None or st["key"] != key:
+            try:
+                st = self._capture_critic(fake, gt, key)
+            except Exception as e:  # noqa: BLE001 -- capture is an optimisation: fall back to the eager step
+                logger.warning(f"critic CUDA-graph capture failed ({e!r}); running the critic step eagerly")
+                self._critic_graph_failed = True
+                self._critic_graph = None
+                return self._critic_eager(fake, gt)
+            self._critic_graph = st
+            return st["warm_loss"]          # (the capture warm-up already took this iteration's step)
+        st["fake"].copy_(fake)
+        st["gt"].copy_(gt)
+        st["graph"].replay()
+        return st["loss"].clone()
+
+    def _capture_critic(self, fake, gt, key):
+        s_fake, s_gt = fake.clone(), gt.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):       # warm-up on a side stream (allocator / cuDNN / optimizer state), 1 real step
+            warm_loss = self._critic_eager(s_fake, s_gt)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._critic_eager(s_fake, s_gt)
+        return {"key": key, "graph": graph, "fake": s_fake, "gt": s_gt, "loss": loss, "warm_loss": warm_loss}
 
     # ------------------------------------------------------------------ full loop
     def train(self) -> None:

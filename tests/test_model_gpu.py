@@ -312,3 +312,32 @@ def test_validation_pass_writes_the_reference_evaluation_line(tmp_path):
     assert m, line
     mrse, psnr, one_minus_ssim = (float(v) for v in m.groups())
     assert mrse > 0 and 0 < psnr < 100 and 0 <= one_minus_ssim <= 2
+
+
+def test_critic_step_graph_replay_trains_like_eager(monkeypatch):
+    """The critic step (base_trainer.py:391-412, stays PyTorch) replayed as a CUDA graph: the same update rule as the
+    eager step -- with the gradient-penalty weight at 0 (no RNG in the step) the two d_loss trajectories must agree to
+    fp32 round-off; with the penalty on they stay finite and the critic's weights move."""
+    from pixel_heal_thyself_b200.config import load_config
+    from pixel_heal_thyself_b200.models.afgsa.train import AFGSATrainer
+    torch.manual_seed(3)
+    fake = torch.rand(4, 3, 32, 32, device=DEV)
+    gt = torch.rand(4, 3, 32, 32, device=DEV)
+
+    def run(graph, gp_w):
+        monkeypatch.setenv("PHT_CRITIC_GRAPH", "1" if graph else "0")
+        cfg = load_config("ci", ["data.synthetic.num_images=1", "data.synthetic.height=128", "data.synthetic.width=128",
+                                 "data.patches.num_patches=16", f"model.losses.gp_loss_w={gp_w}"])
+        tr = AFGSATrainer(cfg)
+        tr.setup()
+        w0 = next(tr.D.parameters()).detach().clone()
+        losses = [float(tr._critic_step(fake, gt)) for _ in range(5)]
+        return losses, float((next(tr.D.parameters()).detach() - w0).abs().max()), getattr(tr, "_critic_graph", None)
+
+    eager, moved_e, _ = run(False, 0.0)
+    graph, moved_g, st = run(True, 0.0)
+    assert st is not None, "the critic step did not take the CUDA-graph path"
+    assert max(abs(a - b) for a, b in zip(eager, graph)) < 1e-4 * max(1.0, max(abs(a) for a in eager)), (eager, graph)
+    assert moved_e > 0 and abs(moved_e - moved_g) < 1e-3 * moved_e + 1e-7
+    with_gp, moved, st = run(True, 10.0)
+    assert st is not None and all(math.isfinite(v) for v in with_gp) and moved > 0

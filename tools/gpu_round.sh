@@ -9,7 +9,7 @@ else
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1
 fi
 echo "pytest rc=$?"; tail -5 gpurun_out/${tag}_pytest.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-inference > gpurun_out/${tag}_bench_prod.log 2>&1
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-inference --no-gan-extra > gpurun_out/${tag}_bench_prod.log 2>&1
 echo "bench rc=$?"; tail -1 gpurun_out/${tag}_bench_prod.log | cut -c1-400
 timeout 300 python tools/profile_step.py > gpurun_out/${tag}_plain.log 2>&1
 echo "plain rc=$?"
