@@ -120,11 +120,11 @@ def test_padded_conv_forward_and_backward(dtype, mode):
     assert rel_err(db, dpre.float().sum((0, 2, 3))) < 1e-4
 
 
-@pytest.mark.parametrize("B,C,N,H,W", [(2, 64, 64, 16, 24), (1, 256, 256, 32, 32), (2, 128, 64, 8, 40)])
+@pytest.mark.parametrize("B,C,N,H,W", [(2, 64, 64, 16, 24), (1, 256, 256, 32, 32), (2, 128, 64, 8, 40), (1, 64, 64, 24, 136)])
 def test_fused_replicate_padfold_dgrad(B, C, N, H, W):
     """PHT_EPI_PADFOLD: data-gradient of a replicate-padded 3x3 conv with the padding backward, the residual add and
     the ReLU mask fused into the GEMM epilogue == autograd of F.pad(replicate) + conv2d, and == the unfused
-    conv_gemm + pht_pad_fold pair.  (W = 24 / 40 exercise the half-filled last 16-pixel tile column.)"""
+    conv_gemm + pht_pad_fold pair.  (W = 24 / 40 exercise the half-filled last 16-pixel tile column, W = 136 three 2x64 strip tiles on the last two rows.)"""
     ops = _ops()
     from pixel_heal_thyself_b200._lib import PAD_MODES
     torch.manual_seed(5)
