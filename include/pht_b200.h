@@ -367,11 +367,14 @@ void pht_set_force_simple(int on);
  * "wgrad_split_div" = d: 1x1 weight-gradients use 1/d of the pixel splits (fewer fp32 partials);
  * "pdl" = 0 / 1 (default 1): launch the tcgen05 kernels with programmatic dependent launch (their preamble overlaps
  * the previous kernel's tail);
+ * "conv_trace" = 1: CTA 0 of pht_conv_gemm records clock64 stamps per tile (diagnostics);
  * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics) */
 int pht_set_option(const char* name, int value);
 /* Copies the stamps recorded under "attn_trace" ([iteration][12 events], first 48 iterations of CTA 0) to host memory
  * after a device synchronise; returns the number of values copied or a negative status. */
 int pht_attn_bwd_trace(int64_t* host, int32_t n);
+/* Same for pht_conv_gemm under "conv_trace" = 1: [tile][8 events] of CTA 0 (first 32 tiles). */
+int pht_conv_gemm_trace(int64_t* host, int32_t n);
 
 #ifdef __cplusplus
 }

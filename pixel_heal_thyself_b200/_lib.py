@@ -116,6 +116,7 @@ SYMBOLS = {
     "pht_reset_counters": (None, []),
     "pht_set_force_simple": (None, [C.c_int]),
     "pht_attn_bwd_trace": (C.c_int, [C.POINTER(C.c_int64), C.c_int32]),
+    "pht_conv_gemm_trace": (C.c_int, [C.POINTER(C.c_int64), C.c_int32]),
     "pht_set_option": (C.c_int, [C.c_char_p, C.c_int]),
 }
 

@@ -41,6 +41,7 @@ struct TcGemmP {
   int has_out1, has_out2, has_resid, has_mask;
   int out1_f32;       // out1 is fp32 (direct stores; used by the 64-wide decoder-tail GEMM only)
   int rev;            // walk the tiles last-to-first
+  int trace;          // diagnostics: CTA 0 records clock64 stamps of its pipeline events per tile
   int strip_rows;     // > 0: the last 2 output rows are covered by 2 x 64-pixel strip tiles (pad-fold domain, see conv_gemm_tc)
   int n_strip, reg_tiles_y;
   int residOy, residOx, maskOy, maskOx, out1Oy, out1Ox, out2Oy, out2Ox;
@@ -69,6 +70,17 @@ template <int BN, int MODE> struct TcCfg {
 };
 static_assert(TcCfg<256, 0>::SMEM_BYTES <= 232448 && TcCfg<256, 1>::SMEM_BYTES <= 232448 && TcCfg<256, 2>::SMEM_BYTES <= 232448,
               "conv_gemm_tc: shared memory budget");
+
+constexpr int CG_TRACE_TILES = 32, CG_TRACE_EVENTS = 8;
+__device__ long long g_conv_trace[CG_TRACE_TILES * CG_TRACE_EVENTS];
+static int g_conv_trace_on = 0;
+void set_conv_trace(int v) { g_conv_trace_on = v; }
+int read_conv_trace(long long* host, int n) {
+  if (n > CG_TRACE_TILES * CG_TRACE_EVENTS) n = CG_TRACE_TILES * CG_TRACE_EVENTS;
+  PHT_CUDA(cudaDeviceSynchronize());
+  PHT_CUDA(cudaMemcpyFromSymbol(host, g_conv_trace, (size_t)n * sizeof(long long)));
+  return n;
+}
 
 // tile index -> image, tile origin, shape.  Regular tiles are 8 x 16 pixels; with P.strip_rows the domain's last two
 // rows are covered by 2 x 64 strips (a 130-row padded domain needs 16 tile rows + 3 strips per image instead of 17 x 9
@@ -183,21 +195,28 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
   const int T = P.ks * P.ks, half = P.ks / 2;
   const int n_kinds = P.has_resid + P.has_mask;   // epilogue-input tiles per 64-channel chunk
+  const bool tracing = P.trace && blockIdx.x == 0 && lane == 0;
+  auto stamp = [&](int it, int ev) {
+    if (tracing && it < CG_TRACE_TILES) g_conv_trace[it * CG_TRACE_EVENTS + ev] = clock64();
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      int pit = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++pit) {
         const TileXY tl = decode_tile(P, tile);
         const int b = tl.b, x0 = tl.x0, y0 = tl.y0, n0 = tl.nt * BN;
+        bool first = true;
         for (int t = 0; t < T; ++t) {
           const int dy = t / P.ks - half, dx = t % P.ks - half;
           for (int s = 0; s < P.n_src; ++s) {
             const CUtensorMap* tm = tl.strip ? &tmA0s : (s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2));
             for (int kc = 0; kc < P.srcC[s]; kc += BK) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
+              if (first) { stamp(pit, 0); first = false; }
               uint8_t* a_dst = stage_base + stage * Cfg::STAGE_BYTES;
               uint8_t* b_dst = a_dst + Cfg::A_BYTES;
               mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -207,6 +226,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             }
           }
         }
+        stamp(pit, 1);
       }
     }
   } else if (warp == 1) {
@@ -228,6 +248,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         for (int ki = 0; ki < kiters; ++ki) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (ki == 0) stamp(it, 2);
           const uint32_t a_addr = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = umma_desc_k_sw128(a_addr);
           const uint64_t bdesc = umma_desc_k_sw128(a_addr + Cfg::A_BYTES);
@@ -240,6 +261,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_elect(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        stamp(it, 3);
       }
     }
   } else if (warp == 6) {
@@ -331,6 +353,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (warp == 2 || warp == 7) stamp(it, warp == 2 ? 4 : 6);
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
       if (part * 64 >= BN) {               // this group has no chunk of the tile
         tc_fence_before();
@@ -406,6 +429,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           stage_and_store(v, tmOut2, n0 + c0, x0 + P.out2Ox, y0 + P.out2Oy, b);
         }
       }
+      if (warp == 2 || warp == 7) stamp(it, warp == 2 ? 5 : 7);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all tensor stores complete before exit
   }
@@ -589,6 +613,7 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   // pad-fold domain (H+2 rows, (H+2) % 8 == 2): the last two rows as 2 x 64 strips instead of a ninth/seventeenth
   // row of 8 x 16 tiles that would be 3/4 empty
   const bool strips = padfold && a->n_src == 1 && g_strips.load(std::memory_order_relaxed) != 0;
+  P.trace = g_conv_trace_on;
   P.strip_rows = strips ? 2 : 0;
   P.reg_tiles_y = strips ? (a->Ho - 2) / TILE_H : P.tiles_y;
   P.n_strip = strips ? ceil_div(a->Wo, 64) : 0;

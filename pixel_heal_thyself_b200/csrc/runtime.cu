@@ -23,6 +23,8 @@ void set_tc_cfg(int v);  // igemm_tc.cu
 void set_wgrad_split_div(int v);  // wgrad_tc.cu
 void set_serpentine(int v);  // igemm_tc.cu
 void set_strips(int v);  // igemm_tc.cu
+void set_conv_trace(int v);  // igemm_tc.cu
+int read_conv_trace(long long* host, int n);  // igemm_tc.cu
 void set_attn_trace(int v);  // attention_tc.cu
 int read_attn_trace(long long* host, int n);  // attention_tc.cu
 bool force_simple() { return g_force_simple.load(std::memory_order_relaxed) != 0; }
@@ -43,6 +45,7 @@ void pht_reset_counters(void) {
 int pht_set_option(const char* name, int value) {
   if (name && !strcmp(name, "tc_cfg")) { pht::set_tc_cfg(value); return PHT_OK; }
   if (name && !strcmp(name, "wgrad_split_div")) { pht::set_wgrad_split_div(value); return PHT_OK; }
+  if (name && !strcmp(name, "conv_trace")) { pht::set_conv_trace(value); return PHT_OK; }
   if (name && !strcmp(name, "strips")) { pht::set_strips(value); return PHT_OK; }
   if (name && !strcmp(name, "serpentine")) { pht::set_serpentine(value); return PHT_OK; }
   if (name && !strcmp(name, "pdl")) { pht::g_pdl.store(value ? 1 : 0, std::memory_order_relaxed); return PHT_OK; }
@@ -50,6 +53,7 @@ int pht_set_option(const char* name, int value) {
   pht::set_error("pht_set_option: unknown option");
   return PHT_ERR_INVALID;
 }
+int pht_conv_gemm_trace(int64_t* host, int32_t n) { return pht::read_conv_trace((long long*)host, n); }
 int pht_attn_bwd_trace(int64_t* host, int32_t n) { return pht::read_attn_trace((long long*)host, n); }
 void pht_set_force_simple(int on) { pht::g_force_simple.store(on ? 1 : 0, std::memory_order_relaxed); }
 
