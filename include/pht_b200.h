@@ -367,6 +367,10 @@ void pht_set_force_simple(int on);
  * "wgrad_split_div" = d: 1x1 weight-gradients use 1/d of the pixel splits (fewer fp32 partials);
  * "pdl" = 0 / 1 (default 1): launch the tcgen05 kernels with programmatic dependent launch (their preamble overlaps
  * the previous kernel's tail);
+ * "serpentine" = 0 / 1 (default 1): pht_conv_gemm walks its tiles opposite to the direction its first source was last
+ * written in (the most recently written part of the input is still in L2);
+ * "strips" = 0 / 1 (default 1): PHT_EPI_PADFOLD launches cover the last two rows of the padded domain with 2 x 64-pixel
+ * tiles (fewer, fuller tiles); none of these three changes a result bit;
  * "conv_trace" = 1: CTA 0 of pht_conv_gemm records clock64 stamps per tile (diagnostics);
  * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics) */
 int pht_set_option(const char* name, int value);
