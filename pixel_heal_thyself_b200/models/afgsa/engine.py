@@ -16,6 +16,8 @@ backward.  Layout decisions:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from ... import ops
@@ -59,6 +61,7 @@ class AfgsaEngine:
         self._packed_key = None
         self._pack_plans = {}
         self._wg_bucket = None
+        self._side_stream = None
         self._saved_gen = {}
         self._gen = 0
         # data-parallel hook: called with "decoder" / "block<i>" / "encoders" as soon as that group's
@@ -350,6 +353,27 @@ class AfgsaEngine:
             else:
                 bucket.wgrad(dy, srcs, dw, **kw)
 
+        # The 1x1 weight-gradient GEMMs run on half of the SMs each (74 CTAs: fewer fp32 partials to reduce).  Two that
+        # are ready at the same time are launched side by side -- one on a second stream -- and joined right away, so
+        # nothing else ever overlaps them and no buffer they read can be overwritten underneath them.
+        pair_ok = bucket is not None and os.environ.get("PHT_PAIR_WGRADS", "1") != "0"
+
+        def paired(main_fn, side_fns):
+            if not pair_ok:
+                main_fn()
+                for f in side_fns:
+                    f()
+                return
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            cur = torch.cuda.current_stream()
+            self._side_stream.wait_stream(cur)
+            with torch.cuda.stream(self._side_stream):
+                for f in side_fns:
+                    f()
+            main_fn()
+            cur.wait_stream(self._side_stream)
+
         def unpack(wg, packed, **kw):
             if bucket is None:
                 ops.unpack_wgrad(wg, packed, **kw)
@@ -427,10 +451,10 @@ class AfgsaEngine:
                          dQK[..., :C], dQK[..., C:], dV, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,
                          heads=self.heads, block=self.block, halo=self.halo)
             wqk = tmp(2 * C * C).view(1, 2 * C, C)
-            wgrad(dQK, [M], wqk)
+            paired(lambda: wgrad(dQK, [M], wqk),
+                   [lambda: wgrad(dV, [X], G[pre + "attention.v_conv.weight"])])
             unpack(G[pre + "attention.q_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=0, scale=self.scale)
             unpack(G[pre + "attention.k_conv.weight"], wqk, ksize=1, Ntot=2 * C, Ktot=C, n_off=C)
-            wgrad(dV, [X], G[pre + "attention.v_conv.weight"])
             first = i == self.num_sa - 1
             if net.use_film:
                 FH = pk[f"b{i}.film0"].shape[1]
@@ -475,16 +499,16 @@ class AfgsaEngine:
         catN, catA = g("catN", (B, H, W, 768), T), g("catA", (B, H, W, 768), T)
         colN = g("colN", (B, H, W, pk["encN"].shape[-1]), T)
         colA = g("colA", (B, H, W, pk["encA"].shape[-1]), T)
-        wgrad(G0, [catN], G["conv_map.0.weight"], dbias=G["conv_map.0.bias"])
         ops.conv_gemm([G0], pk["conv_map.T"], 768, mask=catN, mslope=slopeN, out2=dcat)
-        self._encoder_wgrad(dcat, colN, ("conv1", "conv3", "conv5"), G, tmp, wgrad, unpack)
+        paired(lambda: wgrad(G0, [catN], G["conv_map.0.weight"], dbias=G["conv_map.0.bias"]),
+               [lambda: self._encoder_wgrad(dcat, colN, ("conv1", "conv3", "conv5"), G, tmp, wgrad, unpack)])
         # ---- aux encoder: G2 = d(conv_aenc2 pre-act) ------------------------------------------------
         if self.num_sa > 0:
-            wgrad(G2, [A1], G["conv_aenc2.0.weight"], dbias=G["conv_aenc2.0.bias"])
             ops.conv_gemm([G2], pk["conv_aenc2.T"], C, mask=A1, mslope=leaky, out2=G1)   # G1 = d(aenc1 pre-act)
-            wgrad(G1, [catA], G["conv_aenc1.0.weight"], dbias=G["conv_aenc1.0.bias"])
             ops.conv_gemm([G1], pk["conv_aenc1.T"], 768, mask=catA, mslope=slopeA, out2=dcat)
-            self._encoder_wgrad(dcat, colA, ("conv_a1", "conv_a3", "conv_a5"), G, tmp, wgrad, unpack)
+            paired(lambda: wgrad(G1, [catA], G["conv_aenc1.0.weight"], dbias=G["conv_aenc1.0.bias"]),
+                   [lambda: self._encoder_wgrad(dcat, colA, ("conv_a1", "conv_a3", "conv_a5"), G, tmp, wgrad, unpack),
+                    lambda: wgrad(G2, [A1], G["conv_aenc2.0.weight"], dbias=G["conv_aenc2.0.bias"])])
         else:  # no attention block consumes the aux features: their gradient is zero
             for n in ("conv_a1", "conv_a3", "conv_a5", "conv_aenc1", "conv_aenc2"):
                 G[n + ".0.weight"].zero_()
