@@ -231,8 +231,11 @@ def run_ours(args):
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h0.record()
     last = 0.0
-    for i in range(args.steps):
-        g_loss, _ = tr.train_step(*preprocess_host_batch(staged[i], dev))
+    from pixel_heal_thyself_b200.data import DevicePrefetcher
+    # every step copies ITS batch from pinned host memory and reads ITS loss back; the copy + preprocess of batch i+1 is
+    # enqueued on a side stream before step i's loss is read (the reference's DataLoader prefetches the same way)
+    for dev_batch in DevicePrefetcher(staged, dev):
+        g_loss, _ = tr.train_step(*dev_batch)
         last = float(g_loss)                      # device -> host read of the step's result, every step
     h1.record()
     sync_all()

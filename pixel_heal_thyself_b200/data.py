@@ -113,3 +113,39 @@ def preprocess_host_batch(batch: dict[str, torch.Tensor], device):
     aux = torch.empty(B, 7, P, P, device=device)
     ops.preprocess(n, g, a, noisy, gt, aux)
     return noisy, gt, aux
+
+
+class DevicePrefetcher:
+    """Iterates over pinned host batches and yields preprocessed device batches, with the H2D copy + ``pht_preprocess`` of
+    batch i+1 enqueued on a side stream while step i runs (the reference hides its input path the same way:
+    DataLoader workers + ``BackgroundGenerator`` prefetch thread, prefetch_dataloader.py:7-12).  Usage::
+
+        for noisy, gt, aux in DevicePrefetcher(host_batches, device):
+            trainer.train_step(noisy, gt, aux)
+    """
+
+    def __init__(self, host_batches, device):
+        self.batches, self.device = host_batches, device
+        self.stream = torch.cuda.Stream(device=device)
+
+    def _stage(self, batch):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            return preprocess_host_batch(batch, self.device)
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)    # batch i is on the device
+            cur = nxt
+            for t in cur:
+                t.record_stream(torch.cuda.current_stream())
+            try:
+                nxt = self._stage(next(it))                           # batch i+1: copy + preprocess behind step i
+            except StopIteration:
+                nxt = None
+            yield cur

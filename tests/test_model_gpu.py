@@ -341,3 +341,20 @@ def test_critic_step_graph_replay_trains_like_eager(monkeypatch):
     assert moved_e > 0 and abs(moved_e - moved_g) < 1e-3 * moved_e + 1e-7
     with_gp, moved, st = run(True, 10.0)
     assert st is not None and all(math.isfinite(v) for v in with_gp) and moved > 0
+
+
+def test_device_prefetcher_yields_the_same_batches():
+    """DevicePrefetcher (H2D + pht_preprocess of batch i+1 on a side stream behind step i) == preprocess_host_batch."""
+    from pixel_heal_thyself_b200.data import DevicePrefetcher, preprocess_host_batch
+    g = torch.Generator().manual_seed(5)
+    host = [{"noisy": torch.rand(2, 16, 16, 3, generator=g).pin_memory(), "gt": torch.rand(2, 16, 16, 3, generator=g).pin_memory(),
+             "aux": (torch.rand(2, 16, 16, 7, generator=g) * 2 - 1).pin_memory()} for _ in range(4)]
+    got = []
+    for batch in DevicePrefetcher(host, torch.device(DEV)):
+        got.append([t.clone() for t in batch])
+        torch.cuda.synchronize()
+    assert len(got) == 4
+    for hb, gb in zip(host, got):
+        ref = preprocess_host_batch(hb, torch.device(DEV))
+        assert all(torch.equal(a, b) for a, b in zip(ref, gb))
+    assert list(DevicePrefetcher([], torch.device(DEV))) == []
