@@ -151,7 +151,14 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream on the current device (every launch asks: the raw query costs < 1 us, the
+    Stream-object route ~16 us, i.e. 2.5 ms of host time per prod step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
