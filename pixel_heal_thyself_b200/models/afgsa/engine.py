@@ -123,7 +123,7 @@ class AfgsaEngine:
 
     def _build_pack_plan(self, backward: bool):
         net, C = self.net, self.C
-        P = dict(net.named_parameters())
+        P = net.params_dict_cached()
         plan = ops.PackPlan()
         pw = plan.add
         tc_tail = self.dtype == torch.bfloat16
@@ -210,7 +210,7 @@ class AfgsaEngine:
         aux = aux.contiguous().float()
         self._maybe_pack(backward=save)
         A = self._arena(B, H, W, "train" if save else "eval")
-        pk, P = self._packed, dict(net.named_parameters())
+        pk, P = self._packed, net.params_dict_cached()
         relu = self._const("relu", [0.0] * C)
         leaky = self._const("leaky", [LEAKY] * C)
         slopeN = self._const("slopeN", [0.0] * 768)
@@ -306,7 +306,7 @@ class AfgsaEngine:
         A = self._arena(B, H, W, "train")
         g, pk, mode = A.get, self._packed, self.pad_mode
         G = net.grad_views()
-        P = dict(net.named_parameters())
+        P = net.params_dict_cached()
         relu0 = self._const("relu", [0.0] * C)
         leaky = self._const("leaky", [LEAKY] * C)
         slopeN = self._const("slopeN", [0.0] * 768)

@@ -136,7 +136,7 @@ class _GeneratorFn(torch.autograd.Function):
         net.select_grad_arena()
         net.engine.backward(ctx.token, d_out)
         views = net.grad_views()
-        grads = tuple(views[n].detach() if p.requires_grad else None for n, p in net.named_parameters())
+        grads = tuple(views[n].detach() if p.requires_grad else None for n, p in net.named_params_cached())
         return (None, None, None) + grads
 
 
@@ -194,11 +194,25 @@ class AFGSANet(nn.Module):
         self._dirty = 0
         self.engine = AfgsaEngine(self)
 
+    # ------------------------------------------------------------------ cached parameter list
+    def named_params_cached(self) -> list[tuple[str, nn.Parameter]]:
+        """``list(self.named_parameters())`` computed once: the module tree is fixed after construction (``.to()`` and
+        ``load_state_dict`` keep the Parameter objects), and walking it costs ~0.4 ms -- seven times per training step."""
+        c = self.__dict__.get("_np_cache")
+        if c is None:
+            c = self.__dict__["_np_cache"] = list(self.named_parameters())
+            self.__dict__["_np_dict"] = dict(c)
+        return c
+
+    def params_dict_cached(self) -> dict[str, nn.Parameter]:
+        self.named_params_cached()
+        return self.__dict__["_np_dict"]
+
     # ------------------------------------------------------------------ flat parameter arena
     def _flatten(self) -> None:
         """Re-home every parameter into one flat fp32 CUDA buffer (fused Adam and
         the data-parallel all-reduce then work on two flat arrays)."""
-        params = list(self.named_parameters())
+        params = self.named_params_cached()
         dev = params[0][1].device
         if dev.type != "cuda":
             raise RuntimeError("AFGSANet (B200) needs its parameters on a CUDA device: there is no CPU fallback")
@@ -226,20 +240,20 @@ class AFGSANet(nn.Module):
 
     def select_grad_arena(self) -> None:
         """Pick the gradient arena the next backward writes: never the one a live ``p.grad`` aliases."""
-        p0 = next(self.parameters())
+        p0 = self.named_params_cached()[0][1]
         if p0.grad is not None and p0.grad.data_ptr() == self._grad_arenas[self._cur].data_ptr() + 4 * 0:
             self._cur ^= 1
         self.flat_grad = self._grad_arenas[self._cur]
 
     def grad_views(self) -> dict[str, torch.Tensor]:
         if self._grad_view_cache[self._cur] is None:
-            shapes = {n: p.shape for n, p in self.named_parameters()}
+            shapes = {n: p.shape for n, p in self.named_params_cached()}
             self._grad_view_cache[self._cur] = {n: self.flat_grad[o:o + k].view(shapes[n])
                                                 for n, (o, k) in self._offsets.items()}
         return self._grad_view_cache[self._cur]
 
     def weights_version(self) -> int:
-        return self._dirty + sum(p._version for p in self.parameters())
+        return self._dirty + sum(p._version for _, p in self.named_params_cached())
 
     def mark_weights_dirty(self) -> None:
         """Call after updating ``flat_param`` outside autograd's version tracking (fused Adam)."""
@@ -252,7 +266,7 @@ class AFGSANet(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, aux: torch.Tensor) -> torch.Tensor:
         self._flatten()
-        params = list(self.parameters())
+        params = [p for _, p in self.named_params_cached()]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _GeneratorFn.apply(self, x, aux, *params)
         out, _ = self.engine.forward(x, aux, save=False)

@@ -28,7 +28,7 @@ class FlatAdam(torch.optim.Optimizer):
         arena = net.flat_grad
         base = arena.data_ptr()
         aliased = True
-        for n, p in net.named_parameters():
+        for n, p in net.named_params_cached():
             o, k = net._offsets[n]
             if p.grad is None:
                 arena[o:o + k].zero_()
