@@ -516,6 +516,10 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
 // dK / dV leave the SM window-major in bf16 (rows transposed through smem into 64-byte segments, no atomics); a fold kernel sums the <= 4
 // overlapping windows of every pixel deterministically and writes the final NHWC gradients.
 // =================================================================================================
+#ifndef PHT_AB_DK_EARLY
+#define PHT_AB_DK_EARLY 0
+#endif
+constexpr bool AB_DK_EARLY = PHT_AB_DK_EARLY != 0;   // A/B: dK rows read out right behind the dV rows (under S/dP(i+1)) instead of behind the next softmax
 constexpr int AB_THREADS = 320;
 constexpr int AB_HALF = 104;                                    // keys per lane half (2 x 104 = 208 >= 196)
 constexpr int AB_ROWS = 2 * AB_HALF;                            // K / V / REL tile rows
@@ -902,7 +906,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       stamp(it, 3);
       // While the tensor core computes dQ(it): the deferred half of the previous iteration's read-out (dK rows), the
       // next iteration's coordinates and lse.  dV/dK(it) are issued behind dQ(it) and wait for dvk_free.
-      if (it > 0) readout_dk(zprev, it);
+      if (!AB_DK_EARLY && it > 0) readout_dk(zprev, it);
       stamp(it, 10);
       if (it + 1 < n_it) {
         if (((it + 1) & 3) == 0) coords(it + 1);
@@ -935,8 +939,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_wait();
         stage_store(c, P.dv_scratch, 32, zprev);
       }
+      if (AB_DK_EARLY) readout_dk(zprev, it + 1);
     }
-    if (n_it > 0) readout_dk(zprev, AB_TRACE_ITERS);
+    if (!AB_DK_EARLY && n_it > 0) readout_dk(zprev, AB_TRACE_ITERS);
     // relative-position gradient partial of this CTA
     const int rkey = row0 + lane;
     if (rkey < AT_NK) {
