@@ -170,9 +170,12 @@ def require_cuda(*tensors: torch.Tensor) -> None:
 
 def view(t: torch.Tensor | None, oy: int = 0, ox: int = 0) -> PhtView:
     """pht_view of a [B, H, W, C] tensor (any pixel strides, channel stride 1)."""
-    v = PhtView()
     if t is None:
-        return v
+        return PhtView()
+    sh, st = t.shape, t.stride()
+    assert len(sh) == 4 and (st[3] == 1 or sh[3] == 1), "view: need channels-last [B,H,W,C]"
+    # (positional construction: ten ctypes field assignments cost ~3x as much, and a step builds ~400 views)
+    return PhtView(t.data_ptr(), sh[1], sh[2], sh[3], oy, ox, DTYPES[t.dtype], st[0], st[1], st[2])
     assert t.dim() == 4 and (t.stride(3) == 1 or t.shape[3] == 1), "view: need channels-last [B,H,W,C]"
     v.ptr = t.data_ptr()
     v.H, v.W, v.C = t.shape[1], t.shape[2], t.shape[3]

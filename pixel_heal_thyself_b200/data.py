@@ -124,9 +124,11 @@ class DevicePrefetcher:
             trainer.train_step(noisy, gt, aux)
     """
 
-    def __init__(self, host_batches, device):
+    def __init__(self, host_batches, device, stream=None):
+        """``stream``: reuse one side stream across prefetchers (the caching allocator keeps a pool per stream: a fresh
+        stream's first copies cudaMalloc, which synchronises the device)."""
         self.batches, self.device = host_batches, device
-        self.stream = torch.cuda.Stream(device=device)
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
 
     def _stage(self, batch):
         self.stream.wait_stream(torch.cuda.current_stream())
