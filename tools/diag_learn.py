@@ -11,7 +11,7 @@ from pixel_heal_thyself_b200.models.afgsa.train import AFGSATrainer  # noqa: E40
 
 cfg = load_config("ci", ["data.synthetic.num_images=1", "data.synthetic.height=128", "data.synthetic.width=128",
                          "data.patches.num_patches=16"])
-for simple in (0, 1, 0):
+for simple in (0, 0):
     _lib.lib.pht_set_force_simple(simple)
     tr = AFGSATrainer(cfg)
     tr.setup(g_only=True)
