@@ -33,6 +33,7 @@ class _Arena:
     def __init__(self, device):
         self.device = device
         self.bufs: dict[str, torch.Tensor] = {}
+        self.slices: dict = {}
 
     def get(self, name, shape, dtype, zero=False):
         t = self.bufs.get(name)
@@ -43,6 +44,26 @@ class _Arena:
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+    # cached slices: the same Python objects every step (slicing costs ~5 us, and ops memoise pht_view per object)
+    def _slice(self, t, kind, fn):
+        key = (id(t), kind)
+        ent = self.slices.get(key)
+        if ent is None or ent[0] is not t:
+            if len(self.slices) > 1024:
+                self.slices.clear()
+            ent = self.slices[key] = (t, fn(t))
+        return ent[1]
+
+    def inner(self, t):
+        """interior [:, 1:-1, 1:-1, :] of a padded buffer"""
+        return self._slice(t, "inner", lambda u: u[:, 1:-1, 1:-1, :])
+
+    def lo(self, t, c):
+        return self._slice(t, ("lo", c), lambda u: u[..., :c])
+
+    def hi(self, t, c):
+        return self._slice(t, ("hi", c), lambda u: u[..., c:])
 
 
 class AfgsaEngine:
@@ -228,7 +249,7 @@ class AfgsaEngine:
         ops.conv_gemm([colN], pk["encN"], 768, bias=pk["encN.bias"], slope=slopeN, out1=catN)
         ops.conv_gemm([colA], pk["encA"], 768, bias=pk["encA.bias"], slope=slopeA, out1=catA)
         Xp = g("Xp0", (B, H + 2, W + 2, C), T)
-        X = Xp[:, 1:-1, 1:-1, :]
+        X = A.inner(Xp)
         ops.conv_gemm([catN], pk["conv_map"], C, bias=P["conv_map.0.bias"], slope=relu, out1=X)
         A1 = g("A1", (B, H, W, C), T)
         Af = g("A", (B, H, W, C), T)
@@ -246,7 +267,7 @@ class AfgsaEngine:
             H2 = g(f"H2{j}", (B, H, W, C), T)
             lse = g(f"lse{j}", (B, H, W, self.heads), torch.float32)
             Xn = g(f"Xp{(i + 1) if save else (i + 1) % 2}", (B, H + 2, W + 2, C), T)
-            X1 = X1p[:, 1:-1, 1:-1, :]
+            X1 = A.inner(X1p)
             if net.use_film:
                 # n_aux = gamma * x + beta with [gamma | beta] = W2 relu(W0 a + b0) + b2 (film.py:36-45, model.py:458-460)
                 FH = pk[f"b{i}.film0"].shape[1]
@@ -260,22 +281,22 @@ class AfgsaEngine:
                 ops.conv_gemm([X, Af], pk[f"b{i}.map"], C, bias=P[pre + "attention.conv_map.0.bias"], slope=relu, out1=M)
             ops.conv_gemm([M], pk[f"b{i}.qk"], 2 * C, out1=QK)
             ops.conv_gemm([X], pk[f"b{i}.v"], C, out1=V)
-            ops.attn_fwd(QK[..., :C], QK[..., C:], V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], X1,
+            ops.attn_fwd(A.lo(QK, C), A.hi(QK, C), V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], X1,
                          heads=self.heads, block=self.block, halo=self.halo, resid=X, lse=lse)
             ops.border_fill(X1p, mode)
             ops.conv_gemm([X1p], pk[f"b{i}.ff0"], C, ksize=3, src_offsets=[(1, 1)],
-                          bias=P[pre + "feed_forward.0.0.bias"], slope=relu, out1=H1p[:, 1:-1, 1:-1, :])
+                          bias=P[pre + "feed_forward.0.0.bias"], slope=relu, out1=A.inner(H1p))
             ops.border_fill(H1p, mode)
             ops.conv_gemm([H1p], pk[f"b{i}.ff1"], C, ksize=3, src_offsets=[(1, 1)],
                           bias=P[pre + "feed_forward.1.0.bias"], slope=relu, resid=X1, resid_mode="post",
-                          out1=H2, out2=Xn[:, 1:-1, 1:-1, :])
-            Xp, X = Xn, Xn[:, 1:-1, 1:-1, :]
+                          out1=H2, out2=A.inner(Xn))
+            Xp, X = Xn, A.inner(Xn)
 
         ops.border_fill(Xp, mode)
         D1p = g("D1p", (B, H + 2, W + 2, C), T)
         D2 = g("D2", (B, H, W, C), T)
         ops.conv_gemm([Xp], pk["dec0"], C, ksize=3, src_offsets=[(1, 1)], bias=P["decoder.0.0.bias"], slope=relu,
-                      out1=D1p[:, 1:-1, 1:-1, :])
+                      out1=A.inner(D1p))
         ops.border_fill(D1p, mode)
         ops.conv_gemm([D1p], pk["dec1"], C, ksize=3, src_offsets=[(1, 1)], bias=P["decoder.1.0.bias"], slope=relu,
                       out1=D2)
@@ -316,7 +337,7 @@ class AfgsaEngine:
         # gradient ping-pong buffers live in padded frames: the fused data-gradient (PHT_EPI_PADFOLD) stores whole
         # padded-domain tiles (frame = don't care), everything else addresses the interior views
         Gpad = {n: g(n + "p", (B, H + 2, W + 2, C), T) for n in ("G0", "G1", "G2", "GX")}
-        G0, G1, G2, GX = (Gpad[n][:, 1:-1, 1:-1, :] for n in ("G0", "G1", "G2", "GX"))
+        G0, G1, G2, GX = (A.inner(Gpad[n]) for n in ("G0", "G1", "G2", "GX"))
         pad_of = {id(G0): Gpad["G0"], id(G1): Gpad["G1"], id(G2): Gpad["G2"], id(GX): Gpad["GX"]}
         GA = g("GA", (B, H, W, C), T)
         fused_fold = T == torch.bfloat16 and net.padding_mode == "replicate" and not getattr(self, "no_fused_fold", False)
@@ -326,7 +347,7 @@ class AfgsaEngine:
         dcat = g("dcat", (B, H, W, 768), T)
         wtmp = g("wtmp", (9 * C * 768,), torch.float32)
         btmp = g("btmp", (768,), torch.float32)
-        attn_ws = g("attn_ws", (max(ops.attn_bwd_workspace_bytes(dQK[..., :C], self.heads, self.block, self.halo), 16) // 4,),
+        attn_ws = g("attn_ws", (max(ops.attn_bwd_workspace_bytes(A.lo(dQK, C), self.heads, self.block, self.halo), 16) // 4,),
                     torch.float32)
         tail_ws = g("tail_ws", (max(ops.dec_tail_ws_bytes(B, H, W, C), 16) // 4,), torch.float32)
         wg_ws = g("wg_ws", (64 * 1024 * 1024 // 4,), torch.float32)
@@ -422,7 +443,7 @@ class AfgsaEngine:
             ops.dec_tail_bwd_data(d_out, pk["dec2"], D2, G0)                       # G0 = d(D2 pre-act)
         self._dbg("dD2pre", G0); self._dbg("d_out", d_out); self._dbg("D2", D2); self._dbg("D1", D1p)
         conv3_wgrad(G0, D1p, "decoder.1.0")
-        conv3_dgrad(G0, pk["dec1.T"], mask=D1p[:, 1:-1, 1:-1, :], out2=G1)          # G1 = d(D1 pre-act)
+        conv3_dgrad(G0, pk["dec1.T"], mask=A.inner(D1p), out2=G1)          # G1 = d(D1 pre-act)
         self._dbg("dD1pre", G1)
         Xlast = g(f"Xp{self.num_sa}", (B, H + 2, W + 2, C), T)
         conv3_wgrad(G1, Xlast, "decoder.0.0")
@@ -431,7 +452,7 @@ class AfgsaEngine:
             conv3_dgrad(G1, pk["dec0.T"], mask=g(f"H2{self.num_sa - 1}", (B, H, W, C), T), out1=GX, out2=G0)
             self._dbg("dXlast", GX); self._dbg("dH2pre_last", G0)
         else:
-            conv3_dgrad(G1, pk["dec0.T"], mask=Xlast[:, 1:-1, 1:-1, :], out2=G0)
+            conv3_dgrad(G1, pk["dec0.T"], mask=A.inner(Xlast), out2=G0)
 
         Af, A1 = g("A", (B, H, W, C), T), g("A1", (B, H, W, C), T)
         # ---- transformer blocks, last to first ------------------------------------------------
@@ -440,15 +461,15 @@ class AfgsaEngine:
             M, QK, V = g(f"M{i}", (B, H, W, C), T), g(f"QK{i}", (B, H, W, 2 * C), T), g(f"V{i}", (B, H, W, C), T)
             X1p, H1p = g(f"X1p{i}", (B, H + 2, W + 2, C), T), g(f"H1p{i}", (B, H + 2, W + 2, C), T)
             lse = g(f"lse{i}", (B, H, W, self.heads), torch.float32)
-            X = g(f"Xp{i}", (B, H + 2, W + 2, C), T)[:, 1:-1, 1:-1, :]
+            X = A.inner(g(f"Xp{i}", (B, H + 2, W + 2, C), T))
             # GX = d(block output) raw, G0 = d(H2 pre-act)
             conv3_wgrad(G0, H1p, pre + "feed_forward.1.0")
-            conv3_dgrad(G0, pk[f"b{i}.ff1.T"], mask=H1p[:, 1:-1, 1:-1, :], out2=G1)       # G1 = d(H1 pre-act)
+            conv3_dgrad(G0, pk[f"b{i}.ff1.T"], mask=A.inner(H1p), out2=G1)       # G1 = d(H1 pre-act)
             conv3_wgrad(G1, X1p, pre + "feed_forward.0.0")
             conv3_dgrad(G1, pk[f"b{i}.ff0.T"], resid=GX, out1=G2)                          # G2 = dX1 = dO
             # attention
-            ops.attn_bwd(QK[..., :C], QK[..., C:], V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], lse, G2,
-                         dQK[..., :C], dQK[..., C:], dV, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,
+            ops.attn_bwd(A.lo(QK, C), A.hi(QK, C), V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], lse, G2,
+                         A.lo(dQK, C), A.hi(dQK, C), dV, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,
                          heads=self.heads, block=self.block, halo=self.halo)
             wqk = tmp(2 * C * C).view(1, 2 * C, C)
             paired(lambda: wgrad(dQK, [M], wqk),
