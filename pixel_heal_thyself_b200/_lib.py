@@ -192,13 +192,6 @@ def view(t: torch.Tensor | None, oy: int = 0, ox: int = 0) -> PhtView:
         _view_memo.clear()
     _view_memo[key] = (weakref.ref(t), ptr, oy, ox, v)
     return v
-    assert t.dim() == 4 and (t.stride(3) == 1 or t.shape[3] == 1), "view: need channels-last [B,H,W,C]"
-    v.ptr = t.data_ptr()
-    v.H, v.W, v.C = t.shape[1], t.shape[2], t.shape[3]
-    v.oy, v.ox = oy, ox
-    v.dtype = DTYPES[t.dtype]
-    v.sb, v.sy, v.sx = t.stride(0), t.stride(1), t.stride(2)
-    return v
 
 
 def ptr(t: torch.Tensor | None) -> int | None:

@@ -55,6 +55,28 @@ def test_invalid_arguments_return_error_not_crash():
         _lib.check(rc, "pht_conv_gemm")
 
 
+def test_view_memo_follows_the_tensor_not_its_id():
+    """pht_view structs are memoised per tensor object; a new tensor (even at a recycled id), a different slice or a
+    different origin must get its own struct."""
+    from pixel_heal_thyself_b200 import _lib
+    t = torch.zeros(2, 6, 6, 8)
+    v = _lib.view(t)
+    assert _lib.view(t) is v and (v.H, v.W, v.C, v.sb, v.sy, v.sx) == (6, 6, 8, 288, 48, 8)
+    assert _lib.view(t, 1, 1) is not v and _lib.view(t, 1, 1).oy == 1
+    inner = t[:, 1:-1, 1:-1, :]
+    vi = _lib.view(inner)
+    assert vi.ptr == t.data_ptr() + 4 * (48 + 8) and (vi.H, vi.W, vi.sy) == (4, 4, 48)
+    for _ in range(64):                     # short-lived tensors recycle ids: the weak reference must catch it
+        u = torch.zeros(1, 2, 2, 4)
+        vu = _lib.view(u)
+        assert vu.ptr == u.data_ptr() and (vu.H, vu.W, vu.C) == (2, 2, 4)
+        del u
+    w = torch.zeros(1, 3, 3, 4)
+    vw = _lib.view(w)
+    w.set_(torch.zeros(1, 5, 5, 4))          # same object, new storage: the pointer guard
+    assert _lib.view(w) is not vw and _lib.view(w).H == 5
+
+
 def test_param_init_matches_reference(golden_meta):
     from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
     torch.manual_seed(golden_meta["seed"])
