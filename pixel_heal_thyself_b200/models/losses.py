@@ -38,16 +38,34 @@ class L1ReconstructionLoss(nn.Module):
 
 
 class GANLoss(nn.Module):
-    """WGAN critic loss (reference: losses.py:103-172, loss_type "wgan" as used at base_trainer.py:141)."""
+    """Adversarial loss on critic scores (reference: losses.py:103-172).  The AFGSA trainer uses "wgan"
+    (base_trainer.py:141); "nsgan" (BCE on probabilities), "lsgan" (MSE) and "hinge" follow the reference's
+    definitions so that the class is a drop-in for every ``loss_type`` it accepts.  Plain torch on the critic's output
+    (a [B, 1] tensor) -- the critic is outside the hand-written path."""
 
-    def __init__(self, loss_type: str = "wgan") -> None:
+    TYPES = ("nsgan", "wgan", "lsgan", "hinge")
+
+    def __init__(self, loss_type: str = "nsgan", target_real_label: float = 1.0, target_fake_label: float = 0.0) -> None:
         super().__init__()
-        if loss_type != "wgan":
-            raise NotImplementedError("only the WGAN loss the AFGSA trainer uses is provided")
+        if loss_type not in self.TYPES:
+            raise NotImplementedError(f"GAN type {loss_type} is not found!")
         self.type = loss_type
+        self.register_buffer("real_label", torch.tensor(target_real_label))
+        self.register_buffer("fake_label", torch.tensor(target_fake_label))
 
-    def forward(self, input_data: torch.Tensor, target_is_real: bool) -> torch.Tensor:
-        return -input_data.mean() if target_is_real else input_data.mean()
+    def forward(self, input_data: torch.Tensor, target_is_real: bool,
+                is_discriminator: bool | None = None) -> torch.Tensor:
+        if self.type == "wgan":
+            return -input_data.mean() if target_is_real else input_data.mean()
+        if self.type == "hinge":
+            if not is_discriminator:
+                return (-input_data).mean()
+            sign = -1.0 if target_is_real else 1.0
+            return torch.relu(1.0 + sign * input_data).mean()
+        label = (self.real_label if target_is_real else self.fake_label).expand_as(input_data)
+        if self.type == "lsgan":
+            return torch.nn.functional.mse_loss(input_data, label)
+        return torch.nn.functional.binary_cross_entropy(input_data, label)
 
 
 class GradientPenaltyLoss(nn.Module):

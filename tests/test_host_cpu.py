@@ -77,6 +77,29 @@ def test_view_memo_follows_the_tensor_not_its_id():
     assert _lib.view(w) is not vw and _lib.view(w).H == 5
 
 
+def test_gan_loss_types_match_reference_golden():
+    """GANLoss for every loss_type the reference accepts (losses.py:103-172) against values from the real class."""
+    import json
+    import importlib.util
+    from pixel_heal_thyself_b200.models.losses import GANLoss
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "tests", "golden", "make_golden_ganloss.py"))
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "ganloss.json")))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    assert len(gold) == 10
+    for key, want in gold.items():
+        t, real, disc = key.split("/")
+        x = mk.scores(t).requires_grad_(True)
+        crit = GANLoss(t)
+        loss = crit(x, bool(int(real)), disc == "True") if t == "hinge" else crit(x, bool(int(real)))
+        (grad,) = torch.autograd.grad(loss, x)
+        assert abs(float(loss.detach()) - want["loss"]) <= 1e-6 * max(1.0, abs(want["loss"])), key
+        assert torch.allclose(grad.reshape(-1), torch.tensor(want["grad"]), rtol=1e-5, atol=1e-7), key
+    with pytest.raises(NotImplementedError):
+        GANLoss("ragan")
+
+
 def test_param_init_matches_reference(golden_meta):
     from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
     torch.manual_seed(golden_meta["seed"])
