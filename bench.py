@@ -138,6 +138,76 @@ def cpu_reference_step_time(patch: int, steps: int, warmup: int, budget_s: float
     return sum(times) / len(times), cores, len(times)
 
 
+def stock_torch_step_time(device: str, patch: int, batch: int, steps: int, warmup: int, autocast_bf16: bool):
+    """SURVEY 8d's "bar to beat": the reference's algorithm (the oracle port: plain torch ops + autograd + torch's fused
+    Adam) on ONE GPU through stock cuDNN / cuBLAS, TF32 allowed, optionally under ``torch.autocast(bfloat16)``.
+    Same G-only step and batch as our arm.  Returns seconds per step."""
+    import torch
+    from oracle import afgsa_oracle as O
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    dev = torch.device(device)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(990819)
+    net = AFGSANet(3, 7, 256, num_gcp=0, padding_mode="replicate")   # parameter container only
+    params = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in net.state_dict().items()
+              if v.dtype.is_floating_point}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4, betas=(0.9, 0.999), **({"fused": True} if dev.type == "cuda" else {}))
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(batch, 3, patch, patch, generator=g) * 0.5).to(dev)
+    aux = torch.rand(batch, 7, patch, patch, generator=g).to(dev)
+    gt = (torch.randn(batch, 3, patch, patch, generator=g) * 0.5).to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast_bf16):
+            out = O.afgsa_net_forward(x, aux, params, "replicate")
+        loss = O.l1_loss(out.float(), gt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / steps
+    else:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = step()
+        sec = (time.perf_counter() - t0) / steps
+    assert bool(torch.isfinite(loss)), "stock torch step produced a non-finite loss"
+    return sec
+
+
+def run_reference_stock_gpu(args):
+    """``--impl reference --ref-device cuda``: the oracle port on one B200 through stock cuDNN / cuBLAS (not the
+    driver's reference arm, which is the CPU path; this is the extra comparison SURVEY 8d asks for)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    patch, batch, preset = WORKLOADS[args.workload]
+    res = {}
+    for name, ac in (("tf32", False), ("bf16_autocast", True)):
+        sec = stock_torch_step_time("cuda:0", patch, batch, max(args.steps, 3), 3, ac)
+        res[name] = {"patches_per_s": batch / sec, "ms_per_step": sec * 1e3}
+    best = max(res.values(), key=lambda r: r["patches_per_s"])
+    print(json.dumps({
+        "impl": "reference", "kind": "port on GPU: torch ops + autograd + fused torch Adam via stock cuDNN/cuBLAS",
+        "metric": "AFGSA train patches/sec", "value": best["patches_per_s"], "unit": "patches/s", "n_gpus": 1,
+        "steps": max(args.steps, 3), "warmup": 3, "ms_per_step": best["ms_per_step"], "higher_is_better": True,
+        "dtype": "tf32 / bf16 autocast", "data": "synthetic",
+        "config": {"workload": f"{preset}: AFGSA G-only (hot path) training step, {patch}x{patch} patches, batch {batch}"},
+        "stock": res, "gpu_launches": 0}), flush=True)
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path.  The reference is pure Python with
     third-party imports that are absent from this image and from the GPU box, so this is the
@@ -355,6 +425,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cpu = the reference arm (default); cuda = the same port on one GPU "
+                         "through stock cuDNN/cuBLAS (extra comparison, SURVEY 8d)")
     ap.add_argument("--workload", default="prod", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gan", action="store_true", help="time the full GAN iteration (adds the PyTorch critic step)")
@@ -364,7 +437,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_stock_gpu if args.ref_device == "cuda" else run_reference)(args)
     else:
         run_ours(args)
 
