@@ -188,6 +188,34 @@ def stock_torch_step_time(device: str, patch: int, batch: int, steps: int, warmu
     return sec
 
 
+def stock_torch_inference_mpix(device: str, side: int, steps: int, autocast_bf16: bool) -> float:
+    """Forward-only (no_grad) pass of the oracle port over one side x side frame through stock cuDNN / cuBLAS -> MPix/s."""
+    import torch
+    from oracle import afgsa_oracle as O
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    dev = torch.device(device)
+    torch.manual_seed(990819)
+    net = AFGSANet(3, 7, 256, num_gcp=0, padding_mode="replicate")   # parameter container only
+    params = {k: v.detach().clone().to(dev) for k, v in net.state_dict().items() if v.dtype.is_floating_point}
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(1, 3, side, side, generator=g) * 0.5).to(dev)
+    aux = torch.rand(1, 7, side, side, generator=g).to(dev)
+    times = []
+    with torch.no_grad():
+        for it in range(steps + 2):
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast_bf16):
+                out = O.afgsa_net_forward(x, aux, params, "replicate")
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            if it >= 2:
+                times.append(time.perf_counter() - t0)
+    assert bool(torch.isfinite(out.float()).all())
+    return side * side / (sum(times) / len(times)) / 1e6
+
+
 def run_reference_stock_gpu(args):
     """``--impl reference --ref-device cuda``: the oracle port on one B200 through stock cuDNN / cuBLAS (not the
     driver's reference arm, which is the CPU path; this is the extra comparison SURVEY 8d asks for)."""
@@ -199,13 +227,20 @@ def run_reference_stock_gpu(args):
         sec = stock_torch_step_time("cuda:0", patch, batch, max(args.steps, 3), 3, ac)
         res[name] = {"patches_per_s": batch / sec, "ms_per_step": sec * 1e3}
     best = max(res.values(), key=lambda r: r["patches_per_s"])
+    infer = {}
+    try:
+        for name, ac in (("tf32", False), ("bf16_autocast", True)):
+            infer[name] = stock_torch_inference_mpix("cuda:0", 1024, 3, ac)
+        infer["frame"] = "1024x1024, whole frame in one forward pass"
+    except Exception as e:                                   # e.g. out of memory: report, do not fail the training number
+        infer["error"] = f"{type(e).__name__}: {e}"[:200]
     print(json.dumps({
         "impl": "reference", "kind": "port on GPU: torch ops + autograd + fused torch Adam via stock cuDNN/cuBLAS",
         "metric": "AFGSA train patches/sec", "value": best["patches_per_s"], "unit": "patches/s", "n_gpus": 1,
         "steps": max(args.steps, 3), "warmup": 3, "ms_per_step": best["ms_per_step"], "higher_is_better": True,
         "dtype": "tf32 / bf16 autocast", "data": "synthetic",
         "config": {"workload": f"{preset}: AFGSA G-only (hot path) training step, {patch}x{patch} patches, batch {batch}"},
-        "stock": res, "gpu_launches": 0}), flush=True)
+        "stock": res, "stock_inference_mpix_per_s": infer, "gpu_launches": 0}), flush=True)
 
 
 def run_reference(args):
