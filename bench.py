@@ -6,8 +6,8 @@
 Own arm: one "step" is one pass of the hot path over one patch batch -- generator
 forward, L1 image loss, generator backward and the fused Adam update -- on the
 prod configuration (128x128 patches, batch 8 per GPU, bf16), weak scaling over N
-GPUs (one process per GPU under torchrun, bucketed NCCL all-reduce overlapped
-with backward).  `value` is timed with inputs resident in HBM; `e2e` is the same
+GPUs (one process per GPU under torchrun, one NCCL all-reduce of the flat
+gradient arena per step).  `value` is timed with inputs resident in HBM; `e2e` is the same
 metric through the trainer's public API starting from pinned host buffers.
 Reference arm (--impl reference): the CPU restatement of the reference's path
 (oracle/) on the host cores, on a bounded sample of the same workload.
@@ -16,6 +16,8 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import atexit
+import datetime
 import json
 import os
 import statistics
@@ -61,9 +63,13 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md clocks line).
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    nvidia-smi needs 0.1-0.5 s before its first sample (longer on multi-GPU boxes), which is longer than a 10-step timed
+    region, so it is started well before the region and the samples are selected by their timestamps:
+    ``mark_begin()`` / ``mark_end()`` bracket the region on the host clock (the device is idle at both marks)."""
+
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -71,38 +77,78 @@ class ClockSampler:
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
         self.idx = gpu_index
+        self.t0 = self.t1 = None
+        self.pos0 = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                          "-lms", "25", "-i", str(self.idx)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
+            atexit.register(self._kill)             # never leave the poller behind if the bench dies early
         except OSError:
             self.proc = None
+
+    def _kill(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.kill()
+
+    def mark_begin(self):
+        self.t0 = datetime.datetime.now()
+        try:
+            self.pos0 = os.path.getsize(self.path)      # fallback selector if the stamps cannot be used
+        except OSError:
+            self.pos0 = 0
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
+
+    @staticmethod
+    def _stamp(text: str):
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f")
+        except ValueError:
+            return None
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.1)
         self.proc.terminate()
         self.proc.wait()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
+        rows = []                                   # (timestamp | None, sm MHz, max MHz, {reasons})
+        try:
+            text = open(self.path).read()
+        except OSError:
+            text = ""
+        pos = 0
+        for line in text.splitlines(keepends=True):
+            at, pos = pos, pos + len(line)
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
+                sm, mx = float(f[2]), float(f[3])
             except ValueError:
                 continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.path)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            rows.append((self._stamp(f[0]), sm, mx, {n for n, v in zip(names, f[6:10]) if v.lower().startswith("active")},
+                         at >= self.pos0))
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        window = "timed region"
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None
+                  and self.t0 <= r[0] <= self.t1]
+        if not inside:                              # unparsable stamps / region shorter than one period: samples written
+            late = [r for r in rows if r[4]]        # after the region began (the region + 0.1 s), else everything
+            inside, window = (late, "from the start of the timed region to 0.1 s after it") if late else \
+                             (rows, "all samples since the data set-up (none could be placed inside the timed region)")
+        sm = [r[1] for r in inside]
+        reasons = set().union(*[r[3] for r in inside]) if inside else set()
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": inside[-1][2] if inside else None,
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference_step_time(patch: int, steps: int, warmup: int, budget_s: float | None = None):
@@ -286,6 +332,9 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     tr.setup(g_only=not args.gan)
+    clocks = ClockSampler(tr.local_rank)
+    if rank == 0:
+        clocks.start()                       # early: nvidia-smi takes a few hundred ms to deliver its first sample
     ds = tr.setup_data()
     gen = torch.Generator().manual_seed(cfg.seed + rank)
     total = args.warmup + args.steps
@@ -306,9 +355,7 @@ def run_ours(args):
         tr.train_step(*batches[i])
     sink = []
     sync_all()
-    clocks = ClockSampler(tr.local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     _lib.lib.pht_reset_counters()
     ops.set_launch_profiler(sink, lambda tag: tag[0] == 3 and tag[1] == 256 and tag[2] == 256)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,6 +364,7 @@ def run_ours(args):
         tr.train_step(*batches[i])
     e1.record()
     sync_all()
+    clocks.mark_end()
     ops.set_launch_profiler(None)
     counters = _lib.counters()
     ms = e0.elapsed_time(e1)

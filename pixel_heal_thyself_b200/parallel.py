@@ -4,9 +4,12 @@ The reference is single-device (base_trainer.py:46).  The generator has no
 cross-sample operation and L1 is a mean, so data parallelism is exact: each rank
 runs the hot path on its shard of the patch batch and the only exchange is one
 SUM all-reduce of the generator's flat gradient arena (9.28 M fp32 = 37 MB per
-step), issued bucket by bucket on a side stream while backward is still
-producing the earlier layers' gradients (decoder -> block 4..0 -> encoders), and
-averaged inside the fused Adam kernel (grad_scale = 1/world).
+step), averaged inside the fused Adam kernel (grad_scale = 1/world).  By default
+it is ONE all-reduce right after backward (~0.1-0.15 ms exposed); with
+PHT_GRAD_ALLREDUCE=overlap it is issued bucket by bucket on a side stream while
+backward is still producing the earlier layers' gradients (decoder -> block 4..0
+-> encoders) -- measured slower (2 GPUs 11.06 vs 10.89 ms/step, 4 GPUs 11.39 vs
+11.07): NCCL's CTAs occupy SMs that the persistent one-CTA-per-SM kernels need.
 """
 from __future__ import annotations
 
@@ -66,14 +69,21 @@ def bucket_ranges(offsets: dict[str, tuple[int, int]], order: list[str], total: 
 
 
 class GradBucketer:
-    """Overlapped bucketed all-reduce of a flat gradient arena.
+    """All-reduce of a flat gradient arena, in one of two schedules (environment ``PHT_GRAD_ALLREDUCE``):
 
-    ``ready(tag)`` is called by the backward schedule as soon as the gradients of a bucket are final (on the
-    compute stream); the all-reduce of that slice is enqueued on a side stream behind an event.  ``finish()``
+    ``end`` (default): ONE all-reduce of the whole arena on the compute stream in ``finish()``: nothing overlaps the
+    backward pass, so NCCL's CTAs never take SMs away from the persistent one-CTA-per-SM kernels (a 148-CTA kernel
+    that finds an SM occupied runs that CTA's tiles as a second wave).
+
+    ``overlap``: ``ready(tag)`` is called by the backward schedule as soon as the gradients of a bucket are final (on
+    the compute stream); the all-reduce of that slice is enqueued on a side stream behind an event, and ``finish()``
     makes the compute stream wait for all outstanding buckets."""
 
     def __init__(self, get_flat_grad, offsets, order, total, group=None):
         self.get_flat_grad = get_flat_grad
+        self.total = total
+        self.mode = os.environ.get("PHT_GRAD_ALLREDUCE", "end")
+        assert self.mode in ("overlap", "end"), "PHT_GRAD_ALLREDUCE must be overlap or end"
         self.ranges = {k: (lo, hi) for k, lo, hi in bucket_ranges(offsets, order, total)}
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -87,6 +97,8 @@ class GradBucketer:
         lo, hi = self.ranges[tag]
         g = self.get_flat_grad()[lo:hi]
         self.launched.append(tag)
+        if self.mode == "end":
+            return
         if g.is_cuda:
             if self._stream is None:
                 self._stream = torch.cuda.Stream()
@@ -100,6 +112,8 @@ class GradBucketer:
             self._pending.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self) -> None:
+        if self.mode == "end" and self.world > 1:
+            dist.all_reduce(self.get_flat_grad()[:self.total], op=dist.ReduceOp.SUM, group=self.group)
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
         for w in self._pending:

@@ -208,6 +208,7 @@ assert world == 2 and dist.get_backend() == "gloo"
 offsets = {"conv1.0.weight": (0, 100), "transformer_blocks.0.attention.rel_h": (128, 60),
            "transformer_blocks.1.attention.rel_h": (192, 60), "decoder.0.0.weight": (256, 200)}
 order = list(offsets)
+os.environ["PHT_GRAD_ALLREDUCE"] = "overlap"        # bucket by bucket as backward completes them
 flat = torch.arange(512, dtype=torch.float32) * (rank + 1)
 b = parallel.GradBucketer(lambda: flat, offsets, order, 512)
 for tag in ("decoder", "block1", "block0", "encoders"):
@@ -215,6 +216,14 @@ for tag in ("decoder", "block1", "block0", "encoders"):
 assert b.launched == ["decoder", "block1", "block0", "encoders"]
 b.finish()
 assert torch.equal(flat, torch.arange(512, dtype=torch.float32) * 3), "all-reduce(sum) over 2 ranks"
+os.environ["PHT_GRAD_ALLREDUCE"] = "end"            # the default: one all-reduce of the whole arena in finish()
+flat2 = torch.arange(512, dtype=torch.float32) * (rank + 1)
+b2 = parallel.GradBucketer(lambda: flat2, offsets, order, 512)
+for tag in ("decoder", "block1", "block0", "encoders"):
+    b2.ready(tag)
+assert torch.equal(flat2, torch.arange(512, dtype=torch.float32) * (rank + 1)), "nothing reduced before finish()"
+b2.finish()
+assert torch.equal(flat2, torch.arange(512, dtype=torch.float32) * 3) and b2.launched == []
 perm = torch.randperm(1000, generator=torch.Generator().manual_seed(5))
 mine = parallel.shard_indices(1000, rank, world, 8, perm)
 allidx = [torch.zeros_like(mine) for _ in range(2)]
