@@ -249,3 +249,49 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"DP_OK {r}" in o, o[-2000:]
+
+
+def test_bench_clock_sampler_selects_samples_inside_the_timed_region(tmp_path, monkeypatch):
+    """bench.ClockSampler against a stand-in nvidia-smi that needs 0.3 s for its first sample: started early, only the
+    samples stamped between mark_begin() and mark_end() count; started late, it falls back to the samples written after
+    the region began."""
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.3\nwhile true; do\n"
+                    "echo \"$(date '+%Y/%m/%d %H:%M:%S.%3N'), 0, 1875, 1965, 950.1, 0x4, Not Active, Not Active, Not Active, Active\"\n"
+                    "sleep 0.02\ndone\n")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", f"{tmp_path}:{os.environ['PATH']}")
+    sys.path.insert(0, ROOT)
+    import bench
+    c = bench.ClockSampler(0)
+    c.start()
+    time.sleep(0.6)
+    c.mark_begin()
+    time.sleep(0.15)
+    c.mark_end()
+    got = c.stop()
+    assert got["window"] == "timed region" and 2 <= got["samples"] <= 9, got
+    assert got["sm_mhz"] == 1875.0 and got["sm_max_mhz"] == 1965.0 and got["reasons"] == ["sw_power_cap"]
+    c = bench.ClockSampler(0)
+    c.start()
+    c.mark_begin()
+    time.sleep(0.1)
+    c.mark_end()
+    time.sleep(0.35)
+    got = c.stop()
+    assert got["samples"] >= 1 and got["window"].startswith("from the start of the timed region"), got
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port arm): one JSON line with the contract's keys; dev shape to stay short."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "dev",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "patches/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "config"):
+        assert key in line, key
