@@ -231,7 +231,8 @@ int pht_dec_tail_bwd_weight(const float* dout_nchw, const pht_view* h, float* dw
 
 /* L1 reconstruction loss, fused forward+backward (losses.py:175-184,
  * base_trainer.py:423):  loss[0] = mean|a-b| (OVERWRITTEN),
- * grad[i] = grad_scale * sign(a[i]-b[i]) / n  (grad may be NULL). */
+ * grad[i] = grad_scale * sign(a[i]-b[i]) / n  (grad may be NULL).  The block partials of the deterministic
+ * two-level reduction live in library scratch private to (device, stream): launches on different streams may overlap. */
 int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, float* loss, float* grad, void* stream);
 
 /* Batch preprocessing (base_trainer.py:373-383; preprocessing.py:19-22,34-38):
@@ -372,7 +373,10 @@ void pht_set_force_simple(int on);
  * "strips" = 0 / 1 (default 1): PHT_EPI_PADFOLD launches cover the last two rows of the padded domain with 2 x 64-pixel
  * tiles (fewer, fuller tiles); none of these three changes a result bit;
  * "conv_trace" = 1: CTA 0 of pht_conv_gemm records clock64 stamps per tile (diagnostics);
- * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics) */
+ * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics);
+ * "bf16_fallback" = 0 / 1 (default 0): a PHT_BF16 launch of pht_conv_gemm / pht_wgrad / pht_attn_fwd / pht_attn_bwd whose
+ * shape or views the tcgen05 kernels do not take returns PHT_ERR_UNSUPPORTED instead of silently running the ~20x slower
+ * CUDA-core kernel; 1 re-enables that fallback (pht_set_force_simple(1) always selects the CUDA-core kernels) */
 int pht_set_option(const char* name, int value);
 /* Copies the stamps recorded under "attn_trace" ([iteration][12 events], first 48 iterations of CTA 0) to host memory
  * after a device synchronise; returns the number of values copied or a negative status. */

@@ -333,6 +333,11 @@ int pht_attn_fwd(const pht_attn_args* a, void* stream) {
     int rc = attn_fwd_tc(a, st, &handled);
     if (rc) return rc;
     if (handled) return PHT_OK;
+    if (!bf16_fallback_allowed() && a->H % a->block == 0 && a->W % a->block == 0) {   // (else: the reference's assertion below)
+      set_error("attn_fwd: bf16 launch (heads=%d head_dim=%d block=%d halo=%d) is not eligible for the tcgen05 kernel and the "
+                "CUDA-core fallback is disabled (option bf16_fallback)", a->heads, a->head_dim, a->block, a->halo);
+      return PHT_ERR_UNSUPPORTED;
+    }
   }
   return attn_fwd_simple(a, st);
 }
@@ -353,6 +358,12 @@ int pht_attn_bwd(const pht_attn_bwd_args* a, void* stream) {
     int rc = attn_bwd_tc(a, st, &handled);
     if (rc) return rc;
     if (handled) return PHT_OK;
+    if (!bf16_fallback_allowed()) {
+      set_error("attn_bwd: bf16 launch (heads=%d head_dim=%d block=%d halo=%d, workspace %zu B) is not eligible for the tcgen05 "
+                "kernel and the CUDA-core fallback is disabled (option bf16_fallback)", a->fwd.heads, a->fwd.head_dim,
+                a->fwd.block, a->fwd.halo, a->workspace_bytes);
+      return PHT_ERR_UNSUPPORTED;
+    }
   }
   return attn_bwd_simple(a, st);
 }

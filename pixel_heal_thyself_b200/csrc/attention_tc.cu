@@ -481,14 +481,8 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   P.residOy = a->resid.oy; P.residOx = a->resid.ox; P.outOy = a->out.oy; P.outOx = a->out.ox;
   P.rel_h = a->rel_h; P.rel_w = a->rel_w; P.lse = a->lse;
   P.trace = g_attn_trace_on == 2;
-  static bool attr = false;
-  if (!attr) {
-    PHT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PHT_SMEM_ATTR_ONCE(attn_fwd_tc_kernel, AT_SMEM);
+  const int sms = sm_count();
   int grid = P.nblocks < sms ? P.nblocks : sms;
   PHT_CUDA(launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(AF_THREADS), AT_SMEM, st, tmQ, tmK, tmV, tmR, tmO, P));
   PHT_LAUNCH_CHECK();
@@ -1031,9 +1025,7 @@ __global__ void attn_bwd_rel_reduce_kernel(const float* __restrict__ part, int n
 }
 
 static int at_grid(int nblocks) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   return nblocks < sms ? nblocks : sms;
 }
 
@@ -1070,11 +1062,7 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
   P.dk_scratch = (bf16*)a->workspace;
   P.dv_scratch = P.dk_scratch + scratch;
   P.rel_part = (float*)(P.dv_scratch + scratch);
-  static bool attr = false;
-  if (!attr) {
-    PHT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-    attr = true;
-  }
+  PHT_SMEM_ATTR_ONCE(attn_bwd_tc_kernel, AB_SMEM);
   const int grid = at_grid(P.nblocks);
   PHT_CUDA(launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, P));
   PHT_LAUNCH_CHECK();

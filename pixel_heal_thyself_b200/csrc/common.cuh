@@ -12,6 +12,20 @@ namespace pht {
 void set_error(const char* fmt, ...);
 void count_launch(int slot, uint64_t n = 1);
 bool force_simple();
+// bf16 launches that are not taken by a tcgen05 kernel fail (PHT_ERR_UNSUPPORTED) unless the "bf16_fallback" option
+// allows the CUDA-core kernels: the production dtype must never drop to a 20x slower path silently
+bool bf16_fallback_allowed();
+int cur_device();        // cudaGetDevice
+int sm_count();          // multiprocessor count of the current device (cached per device ordinal)
+// Small library-owned device scratch private to (device, stream, slot): ticketed reductions of launches that overlap
+// on different streams must not share partials.  Zero-initialised once; allocated at the first use (never under
+// stream capture: warm-up runs come first).  Returns nullptr (and sets the error) on failure.
+void* stream_scratch(cudaStream_t st, int slot, size_t bytes);
+
+constexpr int PHT_MAX_DEVICES = 64;
+struct PerDeviceOnce {   // "done once per device" flags (cudaFuncSetAttribute is per device, not per process)
+  unsigned char done[PHT_MAX_DEVICES] = {};
+};
 
 enum CounterSlot { CNT_GEMM_TC = 0, CNT_GEMM_SIMPLE = 1, CNT_WGRAD_TC = 2, CNT_WGRAD_SIMPLE = 3, CNT_ATTN_TC = 4,
                    CNT_ATTN_SIMPLE = 5, CNT_OTHER = 6 };
@@ -35,6 +49,17 @@ enum CounterSlot { CNT_GEMM_TC = 0, CNT_GEMM_SIMPLE = 1, CNT_WGRAD_TC = 2, CNT_W
   } while (0)
 
 #define PHT_LAUNCH_CHECK() PHT_CUDA(cudaGetLastError())
+
+// opt the kernel in to `bytes` of dynamic shared memory, once per device
+#define PHT_SMEM_ATTR_ONCE(kernel, bytes)                                                                     \
+  do {                                                                                                        \
+    static pht::PerDeviceOnce once__;                                                                         \
+    const int d__ = pht::cur_device() & (pht::PHT_MAX_DEVICES - 1);                                           \
+    if (!once__.done[d__]) {                                                                                  \
+      PHT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      once__.done[d__] = 1;                                                                                   \
+    }                                                                                                         \
+  } while (0)
 
 typedef __nv_bfloat16 bf16;
 

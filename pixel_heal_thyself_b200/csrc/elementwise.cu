@@ -9,16 +9,7 @@
 
 namespace pht {
 
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static inline int num_sms() { return sm_count(); }
 
 template <typename T> struct Vec;
 template <> struct Vec<float> {
@@ -382,11 +373,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __
 // L1 loss fused fwd + bwd; deterministic two-level reduction (ticket pattern)
 // ---------------------------------------------------------------------------------------------
 #define L1_MAX_BLOCKS 2048
-__device__ float g_l1_partials[L1_MAX_BLOCKS];
-__device__ unsigned int g_l1_ticket = 0;
-
+// scratch = [L1_MAX_BLOCKS partials | ticket], private to the launching (device, stream): see stream_scratch()
 __global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float gscale,
-                          float* __restrict__ loss, float* __restrict__ grad) {
+                          float* __restrict__ loss, float* __restrict__ grad, float* __restrict__ g_l1_partials) {
+  unsigned int* g_l1_ticket = reinterpret_cast<unsigned int*>(g_l1_partials + L1_MAX_BLOCKS);
   float s = 0.f;
   const float gs = gscale / (float)n;
   long long n4 = n >> 2;
@@ -429,7 +419,7 @@ __global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__
     if (threadIdx.x == 0) {
       g_l1_partials[blockIdx.x] = t;
       __threadfence();
-      unsigned int tk = atomicAdd(&g_l1_ticket, 1u);
+      unsigned int tk = atomicAdd(g_l1_ticket, 1u);
       last = (tk == gridDim.x - 1);
     }
   }
@@ -442,7 +432,7 @@ __global__ void l1_kernel(const float* __restrict__ a, const float* __restrict__
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (threadIdx.x == 0) {
       loss[0] = (float)(t / (double)n);
-      g_l1_ticket = 0;
+      *g_l1_ticket = 0;
     }
   }
 }
@@ -719,9 +709,10 @@ __global__ void tail_im2col_bwd_kernel(const float* __restrict__ dout, bf16* __r
 // dbias[co] = sum over the batch of dout[b][co][:, :].  grid (TAIL_DB_BLOCKS, 3): every block sums a fixed slice, the
 // last block to finish (ticket) adds the block partials in block order -> deterministic regardless of scheduling.
 constexpr int TAIL_DB_BLOCKS = 48;
-__device__ float g_tail_db_part[3 * TAIL_DB_BLOCKS];
-__device__ unsigned int g_tail_db_ticket[3] = {0, 0, 0};
-__global__ void __launch_bounds__(256) tail_dbias_kernel(const float* __restrict__ dout, float* __restrict__ dbias, int B, int HW) {
+// scratch = [3 * TAIL_DB_BLOCKS partials | 3 tickets], private to the launching (device, stream)
+__global__ void __launch_bounds__(256) tail_dbias_kernel(const float* __restrict__ dout, float* __restrict__ dbias, int B, int HW,
+                                                         float* __restrict__ g_tail_db_part) {
+  unsigned int* g_tail_db_ticket = reinterpret_cast<unsigned int*>(g_tail_db_part + 3 * TAIL_DB_BLOCKS);
   const int co = blockIdx.y;
   float s = 0.f;
   for (int b = 0; b < B; ++b) {
@@ -1020,7 +1011,9 @@ int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, flo
   const int one_wave = num_sms() * 8;   // 8 resident 256-thread blocks per SM: exactly one wave, grid-stride inside
   if (grid > one_wave) grid = one_wave;
   if (grid > L1_MAX_BLOCKS) grid = L1_MAX_BLOCKS;
-  l1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, (long long)n, grad_scale, loss, grad);
+  float* scratch = (float*)stream_scratch((cudaStream_t)stream, 0, (L1_MAX_BLOCKS + 4) * sizeof(float));
+  if (!scratch) return PHT_ERR_CUDA;
+  l1_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, (long long)n, grad_scale, loss, grad, scratch);
   count_launch(CNT_OTHER);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
@@ -1177,7 +1170,9 @@ int pht_tail_im2col_bwd(const float* dout_nchw, void* a_bf16, float* dbias, int3
   cudaStream_t st = (cudaStream_t)stream;
   long long n = (long long)B * H * W * 8;
   tail_im2col_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(dout_nchw, (bf16*)a_bf16, B, H, W);
-  tail_dbias_kernel<<<dim3(TAIL_DB_BLOCKS, 3), 256, 0, st>>>(dout_nchw, dbias, B, H * W);
+  float* scratch = (float*)stream_scratch(st, 1, (3 * TAIL_DB_BLOCKS + 4) * sizeof(float));
+  if (!scratch) return PHT_ERR_CUDA;
+  tail_dbias_kernel<<<dim3(TAIL_DB_BLOCKS, 3), 256, 0, st>>>(dout_nchw, dbias, B, H * W, scratch);
   count_launch(CNT_OTHER, 2);
   PHT_LAUNCH_CHECK();
   return PHT_OK;

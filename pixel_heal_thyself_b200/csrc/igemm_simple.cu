@@ -406,9 +406,7 @@ int wgrad_simple(const pht_wgrad_args* a, cudaStream_t st) {
   const int T_ = a->ksize * a->ksize;
   long long npx = (long long)a->B * a->Ho * a->Wo;
   int tiles = ceil_div(a->N, BM) * ceil_div(P.Ktot, BN) * T_;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   int splits = (4 * sms + tiles - 1) / tiles;
   long long maxsplits = (npx + 255) / 256;
   if (splits > maxsplits) splits = (int)maxsplits;
@@ -432,9 +430,7 @@ int colsum(const pht_view& dy, int dtype, int B, int Ho, int Wo, int N, float* o
   int rows = tpp >= 256 ? 1 : 256 / tpp;           // pixel rows per block iteration
   int threads = tpp * rows;
   if (threads > 1024) { rows = 1; threads = tpp; }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   int splits = (int)((npx + 16 * rows - 1) / (16 * rows));
   if (splits > 4 * sms) splits = 4 * sms;
   if (splits < 1) splits = 1;
@@ -486,6 +482,12 @@ int pht_conv_gemm(const pht_conv_gemm_args* a, void* stream) {
     set_error("conv_gemm: PHT_EPI_PADFOLD needs the bf16 tensor-core path (ksize 3, H and W multiples of 8, TMA-able views)");
     return PHT_ERR_UNSUPPORTED;
   }
+  if (a->dtype == PHT_BF16 && !force_simple() && !bf16_fallback_allowed()) {
+    set_error("conv_gemm: bf16 launch (N=%d ksize=%d n_src=%d C0=%d) is not eligible for the tcgen05 kernel (channels must be "
+              "multiples of 64, views 16-byte aligned) and the CUDA-core fallback is disabled (option bf16_fallback)",
+              a->N, a->ksize, a->n_src, a->src[0].C);
+    return PHT_ERR_UNSUPPORTED;
+  }
   return conv_gemm_simple(a, st);
 }
 
@@ -505,6 +507,12 @@ int pht_wgrad(const pht_wgrad_args* a, void* stream) {
     int rc = wgrad_tc(a, st, &handled, nullptr);   // also produces dbias (fused column sums)
     if (rc) return rc;
     if (handled) return PHT_OK;
+    if (!bf16_fallback_allowed()) {
+      set_error("wgrad: bf16 launch (N=%d ksize=%d n_src=%d C0=%d, workspace %zu B) is not eligible for the tcgen05 kernel and "
+                "the CUDA-core fallback is disabled (option bf16_fallback)", a->N, a->ksize, a->n_src, a->src[0].C,
+                a->workspace_bytes);
+      return PHT_ERR_UNSUPPORTED;
+    }
   }
   if (a->dbias) {
     int rc = colsum(a->dy, a->dtype, a->B, a->Ho, a->Wo, a->N, a->dbias, st);

@@ -513,14 +513,8 @@ struct TcMaps {
 template <int BN, int MODE>
 static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
   using Cfg = TcCfg<BN, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PHT_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PHT_SMEM_ATTR_ONCE((conv_gemm_tc_kernel<BN, MODE>), Cfg::SMEM_BYTES);
+  const int sms = sm_count();
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
   PHT_CUDA(launch_pdl(conv_gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1], m.A[2], m.W,
                       m.O[0], m.O[1], m.R, m.M, m.As, m.Os[0], m.Os[1], m.Rs, m.Ms, P));

@@ -1,7 +1,10 @@
 // Error reporting, launch counters, ABI introspection.
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <stdarg.h>
 #include <string.h>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -11,6 +14,7 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_counters[8];
 static std::atomic<int> g_force_simple{0};
 static std::atomic<int> g_pdl{1};
+static std::atomic<int> g_bf16_fallback{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -28,6 +32,42 @@ int read_conv_trace(long long* host, int n);  // igemm_tc.cu
 void set_attn_trace(int v);  // attention_tc.cu
 int read_attn_trace(long long* host, int n);  // attention_tc.cu
 bool force_simple() { return g_force_simple.load(std::memory_order_relaxed) != 0; }
+bool bf16_fallback_allowed() { return g_bf16_fallback.load(std::memory_order_relaxed) != 0; }
+
+int cur_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+int sm_count() {
+  static std::atomic<int> cache[PHT_MAX_DEVICES];
+  const int d = cur_device() & (PHT_MAX_DEVICES - 1);
+  int n = cache[d].load(std::memory_order_relaxed);
+  if (!n) {
+    n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+    cache[d].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
+void* stream_scratch(cudaStream_t st, int slot, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, cudaStream_t, int>, std::pair<void*, size_t>> pool;
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_tuple(cur_device(), st, slot);
+  auto it = pool.find(key);
+  if (it != pool.end() && it->second.second >= bytes) return it->second.first;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("stream_scratch: cannot allocate %zu bytes (first use of a launch that needs library scratch must not "
+              "happen under stream capture)", bytes);
+    return nullptr;
+  }
+  pool[key] = std::make_pair(p, bytes);   // (a smaller earlier block of the same key is leaked: sizes are constants)
+  return p;
+}
 namespace tc { bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; } }
 
 }  // namespace pht
@@ -50,6 +90,7 @@ int pht_set_option(const char* name, int value) {
   if (name && !strcmp(name, "serpentine")) { pht::set_serpentine(value); return PHT_OK; }
   if (name && !strcmp(name, "pdl")) { pht::g_pdl.store(value ? 1 : 0, std::memory_order_relaxed); return PHT_OK; }
   if (name && !strcmp(name, "attn_trace")) { pht::set_attn_trace(value); return PHT_OK; }
+  if (name && !strcmp(name, "bf16_fallback")) { pht::g_bf16_fallback.store(value ? 1 : 0, std::memory_order_relaxed); return PHT_OK; }
   pht::set_error("pht_set_option: unknown option");
   return PHT_ERR_INVALID;
 }

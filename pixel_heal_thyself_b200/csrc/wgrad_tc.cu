@@ -274,13 +274,6 @@ static bool wg_view_ok(const pht_view& v) {
   return v.sx > 0 && v.sy > 0 && v.sb > 0;
 }
 
-static int sm_count() {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return sms;
-}
-
 static std::atomic<int> g_wgrad_split_div{2};   // measured: 668.7 -> 675.6 patches/s at prod (4: 642.8)
 void set_wgrad_split_div(int v) { g_wgrad_split_div.store(v < 1 ? 1 : v, std::memory_order_relaxed); }
 
@@ -417,18 +410,10 @@ int wgrad_tc(const pht_wgrad_args* a, cudaStream_t st, bool* handled, pht_wgrad_
   }
   const int jobs = p.splits * p.T * p.n_ntiles * p.n_ktiles;
   if (p.MH == 2) {
-    static bool attr = false;
-    if (!attr) {
-      PHT_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<2>::SMEM_BYTES));
-      attr = true;
-    }
+    PHT_SMEM_ATTR_ONCE(wgrad_tc_kernel<2>, WgCfg<2>::SMEM_BYTES);
     PHT_CUDA(launch_pdl(wgrad_tc_kernel<2>, dim3(jobs), dim3(WG_THREADS), WgCfg<2>::SMEM_BYTES, st, tmDy, tmS[0], tmS[1], tmS[2], P));
   } else {
-    static bool attr = false;
-    if (!attr) {
-      PHT_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<1>::SMEM_BYTES));
-      attr = true;
-    }
+    PHT_SMEM_ATTR_ONCE(wgrad_tc_kernel<1>, WgCfg<1>::SMEM_BYTES);
     PHT_CUDA(launch_pdl(wgrad_tc_kernel<1>, dim3(jobs), dim3(WG_THREADS), WgCfg<1>::SMEM_BYTES, st, tmDy, tmS[0], tmS[1], tmS[2], P));
   }
   PHT_LAUNCH_CHECK();
