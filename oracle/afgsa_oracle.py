@@ -179,3 +179,52 @@ def g_only_train_step(x, aux, gt, sd, padding_mode="replicate", num_sa=5):
     loss.backward()
     # (parameters the forward never touches, i.e. FiLM's ``alpha``, have no gradient: reported as zeros)
     return out.detach(), loss.detach(), {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in params.items()}
+
+
+def reference_init_state_dict(seed: int = 990819, input_channels: int = 3, aux_channels: int = 7, base_ch: int = 256,
+                              num_sa: int = 5, block: int = 8, halo: int = 3, heads: int = 4) -> dict:
+    """The reference's random initialisation of AFGSANet (non-FiLM) under ``torch.manual_seed(seed)``, built from plain
+    ``torch.nn`` modules created in the reference's registration order (pht/models/afgsa/model.py:606-715; per AFGSA
+    layer: rel_h, rel_w ``randn`` :430-437, conv_map :449, q/k/v :450-452, then ``reset_parameters`` :518-524 =
+    kaiming_normal(fan_out, relu) on q/k/v and normal(0, 1) on rel_h / rel_w).  Same generator draws in the same order
+    => the same numbers as the reference module (pinned by tests/test_oracle_cpu.py against golden_meta.json's
+    ``param_checksums``).  Used by bench.py's CPU arm so that it never imports the product package."""
+    from torch import nn
+    from torch.nn import init
+    torch.manual_seed(seed)
+    sd = {}
+
+    def conv(name, cin, cout, k, bias=True):
+        m = nn.Conv2d(cin, cout, kernel_size=k, padding=(k - 1) // 2, bias=bias)
+        sd[name + ".weight"] = m.weight.detach().clone()
+        if bias:
+            sd[name + ".bias"] = m.bias.detach().clone()
+        return m
+
+    for nm, cin, k in (("conv1", input_channels, 1), ("conv3", input_channels, 3), ("conv5", input_channels, 5)):
+        conv(nm + ".0", cin, 256, k)
+    conv("conv_map.0", 768, base_ch, 1)
+    for nm, k in (("conv_a1", 1), ("conv_a3", 3), ("conv_a5", 5)):
+        conv(nm + ".0", aux_channels, 256, k)
+    conv("conv_aenc1.0", 768, base_ch, 1)
+    conv("conv_aenc2.0", base_ch, base_ch, 1)
+    win, hd = block + 2 * halo, base_ch // heads
+    for i in range(num_sa):
+        pre = f"transformer_blocks.{i}."
+        rel_h = torch.randn(1, win, 1, hd // 2)
+        rel_w = torch.randn(1, 1, win, hd // 2)
+        conv(pre + "attention.conv_map.0", 2 * base_ch, base_ch, 1)
+        qkv = [nn.Conv2d(base_ch, base_ch, kernel_size=1, bias=False) for _ in range(3)]
+        for m in qkv:
+            init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        init.normal_(rel_h, 0, 1)
+        init.normal_(rel_w, 0, 1)
+        sd[pre + "attention.rel_h"], sd[pre + "attention.rel_w"] = rel_h, rel_w
+        for nm, m in zip("qkv", qkv):
+            sd[pre + f"attention.{nm}_conv.weight"] = m.weight.detach().clone()
+        conv(pre + "feed_forward.0.0", base_ch, base_ch, 3)
+        conv(pre + "feed_forward.1.0", base_ch, base_ch, 3)
+    conv("decoder.0.0", base_ch, base_ch, 3)
+    conv("decoder.1.0", base_ch, base_ch, 3)
+    conv("decoder.2.0", base_ch, 3, 3)
+    return sd

@@ -92,6 +92,9 @@ class TrainerConfig:
     lr_gamma: float = 0.5
     lr_milestone: int = 3
     load_model: bool = False
+    # directory holding G.pt / D.pt for load_model (the reference reads cfg.trainer.model_path, base_trainer.py:341-347,
+    # without declaring the field)
+    model_path: str = ""
 
 
 @dataclass

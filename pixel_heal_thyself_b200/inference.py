@@ -41,7 +41,16 @@ def _splits(n: int, parts: int) -> list[tuple[int, int]]:
     return [(edges[i], edges[i + 1]) for i in range(parts)]
 
 
-def plan_tiles(H: int, W: int, rows: int, cols: int, halo: int = EXACT_HALO) -> list[Tile]:
+def _uniform(lo: int, hi: int, size: int, n: int) -> tuple[int, int]:
+    """Grow the haloed range [lo, hi) to `size` inside [0, n): extra halo is harmless (still exact), the origin stays a
+    multiple of ALIGN because lo, size and n are."""
+    lo = max(0, min(lo, n - size))
+    return lo, lo + size
+
+
+def plan_tiles(H: int, W: int, rows: int, cols: int, halo: int = EXACT_HALO, uniform: bool = True) -> list[Tile]:
+    """``uniform``: every tile's haloed input region gets the SAME shape (the largest one; border tiles take a wider
+    halo on their inner side), so the generator runs on one activation arena instead of one per tile shape."""
     if H % ALIGN or W % ALIGN:
         raise AssertionError("feature map dimensions must be divisible by the block size")
     if halo % ALIGN:
@@ -50,6 +59,10 @@ def plan_tiles(H: int, W: int, rows: int, cols: int, halo: int = EXACT_HALO) -> 
     for (y0, y1) in _splits(H, rows):
         for (x0, x1) in _splits(W, cols):
             tiles.append(Tile(y0, y1, x0, x1, max(0, y0 - halo), min(H, y1 + halo), max(0, x0 - halo), min(W, x1 + halo)))
+    if uniform and tiles:
+        th = max(t.ty1 - t.ty0 for t in tiles)
+        tw = max(t.tx1 - t.tx0 for t in tiles)
+        tiles = [Tile(t.y0, t.y1, t.x0, t.x1, *_uniform(t.ty0, t.ty1, th, H), *_uniform(t.tx0, t.tx1, tw, W)) for t in tiles]
     return tiles
 
 

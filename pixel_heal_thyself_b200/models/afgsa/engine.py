@@ -106,12 +106,37 @@ class AfgsaEngine:
     def device(self):
         return self.net.flat_param.device
 
+    # at most this many activation arenas stay alive (least recently used first out): a training shape, an evaluation
+    # shape and the odd partial batch / validation patch.  Tiled inference pads its tiles to ONE haloed shape.
+    max_arenas = 4
+
     def _arena(self, B, H, W, tag):
         key = (B, H, W, self.dtype, tag)
-        a = self._arenas.get(key)
+        a = self._arenas.pop(key, None)
         if a is None:
-            a = self._arenas[key] = _Arena(self.device)
+            a = _Arena(self.device)
+            while len(self._arenas) >= self.max_arenas:
+                # never the arena of a forward whose backward is still pending
+                victim = next((k for k in self._arenas if not (k[4] == "train" and k[:3] in self._saved_gen)), None)
+                if victim is None:
+                    break
+                del self._arenas[victim]
+        self._arenas[key] = a          # (re-)insert as most recently used
         return a
+
+    def release(self):
+        """Drop every cached device buffer (activation arenas, weight-gradient workspaces, packed weights and descriptor
+        tables); they are rebuilt on the next forward.  For long-lived processes that change resolution."""
+        self._arenas.clear()
+        self._saved_gen.clear()
+        self._packed.clear()
+        self._pack_plans.clear()
+        self._packed_key = None
+        self._wg_bucket = None
+        self._consts.clear()
+
+    def arena_bytes(self) -> int:
+        return sum(a.nbytes() for a in self._arenas.values())
 
     def _const(self, name, values):
         t = self._consts.get(name)

@@ -7,9 +7,14 @@ and the same per-iteration arithmetic (base_trainer.py:371-457), restated as
 ``train_step`` so the benchmark can time exactly one step.  Differences, all
 B200-side: batches are preprocessed on the device by ``pht_preprocess`` /
 ``pht_crop_preprocess`` instead of numpy on the host; the generator optimiser is
-the fused flat Adam; under torchrun the batch is sharded over ranks and the
-generator gradients are all-reduced bucket-by-bucket during backward; loss
-scalars are read back once per logging interval instead of every iteration.
+the fused flat Adam; loss scalars are read back once per epoch instead of every
+iteration.  Under torchrun every rank runs ``trainer.batch_size`` patches per
+step (per-rank batch: the global batch is world x batch_size, learning rates
+unscaled -- see ``parallel``), the generator's flat gradient arena is SUM
+all-reduced once after backward (``PHT_GRAD_ALLREDUCE=overlap`` issues it
+bucket by bucket during backward instead) and averaged inside the Adam kernel;
+the critic's gradients are averaged with one flat all-reduce; validation is
+sharded over the ranks and checkpoints are written by rank 0.
 """
 from __future__ import annotations
 
@@ -86,9 +91,8 @@ class BaseTrainer(ABC):
         milestones = [i * t.lr_milestone - 1 for i in range(1, t.epochs // t.lr_milestone)]
         opt_g = FlatAdam(G, lr=t.lr_g, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0 / self.world)
         sch_g = lr_scheduler.MultiStepLR(opt_g, milestones=milestones, gamma=0.5)
-        # capturable: the critic step is replayed as one CUDA graph on a single GPU (same update rule, device-side step count)
-        opt_d = optim.Adam(D.parameters(), lr=t.lr_d, betas=(0.9, 0.999), eps=1e-8,
-                           capturable=self.device.type == "cuda" and self.world == 1)
+        # capturable: the critic step is replayed as CUDA graphs (same update rule, device-side step count)
+        opt_d = optim.Adam(D.parameters(), lr=t.lr_d, betas=(0.9, 0.999), eps=1e-8, capturable=self.device.type == "cuda")
         sch_d = lr_scheduler.MultiStepLR(opt_d, milestones=milestones, gamma=0.5)
         return opt_g, sch_g, opt_d, sch_d
 
@@ -104,6 +108,13 @@ class BaseTrainer(ABC):
             self.sch_g = self.opt_d = self.sch_d = None
         else:
             self.opt_g, self.sch_g, self.opt_d, self.sch_d = self.create_optimizers(self.G, self.D)
+        if self.cfg.trainer.load_model:                     # base_trainer.py:341-347
+            mp = self.cfg.trainer.model_path
+            if not mp:
+                raise ValueError("trainer.load_model=true needs trainer.model_path=<directory with G.pt / D.pt>")
+            self.G.load_state_dict(torch.load(os.path.join(mp, "G.pt"), map_location=self.device))
+            if self.D is not None:
+                self.D.load_state_dict(torch.load(os.path.join(mp, "D.pt"), map_location=self.device))
         self.bucketer = None
         if self.world > 1:
             self.G._flatten()
@@ -115,6 +126,8 @@ class BaseTrainer(ABC):
             if self.D is not None:
                 for p in list(self.D.parameters()) + list(self.D.buffers()):
                     torch.distributed.broadcast(p.data, 0)
+            # the gradient penalty draws torch.rand from the global generator (losses.py:35-39): one stream per rank
+            torch.cuda.manual_seed(self.cfg.seed + self.rank)
 
     def setup_data(self) -> PatchDataset:
         d = self.cfg.data
@@ -146,7 +159,10 @@ class BaseTrainer(ABC):
                 p.requires_grad_(True)
         g_loss.backward()
         if self.bucketer is not None:
-            self.bucketer.finish()
+            # gather first: the all-reduce must act on the arena the optimiser reads (p.grad may not alias the arena
+            # backward wrote: zero_grad(set_to_none=False), accumulation, hooks)
+            _, aliased = self.opt_g.gather_grads()
+            self.bucketer.finish(aliased)
         self.opt_g.step()
         return g_loss.detach(), (d_loss.detach() if d_loss is not None else None)
 
@@ -164,28 +180,39 @@ class BaseTrainer(ABC):
         return d_loss.detach()
 
     def _critic_step(self, fake, gt):
-        """The PyTorch critic step.  On one GPU it is captured once per (shape, learning rate) as a CUDA graph and
-        replayed: the step is ~2,000 small eager launches (BatchNorm / LeakyReLU double backward of the gradient
-        penalty), i.e. bound by the host's launch rate, not by the GPU."""
-        use_graph = (self.world == 1 and fake.is_cuda and os.environ.get("PHT_CRITIC_GRAPH", "1") != "0"
+        """The PyTorch critic step, replayed from CUDA graphs captured once per (shape, learning rate): the step is
+        ~2,000 small eager launches (BatchNorm / LeakyReLU double backward of the gradient penalty), i.e. bound by the
+        host's launch rate, not by the GPU.  One GPU: one graph.  Data parallel: two graphs around the one eager NCCL
+        call -- [zero grads, 3 x D forward, gradient penalty, backward into ONE flat gradient buffer] -> all-reduce(flat)
+        -> [average, Adam step] -- so every rank still replays instead of launching."""
+        use_graph = (fake.is_cuda and os.environ.get("PHT_CRITIC_GRAPH", "1") != "0"
                      and not getattr(self, "_critic_graph_failed", False))
         if not use_graph:
             return self._critic_eager(fake, gt)
         key = (tuple(fake.shape), tuple(float(g["lr"]) for g in self.opt_d.param_groups))
         st = getattr(self, "_critic_graph", None)
         if st is None or st["key"] != key:
+            self._critic_warm_loss = None
             try:
-                st = self._capture_critic(fake, gt, key)
+                st = self._capture_critic(fake, gt, key) if self.world == 1 else self._capture_critic_dp(fake, gt, key)
             except Exception as e:  # noqa: BLE001 -- capture is an optimisation: fall back to the eager step
                 logger.warning(f"critic CUDA-graph capture failed ({e!r}); running the critic step eagerly")
                 self._critic_graph_failed = True
                 self._critic_graph = None
+                if self.world > 1:
+                    for p in self.D.parameters():           # un-home the gradients from the flat buffer
+                        p.grad = None
+                if self._critic_warm_loss is not None:     # the warm-up already took this iteration's critic step
+                    return self._critic_warm_loss
                 return self._critic_eager(fake, gt)
             self._critic_graph = st
             return st["warm_loss"]          # (the capture warm-up already took this iteration's step)
         st["fake"].copy_(fake)
         st["gt"].copy_(gt)
         st["graph"].replay()
+        if self.world > 1:
+            torch.distributed.all_reduce(st["flat"], op=torch.distributed.ReduceOp.SUM)
+            st["graph_step"].replay()
         return st["loss"].clone()
 
     def _capture_critic(self, fake, gt, key):
@@ -195,10 +222,48 @@ class BaseTrainer(ABC):
         with torch.cuda.stream(side):       # warm-up on a side stream (allocator / cuDNN / optimizer state), 1 real step
             warm_loss = self._critic_eager(s_fake, s_gt)
         torch.cuda.current_stream().wait_stream(side)
+        self._critic_warm_loss = warm_loss
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             loss = self._critic_eager(s_fake, s_gt)
         return {"key": key, "graph": graph, "fake": s_fake, "gt": s_gt, "loss": loss, "warm_loss": warm_loss}
+
+    def _capture_critic_dp(self, fake, gt, key):
+        lw = self.cfg.model.losses
+        s_fake, s_gt = fake.clone(), gt.clone()
+        params = [p for p in self.D.parameters() if p.requires_grad]
+        flat = torch.zeros(sum(p.numel() for p in params), device=fake.device)
+        off = 0
+        for p in params:                    # every gradient is a view of ONE flat buffer: one all-reduce, no copies
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+        def fwd_bwd():
+            flat.zero_()                    # (== zero_grad(set_to_none=False): backward accumulates into the views)
+            d_loss = (self.gan_loss(self.D(s_fake), False) + self.gan_loss(self.D(s_gt), True)) / 2 \
+                + lw.gp_loss_w * self.gp_loss(self.D, s_gt, s_fake)
+            d_loss.backward()
+            return d_loss.detach()
+
+        def step():
+            flat.div_(self.world)
+            self.opt_d.step()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):       # warm-up = this iteration's real step
+            warm_loss = fwd_bwd()
+            torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        self._critic_warm_loss = warm_loss
+        g_a, g_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_a):
+            loss = fwd_bwd()
+        with torch.cuda.graph(g_b, pool=g_a.pool()):
+            step()
+        return {"key": key, "graph": g_a, "graph_step": g_b, "flat": flat, "fake": s_fake, "gt": s_gt, "loss": loss,
+                "warm_loss": warm_loss}
 
     # ------------------------------------------------------------------ full loop
     def train(self) -> None:
@@ -220,7 +285,7 @@ class BaseTrainer(ABC):
             start = time.time()
             perm = torch.randperm(n_train, generator=gen)
             idx = parallel.shard_indices(n_train, self.rank, self.world, bs, perm).to(self.device)
-            iters = idx.numel() // bs
+            iters = (idx.numel() + bs - 1) // bs            # one process: the last batch may be partial (base_trainer.py:363)
             acc_g = torch.zeros((), device=self.device)
             acc_d = torch.zeros((), device=self.device)
             for it in range(iters):
@@ -240,7 +305,7 @@ class BaseTrainer(ABC):
             if self.sch_g is not None:
                 self.sch_d.step()
                 self.sch_g.step()
-            if self.rank == 0 and epoch % cfg.trainer.save_interval == 0:
+            if epoch % cfg.trainer.save_interval == 0:      # every rank validates its share; rank 0 writes
                 self._validate_and_save(epoch, ds, n_train, n_val, out_dir)
 
     def _validate_and_save(self, epoch, ds, n_train, n_val, out_dir) -> None:
@@ -248,16 +313,25 @@ class BaseTrainer(ABC):
         base_trainer.py:535-595 on the GPU: tone-mapped uint8 images (tensor2img), MRSE on the linear radiance, PSNR and
         SSIM on the images (``pixel_heal_thyself_b200.metrics``), and the reference's ``evaluation.txt`` line."""
         from .. import metrics as M
-        path = os.path.join(out_dir, f"model_epoch{epoch + 1}")
-        os.makedirs(path, exist_ok=True)
-        torch.save(self.G.state_dict(), os.path.join(path, "G.pt"))
-        if self.D is not None:
-            torch.save(self.D.state_dict(), os.path.join(path, "D.pt"))
+        dp = self.world > 1 and torch.distributed.is_initialized()
+        if dp and self.D is not None:
+            # the critic's BatchNorm running statistics are rank-local: save their average, keep the ranks identical
+            for b in self.D.buffers():
+                if b.dtype.is_floating_point:
+                    torch.distributed.all_reduce(b, op=torch.distributed.ReduceOp.SUM)
+                    b.div_(self.world)
+        if self.rank == 0:
+            path = os.path.join(out_dir, f"model_epoch{epoch + 1}")
+            os.makedirs(path, exist_ok=True)
+            torch.save(self.G.state_dict(), os.path.join(path, "G.pt"))
+            if self.D is not None:
+                torch.save(self.D.state_dict(), os.path.join(path, "D.pt"))
         self.G.eval()
         avg_mrse = avg_psnr = avg_ssim = 0.0
         cnt = 0
         with torch.no_grad():
-            for k in range(n_train, n_train + n_val):
+            # validation patches are strided over the ranks (no rank idles inside a collective while rank 0 validates)
+            for k in range(n_train + (self.rank if dp else 0), n_train + n_val, self.world if dp else 1):
                 noisy, gt_log, aux = ds.batch_device(torch.tensor([k], device=self.device))
                 out = self.G(noisy, aux)
                 gt = torch.expm1(gt_log)                     # the reference validates against the un-preprocessed gt
@@ -267,8 +341,14 @@ class BaseTrainer(ABC):
                 avg_ssim += ssim
                 cnt += 1
         self.G.train()
+        if dp:
+            t = torch.tensor([avg_mrse, avg_psnr, avg_ssim, float(cnt)], dtype=torch.float64, device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+            avg_mrse, avg_psnr, avg_ssim, cnt = float(t[0]), float(t[1]), float(t[2]), int(t[3])
         cnt = max(cnt, 1)
         avg_mrse, avg_psnr, avg_ssim = avg_mrse / cnt, avg_psnr / cnt, avg_ssim / cnt
+        if self.rank != 0:
+            return
         logger.info(f"[Val] epoch={epoch + 1} summary: avg_mrse={avg_mrse:.4f} avg_psnr={avg_psnr:.4f} "
                     f"avg_1-ssim={1 - avg_ssim:.4f}")
         with open(os.path.join(out_dir, "evaluation.txt"), "a") as f:   # format: base_trainer.py:591-595

@@ -20,22 +20,34 @@ class FlatAdam(torch.optim.Optimizer):
         self._step = 0
         self._m = self._v = None
 
-    def _flat_grad(self) -> torch.Tensor:
-        """The gradient arena the last backward wrote.  If autograd cloned instead of adopting our views
-        (or grads were produced elsewhere), gather them into the arena."""
+    def gather_grads(self) -> tuple[torch.Tensor, bool]:
+        """(arena, aliased): the flat gradient arena this optimiser will read, made to hold every ``p.grad``.
+
+        Normally autograd adopts the views of ``net.flat_grad`` that backward returns, so every ``p.grad`` already
+        aliases the arena (aliased = True, nothing is copied).  When it does not -- ``zero_grad(set_to_none=False)`` or
+        gradient accumulation (autograd adds into the previous ``p.grad``), a hook or clip that replaced the tensor, a
+        parameter without gradient -- the values are gathered into the arena and ``p.grad`` is re-homed onto its slice,
+        so that whatever happens to the arena next (the data-parallel all-reduce, ``step()``) acts on the gradients
+        autograd produced and a second call is a no-op.  Data-parallel callers MUST call this BEFORE the all-reduce."""
         net = self.net
         net._flatten()
         arena = net.flat_grad
         base = arena.data_ptr()
+        views = net.grad_views()
         aliased = True
         for n, p in net.named_params_cached():
             o, k = net._offsets[n]
             if p.grad is None:
                 arena[o:o + k].zero_()
-                aliased = aliased and False
+                aliased = False
             elif p.grad.data_ptr() != base + 4 * o:
                 arena[o:o + k].copy_(p.grad.reshape(-1))
-        return arena
+                p.grad = views[n].detach()
+                aliased = False
+        return arena, aliased
+
+    def _flat_grad(self) -> torch.Tensor:
+        return self.gather_grads()[0]
 
     @torch.no_grad()
     def step(self, closure=None):

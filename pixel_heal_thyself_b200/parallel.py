@@ -1,5 +1,9 @@
 """Data-parallel plumbing: one process per GPU, NCCL over NVLink/NVSwitch.
 
+Batch / learning-rate policy: ``trainer.batch_size`` is the PER-RANK batch (weak scaling, the benchmark's contract), so
+the global batch is world x batch_size; the gradient is the MEAN over the global batch (SUM all-reduce, 1/world folded
+into the Adam kernel) and lr_g / lr_d are used unscaled, exactly as a single process with the larger batch would.
+
 The reference is single-device (base_trainer.py:46).  The generator has no
 cross-sample operation and L1 is a mean, so data parallelism is exact: each rank
 runs the hot path on its shard of the patch batch and the only exchange is one
@@ -27,18 +31,27 @@ def init_distributed() -> tuple[int, int, int]:
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        # PHT_DIST_BACKEND=gloo: several ranks may share ONE GPU (NCCL refuses duplicate devices); gloo all-reduces CUDA
+        # tensors through the host -- used by the single-GPU data-parallel parity test, never for throughput
+        backend = os.environ.get("PHT_DIST_BACKEND", "nccl" if torch.cuda.is_available() else "gloo")
         if torch.cuda.is_available():
+            local = local % torch.cuda.device_count()
             torch.cuda.set_device(local)
+        if backend == "nccl":
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
         else:
-            dist.init_process_group("gloo", rank=rank, world_size=world)
+            dist.init_process_group(backend, rank=rank, world_size=world)
     elif torch.cuda.is_available():
         torch.cuda.set_device(local)
     return rank, local, world
 
 
 def shard_indices(n: int, rank: int, world: int, batch: int, perm: torch.Tensor) -> torch.Tensor:
-    """Rank's strided slice of a global permutation, trimmed so every rank sees the same number of full batches."""
+    """Rank's strided slice of a global permutation.  One process: the whole permutation (the reference's DataLoader
+    keeps the final partial batch: ceil(n / batch) iterations, base_trainer.py:363).  Several ranks: trimmed so that
+    every rank runs the same number of full batches (a ragged last step would dead-lock the gradient all-reduce)."""
+    if world == 1:
+        return perm
     per_rank = (n // (world * batch)) * batch
     return perm[rank::world][:per_rank]
 
@@ -111,14 +124,21 @@ class GradBucketer:
         else:
             self._pending.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
-    def finish(self) -> None:
-        if self.mode == "end" and self.world > 1:
-            dist.all_reduce(self.get_flat_grad()[:self.total], op=dist.ReduceOp.SUM, group=self.group)
+    def finish(self, aliased: bool = True) -> None:
+        """Complete the step's exchange.  ``aliased`` = every ``p.grad`` aliases the arena backward wrote
+        (``FlatAdam.gather_grads``, which the caller runs first): if not, the gradients were only just gathered into the
+        arena, so whatever the overlapped buckets reduced during backward is stale and the whole arena is reduced here."""
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
         for w in self._pending:
             w.wait()
         self._pending.clear()
+        if self.world > 1 and (self.mode == "end" or not aliased):
+            if self.mode == "overlap":
+                raise RuntimeError("PHT_GRAD_ALLREDUCE=overlap needs p.grad to alias the flat gradient arena (use "
+                                   "zero_grad(set_to_none=True), no gradient accumulation / hooks), or use the default "
+                                   "PHT_GRAD_ALLREDUCE=end")
+            dist.all_reduce(self.get_flat_grad()[:self.total], op=dist.ReduceOp.SUM, group=self.group)
         self.launched.clear()
 
 

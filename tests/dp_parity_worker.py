@@ -1,0 +1,76 @@
+"""Worker of tests/test_parity_gpu.py::test_data_parallel_2_ranks_equals_single_process_batch (one process per rank).
+
+Every rank builds the same seeded generator and the same 8-patch batch, trains on ITS 4 patches through the trainer's
+data-parallel step, and checks against a single-process step on all 8 patches (computed locally with a second net):
+  * the all-reduced gradient arena / world == the single-process gradient of the concatenated batch,
+  * after three steps -- the second one with zero_grad(set_to_none=False), i.e. p.grad not aliasing the arena that
+    backward writes -- the weights equal the single-process weights and are bit-identical on both ranks.
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+from pixel_heal_thyself_b200.config import load_config  # noqa: E402
+from pixel_heal_thyself_b200.models.afgsa.train import AFGSATrainer  # noqa: E402
+from pixel_heal_thyself_b200.models.losses import L1ReconstructionLoss  # noqa: E402
+from pixel_heal_thyself_b200.optim import FlatAdam  # noqa: E402
+from make_golden_shapes import shape_inputs  # noqa: E402
+
+dtype = os.environ.get("PHT_DP_DTYPE", "fp32")
+cfg = load_config("dev", ["trainer.batch_size=4", f"model.afgsa.compute_dtype={dtype}"])
+tr = AFGSATrainer(cfg)
+rank, world, dev = tr.rank, tr.world, tr.device
+assert world == 2
+tr.setup(g_only=True)
+x, gt, aux = (t.to(dev) for t in shape_inputs("dev"))            # 8 x 32 x 32, identical on both ranks
+mine = slice(4 * rank, 4 * rank + 4)
+
+# single-process reference: same init (rank 0's weights were broadcast), all 8 patches
+torch.manual_seed(cfg.seed)
+ref = tr.create_generator()
+ref.load_state_dict(tr.G.state_dict())
+ref_opt = FlatAdam(ref, lr=cfg.trainer.lr_g)
+l1 = L1ReconstructionLoss()
+tol = 2e-5 if dtype == "fp32" else 3e-2
+
+
+def rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+for step in range(3):
+    keep = step == 1                                      # step 1: gradients accumulate into / stay in the old tensors
+    ref_opt.zero_grad(set_to_none=not keep)
+    l1(ref(x, aux), gt).backward()
+    ref_g, _ = ref_opt.gather_grads()
+    ref_g = ref_g.clone()
+    ref_opt.step()
+
+    # the trainer's own step, with the zero_grad mode under test
+    tr.opt_g.zero_grad(set_to_none=not keep)
+    orig = tr.opt_g.zero_grad
+    tr.opt_g.zero_grad = lambda *a, **k: None             # train_step zeroes again: keep the mode chosen above
+    try:
+        g_loss, _ = tr.train_step(x[mine], gt[mine], aux[mine])
+    finally:
+        tr.opt_g.zero_grad = orig
+    got = tr.G.flat_grad / world                          # SUM all-reduce; the 1/world lives in the Adam kernel
+    e = rel(got, ref_g)
+    assert e < tol, f"rank {rank} step {step}: DP gradient differs from the single-process batch-8 gradient: {e:.3e}"
+    ew = rel(tr.G.flat_param, ref.flat_param)
+    assert ew < tol, f"rank {rank} step {step}: weights drifted from the single-process run: {ew:.3e}"
+    both = [torch.empty_like(tr.G.flat_param) for _ in range(world)]
+    dist.all_gather(both, tr.G.flat_param)
+    assert torch.equal(both[0], both[1]), f"step {step}: the ranks' weights are not bit-identical"
+    print(f"rank {rank} step {step} ({'set_to_none=False' if keep else 'default'}): grad rel {e:.2e}, weights rel {ew:.2e}, "
+          f"loss {float(g_loss):.5f}", flush=True)
+
+dist.barrier()
+dist.destroy_process_group()
+print("DP_PARITY_OK", rank)

@@ -156,14 +156,21 @@ def test_config_presets_and_overrides():
 def test_tile_plan_covers_frame_exactly():
     from pixel_heal_thyself_b200.inference import plan_tiles
     for (H, W, r, c) in ((2048, 2048, 2, 4), (256, 320, 3, 2), (64, 64, 1, 1), (72, 40, 4, 4)):
-        tiles = plan_tiles(H, W, r, c)
-        cover = torch.zeros(H, W, dtype=torch.int32)
-        for t in tiles:
-            cover[t.y0:t.y1, t.x0:t.x1] += 1
-            assert t.y0 % 8 == 0 and t.x0 % 8 == 0 and t.ty0 % 8 == 0 and t.tx0 % 8 == 0
-            assert (t.ty1 - t.ty0) % 8 == 0 and (t.tx1 - t.tx0) % 8 == 0
-            assert t.ty0 == max(0, t.y0 - 48) and t.ty1 == min(H, t.y1 + 48)
-        assert int(cover.min()) == 1 and int(cover.max()) == 1
+        for uniform in (False, True):
+            tiles = plan_tiles(H, W, r, c, uniform=uniform)
+            cover = torch.zeros(H, W, dtype=torch.int32)
+            for t in tiles:
+                cover[t.y0:t.y1, t.x0:t.x1] += 1
+                assert t.y0 % 8 == 0 and t.x0 % 8 == 0 and t.ty0 % 8 == 0 and t.tx0 % 8 == 0
+                assert (t.ty1 - t.ty0) % 8 == 0 and (t.tx1 - t.tx0) % 8 == 0
+                # >= 48 px of halo on every side that is not the frame border, never outside the frame
+                assert 0 <= t.ty0 <= max(0, t.y0 - 48) and min(H, t.y1 + 48) <= t.ty1 <= H
+                assert 0 <= t.tx0 <= max(0, t.x0 - 48) and min(W, t.x1 + 48) <= t.tx1 <= W
+                if not uniform:
+                    assert t.ty0 == max(0, t.y0 - 48) and t.ty1 == min(H, t.y1 + 48)
+            assert int(cover.min()) == 1 and int(cover.max()) == 1
+            if uniform:   # one haloed shape for all tiles: the generator keeps a single activation arena
+                assert len({(t.ty1 - t.ty0, t.tx1 - t.tx0) for t in tiles}) == 1
     with pytest.raises(AssertionError):
         plan_tiles(100, 64, 2, 2)
 
@@ -230,6 +237,20 @@ allidx = [torch.zeros_like(mine) for _ in range(2)]
 dist.all_gather(allidx, mine)
 both = torch.cat(allidx)
 assert mine.numel() == 496 and both.unique().numel() == 992, "disjoint equal shards"
+assert parallel.shard_indices(1000, 0, 1, 8, perm).numel() == 1000, "one process keeps the final partial batch"
+# finish(aliased=False): the caller has just gathered p.grad into the arena -> the whole arena is reduced at the end
+flat3 = torch.arange(512, dtype=torch.float32) * (rank + 1)
+b3 = parallel.GradBucketer(lambda: flat3, offsets, order, 512)
+b3.finish(aliased=False)
+assert torch.equal(flat3, torch.arange(512, dtype=torch.float32) * 3)
+os.environ["PHT_GRAD_ALLREDUCE"] = "overlap"
+b4 = parallel.GradBucketer(lambda: flat3, offsets, order, 512)
+try:
+    b4.finish(aliased=False)
+    raise SystemExit("overlap + non-aliased gradients must raise")
+except RuntimeError:
+    pass
+os.environ["PHT_GRAD_ALLREDUCE"] = "end"
 lin = torch.nn.Linear(4, 4)
 torch.manual_seed(rank); lin(torch.randn(3, 4)).sum().backward()
 g0 = lin.weight.grad.clone(); parallel.allreduce_module_grads(lin, world)

@@ -165,3 +165,41 @@ def test_metrics_oracle_matches_reference_golden():
     assert abs(MO.ssim(out_img, gt_img) - r["ssim_out"]) < 1e-9
     assert abs(MO.ssim(g["noisy_img"], gt_img) - r["ssim_noisy"]) < 1e-9
     assert abs(MO.rmse(np.exp(g["out_log"]) - 1, g["gt"]) - r["mrse_out"]) < 1e-6 * r["mrse_out"]
+
+
+def test_oracle_matches_the_reference_at_the_dev_baseline_shape():
+    """tests/golden/make_golden_shapes.py: the REAL reference's output / loss / gradient norms at dev (8 x 32 x 32);
+    stag / prod are pinned the same way by the generating script (``pins`` in the fixture) and re-checked on the GPU box."""
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    from make_golden_shapes import checksum, shape_inputs
+    meta = load_json("net_shapes_meta.json")
+    for k, v in meta["pins"].items():
+        assert v < (1e-5 if "out" in k or "loss" in k else 5e-3), (k, v)
+    x, gt, aux = shape_inputs("dev")
+    assert abs(checksum(x, gt, aux) - meta["inputs_checksum"]["dev"]) <= 1e-9 * meta["inputs_checksum"]["dev"]
+    from pixel_heal_thyself_b200.models.afgsa.model import AFGSANet
+    torch.manual_seed(990819)
+    sd = {k: v.detach().clone() for k, v in AFGSANet(3, 7, 256, num_gcp=0, padding_mode="replicate").state_dict().items()}
+    out, loss, grads = O.g_only_train_step(x, aux, gt, sd, "replicate")
+    ref = torch.from_numpy(load_npz("net_shapes.npz")["dev_out"])
+    assert float((out - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert abs(float(loss) - meta["dev_loss"]) / meta["dev_loss"] < 1e-5
+    for n, r in meta["grads"]["dev"].items():
+        assert abs(float(grads[n].double().norm()) - r["l2"]) / (r["l2"] + 1e-30) < 5e-3, n
+
+
+def test_oracle_reference_init_reproduces_the_reference_parameters(golden_meta):
+    """oracle.reference_init_state_dict (plain torch.nn modules in the reference's creation order) == the reference's own
+    random init under seed 990819 (checksums recorded from the real module) == the product model's parameter containers."""
+    sd = O.reference_init_state_dict(golden_meta["seed"])
+    assert list(sd) and set(sd) == set(golden_meta["param_checksums"])
+    for k, (s1, s2, first) in golden_meta["param_checksums"].items():
+        v = sd[k]
+        assert list(v.shape) == golden_meta["param_shapes"][k], k
+        assert abs(float(v.double().sum()) - s1) < 1e-9 + 1e-12 * abs(s1) and abs(float(v.double().abs().sum()) - s2) < 1e-9 + 1e-12 * s2, k
+        assert float(v.flatten()[0]) == first, k
+    prod = _ref_init_state_dict()
+    for k, v in sd.items():
+        assert torch.equal(v, prod[k]), k

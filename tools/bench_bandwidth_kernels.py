@@ -21,10 +21,11 @@ if os.path.exists(p):
 
 
 def timeit(fn, iters=20):
+    iters = int(os.environ.get('PHT_BW_ITERS', iters))   # (2 under ncu: every launch is replayed per metric pass)
     # L2 flush by READING a buffer larger than the 126 MB L2 (clean lines: a write flush would leave dirty lines whose
     # write-back is then charged to the timed kernel)
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
-    for _ in range(3):
+    for _ in range(1 if 'PHT_BW_ITERS' in os.environ else 3):
         fn()
     ts = []
     for _ in range(iters):
