@@ -393,7 +393,9 @@ def run_ours(args):
     sink = []
     ops.set_launch_profiler(sink, lambda tag: tag[0] == 3 and tag[1] == 256 and tag[2] == 256)
     prof_steps = 3
+    graphed, tr.use_step_graph = tr.use_step_graph, False      # eager launches: the events bracket individual kernels
     ms_prof = _timed(lambda i: tr.train_step(*batches[i % total]), prof_steps, sync_all)
+    tr.use_step_graph = graphed
     ops.set_launch_profiler(None)
     conv_ms = [a.elapsed_time(b) for _, a, b in sink]
 
@@ -524,7 +526,9 @@ def run_ours(args):
                                f"{patch}x{patch} patches, batch {batch}/GPU, {n_img} synthetic 1024x1024 frames/GPU",
                    "global_batch": batch * world, "parallelism": f"dp{world}",
                    "l2": f"per-step working set ~{3.3 * npx / 131072:.1f} GB >> 126 MB L2 (no explicit flush)",
-                   "step": "G forward + L1 + G backward + fused Adam" + (" + critic step (PyTorch)" if args.gan else "")},
+                   "step": "G forward + L1 + G backward + fused Adam" + (" + critic step (PyTorch)" if args.gan else ""),
+                   "launch": ("captured once, replayed from CUDA graphs" if getattr(tr, "_step_graph", None) is not None
+                              and tr._step_graph.get("rec") is not None else "eager launches")},
         "clocks": clk,
         "e2e": {"value": patches / (ms_e2e * 1e-3), "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last},

@@ -254,6 +254,12 @@ int pht_crop_preprocess(const float* noisy_f, const float* gt_f, const float* au
  * Adam, betas (0.9,0.999), eps 1e-8, no weight decay).  step is 1-based. */
 int pht_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
              int32_t step, float grad_scale, void* stream);
+/* The same update with the step-dependent quantities resident on the device, so that the launch can be replayed from a
+ * CUDA graph: hyper = float[4] {lr, step count so far (int32 bit pattern), scratch, scratch}.  A one-thread prelude
+ * kernel increments the step count and derives lr / (1 - beta1^step) and 1 / sqrt(1 - beta2^step) in fp64 (as
+ * pht_adam does on the host); the caller changes the learning rate by writing hyper[0]. */
+int pht_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps, float grad_scale,
+                 float* hyper, void* stream);
 
 /* Weight (re)packing between the reference's OIHW fp32 parameters and the
  * kernels' [tap][N][K] layout.
@@ -362,6 +368,9 @@ const char* pht_last_error(void);
  * [6] = all other kernel launches.  Reset with pht_reset_counters(). */
 void pht_get_counters(uint64_t* counters8);
 void pht_reset_counters(void);
+/* The counters are bumped by the host-side launch calls.  A caller that captured launches into a CUDA graph and replays
+ * them adds the captured counts (the pht_get_counters delta over the capture) once per replay. */
+void pht_add_counters(const uint64_t* counters8);
 /* 1 = never use tcgen05 paths (debug / A-B testing) */
 void pht_set_force_simple(int on);
 /* tuning / A-B knobs: "tc_cfg" = 0 auto, 1 prefer the deep-ring conv_gemm config, 2 force the wide-epilogue one;

@@ -96,6 +96,7 @@ SYMBOLS = {
     "pht_preprocess": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pht_crop_preprocess": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "pht_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
+    "pht_adam_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp]),
     "pht_pack_weight": (C.c_int, [C.POINTER(PackArgs), _vp]),
     "pht_unpack_wgrad": (C.c_int, [C.POINTER(PackArgs), _vp]),
     "pht_wgrad_partial": (C.c_int, [C.POINTER(WgradArgs), C.POINTER(WgradReduceJob), _vp]),
@@ -115,6 +116,7 @@ SYMBOLS = {
     "pht_last_error": (C.c_char_p, []),
     "pht_get_counters": (None, [C.POINTER(C.c_uint64)]),
     "pht_reset_counters": (None, []),
+    "pht_add_counters": (None, [C.POINTER(C.c_uint64)]),
     "pht_set_force_simple": (None, [C.c_int]),
     "pht_attn_bwd_trace": (C.c_int, [C.POINTER(C.c_int64), C.c_int32]),
     "pht_conv_gemm_trace": (C.c_int, [C.POINTER(C.c_int64), C.c_int32]),
@@ -196,6 +198,12 @@ def view(t: torch.Tensor | None, oy: int = 0, ox: int = 0) -> PhtView:
 
 def ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
+
+
+def raw_counters():
+    arr = (C.c_uint64 * 8)()
+    lib.pht_get_counters(arr)
+    return arr
 
 
 def counters() -> dict[str, int]:

@@ -577,6 +577,42 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     upd(p[i], g[i], m[i], v[i]);
 }
 
+// Device-resident hyper-parameters (CUDA-graph friendly: nothing step-dependent is a kernel argument).
+// hyper = {lr, step (int32 bits), step_size, 1/sqrt(bc2)}: the prelude bumps the step count and derives the two
+// bias-correction factors in fp64 exactly like pht_adam does on the host.
+__global__ void adam_hyper_kernel(float* __restrict__ hyper, float beta1, float beta2) {
+  const int step = __float_as_int(hyper[1]) + 1;
+  hyper[1] = __int_as_float(step);
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  hyper[2] = (float)((double)hyper[0] / bc1);
+  hyper[3] = (float)(1.0 / sqrt(bc2));
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n, const float* __restrict__ hyper, float beta1, float beta2,
+                                float eps, float gscale) {
+  const float step_size = hyper[2], inv_sqrt_bc2 = hyper[3];
+  long long n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    gg *= gscale;
+    mm = mm + (1.0f - beta1) * (gg - mm);
+    vv = vv * beta2 + (1.0f - beta2) * gg * gg;
+    float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+    pp = pp - step_size * (mm / denom);
+  };
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    upd(p[i], g[i], m[i], v[i]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight pack / unpack
 // ---------------------------------------------------------------------------------------------
@@ -1067,6 +1103,19 @@ int pht_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
   adam_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (long long)n, step_size, beta1,
                                                                           beta2, eps, inv_sqrt_bc2, grad_scale);
   count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
+int pht_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps, float grad_scale,
+                 float* hyper, void* stream) {
+  PHT_CHECK_ARG(p && g && m && v && hyper && n > 0, "adam_dev: bad args");
+  PHT_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)hyper) & 15) == 0,
+                "adam_dev: pointers must be 16B aligned");
+  adam_hyper_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, beta1, beta2);
+  adam_dev_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (long long)n, hyper, beta1, beta2, eps,
+                                                                              grad_scale);
+  count_launch(CNT_OTHER, 2);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }

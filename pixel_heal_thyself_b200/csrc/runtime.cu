@@ -79,6 +79,9 @@ const char* pht_last_error(void) { return pht::g_err; }
 void pht_get_counters(uint64_t* c) {
   for (int i = 0; i < 8; ++i) c[i] = pht::g_counters[i].load(std::memory_order_relaxed);
 }
+void pht_add_counters(const uint64_t* c) {
+  for (int i = 0; i < 8; ++i) pht::g_counters[i].fetch_add(c[i], std::memory_order_relaxed);
+}
 void pht_reset_counters(void) {
   for (int i = 0; i < 8; ++i) pht::g_counters[i].store(0, std::memory_order_relaxed);
 }

@@ -40,6 +40,53 @@ from .losses import GANLoss, GradientPenaltyLoss, L1ReconstructionLoss
 logger = logging.getLogger("pht")
 
 
+class _StepRecorder:
+    """One training step as a replayable sequence: CUDA graphs separated by the NCCL all-reduces of a data-parallel step
+    (collectives stay eager; everything between them is captured).  All graphs share one memory pool and are captured on
+    the stream the warm-up steps ran on."""
+
+    def __init__(self, stream):
+        self.stream = stream
+        self.items = []          # ("graph", CUDAGraph) | ("allreduce", tensor)
+        self.pool = None
+        self._ctx = self._g = None
+
+    def begin(self):
+        self._g = torch.cuda.CUDAGraph()
+        kw = {} if self.pool is None else {"pool": self.pool}
+        self._ctx = torch.cuda.graph(self._g, stream=self.stream, **kw)
+        self._ctx.__enter__()
+
+    def end(self, exc=(None, None, None)):
+        ctx, self._ctx = self._ctx, None
+        ctx.__exit__(*exc)
+        if exc[0] is None:
+            self.items.append(("graph", self._g))
+            if self.pool is None:
+                self.pool = self._g.pool()
+
+    def abort(self, e):
+        if self._ctx is not None:
+            try:
+                self.end((type(e), e, e.__traceback__))
+            except Exception:  # noqa: BLE001
+                pass
+
+    def allreduce(self, t):
+        """Called where the eager step all-reduces ``t``: close the running capture, remember the collective, open the
+        next capture.  (Nothing executes during capture, so the collective itself is only issued at replay.)"""
+        self.end()
+        self.items.append(("allreduce", t))
+        self.begin()
+
+    def replay(self):
+        for kind, x in self.items:
+            if kind == "graph":
+                x.replay()
+            else:
+                torch.distributed.all_reduce(x, op=torch.distributed.ReduceOp.SUM)
+
+
 def set_determinism(seed: int, deterministic: bool = True) -> None:
     """reference: base_trainer.py:50-67."""
     random.seed(seed)
@@ -65,6 +112,11 @@ class BaseTrainer(ABC):
         self.padding_mode = "replicate" if self.deterministic else "reflect"  # base_trainer.py:334
         self.G = self.D = None
         self.g_only = False
+        # Replay the whole training step from CUDA graphs (PHT_STEP_GRAPH=0 disables): a prod step is ~155 launches at
+        # ~22 us of Python/ctypes each, which bounds the small presets (dev / stag) and leaves gaps at prod
+        self.use_step_graph = os.environ.get("PHT_STEP_GRAPH", "1") != "0"
+        self._step_graph = None
+        self._capturing = None
 
     # ------------------------------------------------------------------ factories (reference API)
     @abstractmethod
@@ -119,7 +171,8 @@ class BaseTrainer(ABC):
         if self.world > 1:
             self.G._flatten()
             self.bucketer = parallel.GradBucketer(lambda: self.G.flat_grad, self.G._offsets,
-                                                  [n for n, _ in self.G.named_parameters()], self.G.flat_param.numel())
+                                                  [n for n, _ in self.G.named_parameters()], self.G.flat_param.numel(),
+                                                  allreduce=self._allreduce)
             self.G.engine.grad_ready_hook = self.bucketer.ready
             # identical initial weights on every rank
             torch.distributed.broadcast(self.G.flat_param, 0)
@@ -138,9 +191,80 @@ class BaseTrainer(ABC):
         return PatchDataset(frames, d.patches.patch_size, d.patches.num_patches, self.cfg.seed)
 
     # ------------------------------------------------------------------ one iteration
+    def _allreduce(self, t):
+        """SUM all-reduce of a persistent tensor; under step capture the recorder splits its graphs around it."""
+        if self._capturing is not None:
+            self._capturing.allreduce(t)
+        else:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+
     def train_step(self, noisy, gt, aux):
         """One iteration of base_trainer.py:388-457 on preprocessed NCHW device tensors.
-        Returns (g_loss, d_loss) as 0-dim device tensors (no host sync)."""
+        Returns (g_loss, d_loss) as 0-dim device tensors (no host sync).  After two eager warm-up steps of a given
+        batch shape the step is captured once and replayed from CUDA graphs (``use_step_graph``)."""
+        if (self.use_step_graph and noisy.is_cuda and not getattr(self, "_step_graph_failed", False)
+                and not (self.bucketer is not None and self.bucketer.mode == "overlap")):
+            return self._train_step_graphed(noisy, gt, aux)
+        return self._train_step_eager(noisy, gt, aux)
+
+    def _train_step_graphed(self, noisy, gt, aux):
+        from .. import _lib
+        lrs = (float(self.opt_g.param_groups[0]["lr"]),) + (tuple(float(g["lr"]) for g in self.opt_d.param_groups)
+                                                             if self.opt_d is not None else ())
+        key = (tuple(noisy.shape), lrs, self.g_only)
+        st = self._step_graph
+        if st is None or st["key"] != key:
+            st = self._step_graph = {"key": key, "warm": 0, "rec": None, "stream": torch.cuda.Stream(device=self.device)}
+        cur = torch.cuda.current_stream()
+        if st["warm"] < 2:
+            # eager warm-up steps ON THE CAPTURE STREAM (allocator pools, per-stream library scratch, descriptor tables,
+            # cuDNN plans, optimizer state are all created here, never under capture)
+            st["warm"] += 1
+            st["stream"].wait_stream(cur)
+            with torch.cuda.stream(st["stream"]):
+                out = self._train_step_eager(noisy, gt, aux)
+            cur.wait_stream(st["stream"])
+            for t in (noisy, gt, aux) + tuple(o for o in out if o is not None):
+                t.record_stream(st["stream"])
+            return out
+        if st["rec"] is None:
+            st["noisy"], st["gt"], st["aux"] = noisy.clone(), gt.clone(), aux.clone()
+            for attempt in (0, 1):
+                rec = _StepRecorder(st["stream"])
+                before = list(_lib.raw_counters())
+                try:
+                    self.opt_g.sync_lr()
+                    rec.begin()
+                    self._capturing = rec
+                    try:
+                        st["g_loss"], st["d_loss"] = self._train_step_eager(st["noisy"], st["gt"], st["aux"])
+                    finally:
+                        self._capturing = None
+                    rec.end()
+                except Exception as e:  # noqa: BLE001 -- capture is an optimisation: fall back to the eager step
+                    rec.abort(e)
+                    torch.cuda.synchronize()
+                    if attempt == 0 and _lib.lib.pht_set_option(b"pdl", 0) == 0:
+                        logger.warning(f"step capture failed ({e!r}); retrying without programmatic dependent launch")
+                        continue
+                    logger.warning(f"step CUDA-graph capture failed ({e!r}); running the training step eagerly")
+                    self._step_graph_failed = True
+                    self._step_graph = None
+                    return self._train_step_eager(noisy, gt, aux)
+                after = list(_lib.raw_counters())
+                st["launches"] = (_lib.C.c_uint64 * 8)(*[a - b for a, b in zip(after, before)])
+                st["rec"] = rec
+                break
+        st["noisy"].copy_(noisy)
+        st["gt"].copy_(gt)
+        st["aux"].copy_(aux)
+        self.opt_g.sync_lr()
+        st["rec"].replay()
+        self.G.mark_weights_dirty()                     # (the replayed Adam changed the weights behind Python's back)
+        _lib.lib.pht_add_counters(st["launches"])     # launch counters are bumped host-side: account for the replay
+        return st["g_loss"].clone(), (st["d_loss"].clone() if st["d_loss"] is not None else None)
+
+    def _train_step_eager(self, noisy, gt, aux):
         lw = self.cfg.model.losses
         output = self.G(noisy, aux)
         d_loss = None
@@ -175,7 +299,7 @@ class BaseTrainer(ABC):
         d_loss = (self.gan_loss(pred_fake, False) + self.gan_loss(pred_real, True)) / 2 \
             + lw.gp_loss_w * self.gp_loss(self.D, gt, fake)
         d_loss.backward()
-        parallel.allreduce_module_grads(self.D, self.world)
+        parallel.allreduce_module_grads(self.D, self.world, allreduce=self._allreduce)
         self.opt_d.step()
         return d_loss.detach()
 
@@ -185,7 +309,7 @@ class BaseTrainer(ABC):
         host's launch rate, not by the GPU.  One GPU: one graph.  Data parallel: two graphs around the one eager NCCL
         call -- [zero grads, 3 x D forward, gradient penalty, backward into ONE flat gradient buffer] -> all-reduce(flat)
         -> [average, Adam step] -- so every rank still replays instead of launching."""
-        use_graph = (fake.is_cuda and os.environ.get("PHT_CRITIC_GRAPH", "1") != "0"
+        use_graph = (fake.is_cuda and os.environ.get("PHT_CRITIC_GRAPH", "1") != "0" and self._capturing is None
                      and not getattr(self, "_critic_graph_failed", False))
         if not use_graph:
             return self._critic_eager(fake, gt)

@@ -308,6 +308,13 @@ def adam(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, grad_scale
                          step, grad_scale, L.stream_ptr()), "pht_adam")
 
 
+def adam_dev(p, g, m, v, hyper, *, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """pht_adam_dev: hyper = fp32 [4] device tensor {lr, step count (int32 bits), -, -}; CUDA-graph replayable."""
+    L.require_cuda(p, g, m, v, hyper)
+    L.check(lib.pht_adam_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), beta1, beta2, eps, grad_scale,
+                             hyper.data_ptr(), L.stream_ptr()), "pht_adam_dev")
+
+
 def _pack_args(w, packed, *, ksize, Ntot, Ktot, n_off=0, k_off=0, transpose=0, grid=0, i_begin=0, i_count=0,
                scale=1.0):
     a = L.PackArgs()

@@ -17,8 +17,26 @@ class FlatAdam(torch.optim.Optimizer):
         self.net = net
         super().__init__(list(net.parameters()), dict(lr=lr, betas=betas, eps=eps))
         self.grad_scale = grad_scale
-        self._step = 0
         self._m = self._v = None
+        # {lr, step count (int32 bits), -, -} on the device: nothing step-dependent is a kernel argument, so step() can be
+        # captured into / replayed from a CUDA graph
+        self._hyper = None
+        self._hyper_lr = None
+
+    @property
+    def step_count(self) -> int:
+        return 0 if self._hyper is None else int(self._hyper[1:2].view(torch.int32).item())
+
+    def sync_lr(self) -> None:
+        """Push the (scheduler-controlled) learning rate to the device copy if it changed.  Called by step(); callers that
+        replay a captured step() must call it themselves before the replay."""
+        lr = float(self.param_groups[0]["lr"])
+        if self._hyper is None or self._hyper.device != self.net.flat_param.device:
+            self._hyper = torch.zeros(4, dtype=torch.float32, device=self.net.flat_param.device)
+            self._hyper_lr = None
+        if lr != self._hyper_lr:
+            self._hyper[0:1].fill_(lr)
+            self._hyper_lr = lr
 
     def gather_grads(self) -> tuple[torch.Tensor, bool]:
         """(arena, aliased): the flat gradient arena this optimiser will read, made to hold every ``p.grad``.
@@ -57,9 +75,9 @@ class FlatAdam(torch.optim.Optimizer):
         if self._m is None or self._m.shape != net.flat_param.shape or self._m.device != net.flat_param.device:
             self._m = torch.zeros_like(net.flat_param)
             self._v = torch.zeros_like(net.flat_param)
-        self._step += 1
+        self.sync_lr()
         grp = self.param_groups[0]
-        ops.adam(net.flat_param, g, self._m, self._v, lr=float(grp["lr"]), beta1=grp["betas"][0],
-                 beta2=grp["betas"][1], eps=grp["eps"], step=self._step, grad_scale=self.grad_scale)
+        ops.adam_dev(net.flat_param, g, self._m, self._v, self._hyper, beta1=grp["betas"][0], beta2=grp["betas"][1],
+                     eps=grp["eps"], grad_scale=self.grad_scale)
         net.mark_weights_dirty()
         return loss

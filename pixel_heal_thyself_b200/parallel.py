@@ -92,7 +92,10 @@ class GradBucketer:
     the compute stream); the all-reduce of that slice is enqueued on a side stream behind an event, and ``finish()``
     makes the compute stream wait for all outstanding buckets."""
 
-    def __init__(self, get_flat_grad, offsets, order, total, group=None):
+    def __init__(self, get_flat_grad, offsets, order, total, group=None, allreduce=None):
+        """``allreduce(tensor)``: replaces the plain SUM all-reduce of the ``end`` schedule (the trainer's CUDA-graph
+        recorder splits its capture around the collective there)."""
+        self.allreduce = allreduce
         self.get_flat_grad = get_flat_grad
         self.total = total
         self.mode = os.environ.get("PHT_GRAD_ALLREDUCE", "end")
@@ -138,17 +141,23 @@ class GradBucketer:
                 raise RuntimeError("PHT_GRAD_ALLREDUCE=overlap needs p.grad to alias the flat gradient arena (use "
                                    "zero_grad(set_to_none=True), no gradient accumulation / hooks), or use the default "
                                    "PHT_GRAD_ALLREDUCE=end")
-            dist.all_reduce(self.get_flat_grad()[:self.total], op=dist.ReduceOp.SUM, group=self.group)
+            if self.allreduce is not None:
+                self.allreduce(self.get_flat_grad()[:self.total])
+            else:
+                dist.all_reduce(self.get_flat_grad()[:self.total], op=dist.ReduceOp.SUM, group=self.group)
         self.launched.clear()
 
 
-def allreduce_module_grads(module: torch.nn.Module, world: int) -> None:
+def allreduce_module_grads(module: torch.nn.Module, world: int, allreduce=None) -> None:
     """Average the gradients of a stock PyTorch module (the critic) across ranks with one flat all-reduce."""
     if world == 1:
         return
     grads = [p.grad for p in module.parameters() if p.grad is not None]
     flat = torch._utils._flatten_dense_tensors(grads)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if allreduce is not None:
+        allreduce(flat)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat.div_(world)
     for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
         g.copy_(f)

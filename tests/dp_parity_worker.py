@@ -37,14 +37,18 @@ ref = tr.create_generator()
 ref.load_state_dict(tr.G.state_dict())
 ref_opt = FlatAdam(ref, lr=cfg.trainer.lr_g)
 l1 = L1ReconstructionLoss()
-tol = 2e-5 if dtype == "fp32" else 3e-2
+# Step 0 starts from identical weights: the all-reduced gradient must equal the single-process batch-8 gradient to fp32
+# round-off.  From step 1 on the two runs' weights differ in the last bits (a sum of two half-batch gradients vs one
+# batch-8 gradient), and a pre-activation within rounding of a ReLU kink can flip (tests/test_model_gpu.py's header), so
+# the later steps are held to the flip-tolerant bound.
+tol0, tol = (2e-5, 5e-3) if dtype == "fp32" else (3e-2, 3e-2)
 
 
 def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-for step in range(3):
+for step in range(5):    # steps 0-1 run eagerly (warm-up), step 2 is captured, steps 2-4 replay the step's CUDA graphs
     keep = step == 1                                      # step 1: gradients accumulate into / stay in the old tensors
     ref_opt.zero_grad(set_to_none=not keep)
     l1(ref(x, aux), gt).backward()
@@ -62,9 +66,9 @@ for step in range(3):
         tr.opt_g.zero_grad = orig
     got = tr.G.flat_grad / world                          # SUM all-reduce; the 1/world lives in the Adam kernel
     e = rel(got, ref_g)
-    assert e < tol, f"rank {rank} step {step}: DP gradient differs from the single-process batch-8 gradient: {e:.3e}"
+    assert e < (tol0 if step == 0 else tol), f"rank {rank} step {step}: DP gradient differs from the single-process batch-8 gradient: {e:.3e}"
     ew = rel(tr.G.flat_param, ref.flat_param)
-    assert ew < tol, f"rank {rank} step {step}: weights drifted from the single-process run: {ew:.3e}"
+    assert ew < (tol0 if step == 0 else tol), f"rank {rank} step {step}: weights drifted from the single-process run: {ew:.3e}"
     both = [torch.empty_like(tr.G.flat_param) for _ in range(world)]
     dist.all_gather(both, tr.G.flat_param)
     assert torch.equal(both[0], both[1]), f"step {step}: the ranks' weights are not bit-identical"

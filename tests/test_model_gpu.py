@@ -360,3 +360,56 @@ def test_device_prefetcher_yields_the_same_batches():
         ref = preprocess_host_batch(hb, torch.device(DEV))
         assert all(torch.equal(a, b) for a, b in zip(ref, gb))
     assert list(DevicePrefetcher([], torch.device(DEV))) == []
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_graph_replayed_train_step_is_bit_identical_to_eager(dtype):
+    """BaseTrainer.train_step replayed from CUDA graphs (two eager warm-up steps, capture, replays) == the same steps
+    launched eagerly: same kernels, same order, deterministic reductions -> identical losses and weights, and the launch
+    counters account for the replayed launches."""
+    from pixel_heal_thyself_b200 import _lib
+    from pixel_heal_thyself_b200.config import load_config
+    from pixel_heal_thyself_b200.models.afgsa.train import AFGSATrainer
+    cfg = load_config("dev", ["trainer.batch_size=4", f"model.afgsa.compute_dtype={dtype}"])
+    g = torch.Generator().manual_seed(11)
+    batches = [((torch.randn(4, 3, 32, 32, generator=g) * 0.5).to(DEV), (torch.randn(4, 3, 32, 32, generator=g) * 0.5).to(DEV),
+                torch.rand(4, 7, 32, 32, generator=g).to(DEV)) for _ in range(6)]
+    runs = {}
+    for graph in (False, True):
+        tr = AFGSATrainer(cfg)
+        tr.use_step_graph = graph
+        tr.setup(g_only=True)
+        _lib.lib.pht_reset_counters()
+        losses = [float(tr.train_step(n, gt, a)[0]) for (n, gt, a) in batches]
+        torch.cuda.synchronize()
+        if graph:
+            assert tr._step_graph is not None and tr._step_graph["rec"] is not None, "the step was not captured"
+            assert tr.opt_g.step_count == 6
+        runs[graph] = (losses, tr.G.flat_param.clone(), sum(_lib.counters().values()))
+        with torch.no_grad():                                  # an eager forward after replays sees the current weights
+            y = tr.G.eval()(batches[0][0], batches[0][2])
+        runs[graph] += (y,)
+    assert runs[False][0] == runs[True][0], (runs[False][0], runs[True][0])
+    assert torch.equal(runs[False][1], runs[True][1])
+    assert runs[False][2] == runs[True][2] > 0, (runs[False][2], runs[True][2])
+    assert torch.equal(runs[False][3], runs[True][3])
+
+
+def test_graph_replayed_full_gan_step_trains():
+    """The full iteration (generator + PyTorch critic with gradient penalty) captured as one graph: finite losses, both
+    networks move, and a G-only L1 evaluation improves over the steps like the eager trainer's."""
+    from pixel_heal_thyself_b200.config import load_config
+    from pixel_heal_thyself_b200.models.afgsa.train import AFGSATrainer
+    cfg = load_config("dev", ["trainer.batch_size=4"])
+    g = torch.Generator().manual_seed(12)
+    n, gt, a = ((torch.randn(4, 3, 32, 32, generator=g) * 0.5).to(DEV), (torch.randn(4, 3, 32, 32, generator=g) * 0.5).to(DEV),
+                torch.rand(4, 7, 32, 32, generator=g).to(DEV))
+    tr = AFGSATrainer(cfg)
+    tr.setup()
+    w0, d0 = tr.G.flat_param.clone(), next(tr.D.parameters()).detach().clone()
+    out = [tr.train_step(n, gt, a) for _ in range(8)]
+    torch.cuda.synchronize()
+    assert tr._step_graph is not None and tr._step_graph["rec"] is not None, "the GAN step was not captured"
+    assert all(math.isfinite(float(gl)) and math.isfinite(float(dl)) for gl, dl in out)
+    assert not torch.equal(w0, tr.G.flat_param) and not torch.equal(d0, next(tr.D.parameters()).detach())
+    assert float(out[-1][0]) < float(out[0][0]) + 0.5
