@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PHT_ABI_VERSION 1
+#define PHT_ABI_VERSION 2
 
 enum pht_status {
   PHT_OK = 0,
@@ -196,10 +196,13 @@ int pht_attn_fwd(const pht_attn_args* args, void* stream);
 /* Recompute-based backward of the op above (autograd of model.py:474-516):
  * given d_out, recomputes P from q, k, lse and produces dq, dk, dv (views in
  * the activations' dtype, OVERWRITTEN; the up-to-4 overlapping window
- * contributions of a key pixel are summed inside the op) and d_rel_h / d_rel_w
- * fp32 [win][d/2] (OVERWRITTEN).
- * workspace: pht_attn_bwd_workspace_bytes() bytes (window-major dK/dV scratch or
- * fp32 accumulators, plus the relative-position partial sums). */
+ * contributions of a key pixel are summed inside the op, in a fixed order) and
+ * d_rel_h / d_rel_w fp32 [win][d/2] (OVERWRITTEN).
+ * workspace: pht_attn_bwd_workspace_bytes() bytes (relative-position partial sums and
+ * per-block ordering flags; fp32 accumulators for the CUDA-core path).
+ * The tcgen05 path accumulates the window contributions straight into dk / dv with TMA reduce-adds, so they must be
+ * zero when the kernel starts: pht_attn_bwd does that itself unless `prezeroed` is set, in which case the caller has
+ * already run pht_attn_bwd_zero with the same arguments (e.g. on a side stream, overlapped with earlier kernels). */
 typedef struct pht_attn_bwd_args {
   pht_attn_args fwd;        /* q, k, v, rel_*, lse as in the forward; out/resid unused */
   pht_view d_out;
@@ -210,9 +213,12 @@ typedef struct pht_attn_bwd_args {
   float* d_rel_w;
   void* workspace;
   size_t workspace_bytes;
+  int32_t prezeroed;        /* 1: pht_attn_bwd_zero(args) has already been run for this launch */
+  int32_t pad_;
 } pht_attn_bwd_args;
 
 size_t pht_attn_bwd_workspace_bytes(const pht_attn_bwd_args* args);
+int pht_attn_bwd_zero(const pht_attn_bwd_args* args, void* stream);
 int pht_attn_bwd(const pht_attn_bwd_args* args, void* stream);
 
 /* Decoder tail: 3x3 conv 256->3 with ZERO padding, no activation, plus the
@@ -383,6 +389,8 @@ void pht_set_force_simple(int on);
  * tiles (fewer, fuller tiles); none of these three changes a result bit;
  * "conv_trace" = 1: CTA 0 of pht_conv_gemm records clock64 stamps per tile (diagnostics);
  * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics);
+ * "attn_ordered" = 0 / 1 (default 1): pht_attn_bwd adds the overlapping window contributions to dk / dv in a fixed
+ * order (bit-reproducible); 0 = first come, first added (A/B: the cost of the ordering);
  * "bf16_fallback" = 0 / 1 (default 0): a PHT_BF16 launch of pht_conv_gemm / pht_wgrad / pht_attn_fwd / pht_attn_bwd whose
  * shape or views the tcgen05 kernels do not take returns PHT_ERR_UNSUPPORTED instead of silently running the ~20x slower
  * CUDA-core kernel; 1 re-enables that fallback (pht_set_force_simple(1) always selects the CUDA-core kernels) */

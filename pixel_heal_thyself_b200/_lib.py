@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("PHT_LIB_PATH") or os.path.join(_PKG, "libpht_b200.so"
 PHT_F32, PHT_BF16 = 0, 1
 PAD_REPLICATE, PAD_REFLECT = 0, 1
 EPI_RESID_PRE, EPI_RESID_POST, EPI_MASK, EPI_PADFOLD = 1, 2, 4, 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 PAD_MODES = {"replicate": PAD_REPLICATE, "reflect": PAD_REFLECT}
 DTYPES = {torch.float32: PHT_F32, torch.bfloat16: PHT_BF16}
@@ -58,7 +58,7 @@ class AttnArgs(C.Structure):
 class AttnBwdArgs(C.Structure):
     _fields_ = [("fwd", AttnArgs), ("d_out", PhtView), ("dq", PhtView), ("dk", PhtView),
                 ("dv", PhtView), ("d_rel_h", C.c_void_p), ("d_rel_w", C.c_void_p), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_size_t)]
+                ("workspace_bytes", C.c_size_t), ("prezeroed", C.c_int32), ("pad_", C.c_int32)]
 
 
 class PackArgs(C.Structure):
@@ -88,6 +88,7 @@ SYMBOLS = {
     "pht_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pht_attn_bwd_workspace_bytes": (_sz, [C.POINTER(AttnBwdArgs)]),
     "pht_attn_bwd": (C.c_int, [C.POINTER(AttnBwdArgs), _vp]),
+    "pht_attn_bwd_zero": (C.c_int, [C.POINTER(AttnBwdArgs), _vp]),
     "pht_dec_tail_fwd": (C.c_int, [_PV, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pht_dec_tail_bwd_data": (C.c_int, [_vp, _vp, _PV, _PV, _i32, _i32, _i32, _vp]),
     "pht_dec_tail_ws_bytes": (_sz, [_i32, _i32, _i32, _i32]),

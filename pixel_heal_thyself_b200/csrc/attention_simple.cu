@@ -7,6 +7,7 @@ namespace pht {
 
 int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled);       // attention_tc.cu
 int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled);   // attention_tc.cu
+int attn_bwd_zero_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled);   // attention_tc.cu
 size_t attn_bwd_tc_ws_bytes(const pht_attn_args& f);                            // attention_tc.cu
 
 struct AttnP {
@@ -347,6 +348,16 @@ size_t pht_attn_bwd_workspace_bytes(const pht_attn_bwd_args* a) {
   size_t s = attn_bwd_simple_ws_bytes(a->fwd);
   size_t t = a->fwd.dtype == PHT_BF16 ? attn_bwd_tc_ws_bytes(a->fwd) : 0;
   return s > t ? s : t;
+}
+
+int pht_attn_bwd_zero(const pht_attn_bwd_args* a, void* stream) {
+  PHT_CHECK_ARG(a != nullptr, "attn_bwd_zero: null args");
+  if (a->fwd.dtype == PHT_BF16 && !force_simple()) {
+    bool handled = false;
+    int rc = attn_bwd_zero_tc(a, (cudaStream_t)stream, &handled);
+    if (rc) return rc;
+  }
+  return PHT_OK;   // (the CUDA-core path overwrites its outputs: nothing to prepare)
 }
 
 int pht_attn_bwd(const pht_attn_bwd_args* a, void* stream) {

@@ -488,14 +488,27 @@ class AfgsaEngine:
             lse = g(f"lse{i}", (B, H, W, self.heads), torch.float32)
             X = A.inner(g(f"Xp{i}", (B, H + 2, W + 2, C), T))
             # GX = d(block output) raw, G0 = d(H2 pre-act)
+            attn_args = (A.lo(QK, C), A.hi(QK, C), V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], lse, G2,
+                         A.lo(dQK, C), A.hi(dQK, C), dV, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws)
+            attn_kw = dict(heads=self.heads, block=self.block, halo=self.halo)
+            prezero = T == torch.bfloat16 and pair_ok
+            if prezero:
+                # the tcgen05 attention backward ACCUMULATES the window contributions into dK / dV: zero them on the
+                # second stream now, underneath the four feed-forward gradient GEMMs (tensor-bound, HBM mostly idle);
+                # every reader of the previous block's dQK / dV is already enqueued on the main stream
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(device=self.device)
+                self._side_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side_stream):
+                    ops.attn_bwd_zero(*attn_args, **attn_kw)
             conv3_wgrad(G0, H1p, pre + "feed_forward.1.0")
             conv3_dgrad(G0, pk[f"b{i}.ff1.T"], mask=A.inner(H1p), out2=G1)       # G1 = d(H1 pre-act)
             conv3_wgrad(G1, X1p, pre + "feed_forward.0.0")
             conv3_dgrad(G1, pk[f"b{i}.ff0.T"], resid=GX, out1=G2)                          # G2 = dX1 = dO
             # attention
-            ops.attn_bwd(A.lo(QK, C), A.hi(QK, C), V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], lse, G2,
-                         A.lo(dQK, C), A.hi(dQK, C), dV, G[pre + "attention.rel_h"], G[pre + "attention.rel_w"], attn_ws,
-                         heads=self.heads, block=self.block, halo=self.halo)
+            if prezero:
+                torch.cuda.current_stream().wait_stream(self._side_stream)
+            ops.attn_bwd(*attn_args, **attn_kw, prezeroed=prezero)
             wqk = tmp(2 * C * C).view(1, 2 * C, C)
             paired(lambda: wgrad(dQK, [M], wqk),
                    [lambda: wgrad(dV, [X], G[pre + "attention.v_conv.weight"])])

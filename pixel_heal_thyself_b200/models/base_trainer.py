@@ -254,6 +254,7 @@ class BaseTrainer(ABC):
                 after = list(_lib.raw_counters())
                 st["launches"] = (_lib.C.c_uint64 * 8)(*[a - b for a, b in zip(after, before)])
                 st["rec"] = rec
+                st["fresh"] = True          # (the capture itself already bumped the host-side launch counters once)
                 break
         st["noisy"].copy_(noisy)
         st["gt"].copy_(gt)
@@ -261,7 +262,8 @@ class BaseTrainer(ABC):
         self.opt_g.sync_lr()
         st["rec"].replay()
         self.G.mark_weights_dirty()                     # (the replayed Adam changed the weights behind Python's back)
-        _lib.lib.pht_add_counters(st["launches"])     # launch counters are bumped host-side: account for the replay
+        if st.pop("fresh", False) is False:
+            _lib.lib.pht_add_counters(st["launches"])  # launch counters are bumped host-side: account for the replay
         return st["g_loss"].clone(), (st["d_loss"].clone() if st["d_loss"] is not None else None)
 
     def _train_step_eager(self, noisy, gt, aux):

@@ -235,16 +235,30 @@ def attn_bwd_workspace_bytes(q, heads=4, block=8, halo=3) -> int:
     return int(lib.pht_attn_bwd_workspace_bytes(C.byref(a)))
 
 
-def attn_bwd(q, k, v, rel_h, rel_w, lse, d_out, dq, dk, dv, d_rel_h, d_rel_w, workspace, *, heads=4, block=8,
-             halo=3):
-    """dq / dk / dv: [B,H,W,C] views (activation dtype), overwritten with the final gradients."""
-    L.require_cuda(q, k, v, d_out, dq, dk, dv)
+def _attn_bwd_args(q, k, v, rel_h, rel_w, lse, d_out, dq, dk, dv, d_rel_h, d_rel_w, workspace, heads, block, halo):
     a = L.AttnBwdArgs()
     a.fwd = _attn_args(q, k, v, rel_h, rel_w, heads, block, halo, None, None, lse)
     a.d_out, a.dq = L.view(d_out), L.view(dq)
     a.dk, a.dv = L.view(dk), L.view(dv)
     a.d_rel_h, a.d_rel_w = d_rel_h.data_ptr(), d_rel_w.data_ptr()
     a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    return a
+
+
+def attn_bwd_zero(q, k, v, rel_h, rel_w, lse, d_out, dq, dk, dv, d_rel_h, d_rel_w, workspace, *, heads=4, block=8, halo=3):
+    """pht_attn_bwd_zero: zero dk / dv (and the ordering flags in the workspace) ahead of ``attn_bwd(..., prezeroed=True)``
+    with the same arguments; may run on another stream, overlapped with earlier kernels (nothing else is touched)."""
+    L.require_cuda(q, k, v, d_out, dq, dk, dv)
+    a = _attn_bwd_args(q, k, v, rel_h, rel_w, lse, d_out, dq, dk, dv, d_rel_h, d_rel_w, workspace, heads, block, halo)
+    L.check(lib.pht_attn_bwd_zero(C.byref(a), L.stream_ptr()), "pht_attn_bwd_zero")
+
+
+def attn_bwd(q, k, v, rel_h, rel_w, lse, d_out, dq, dk, dv, d_rel_h, d_rel_w, workspace, *, heads=4, block=8,
+             halo=3, prezeroed=False):
+    """dq / dk / dv: [B,H,W,C] views (activation dtype), overwritten with the final gradients."""
+    L.require_cuda(q, k, v, d_out, dq, dk, dv)
+    a = _attn_bwd_args(q, k, v, rel_h, rel_w, lse, d_out, dq, dk, dv, d_rel_h, d_rel_w, workspace, heads, block, halo)
+    a.prezeroed = 1 if prezeroed else 0
     L.check(lib.pht_attn_bwd(C.byref(a), L.stream_ptr()), "pht_attn_bwd")
 
 

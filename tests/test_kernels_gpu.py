@@ -528,3 +528,42 @@ def test_validation_metrics_match_reference_golden():
     assert M.image_metrics(ref_gt, ref_gt)[0] == 0.0          # mse == 0 -> 0.0 (metric.py:22-23)
     with pytest.raises(ValueError):
         M.image_metrics(ref_out, ref_gt[:, :-1])
+
+
+def test_attention_backward_window_accumulation_is_ordered_and_reproducible():
+    """The tcgen05 attention backward adds the <= 4 overlapping 14x14-window contributions of a key pixel into dK / dV
+    with TMA reduce-adds in a FIXED order (option "attn_ordered", default on): two runs are bit-identical, at a size
+    where every CTA walks several blocks (8 x 128 x 128 = 2048 blocks on 148 CTAs) and with dK living in a channel
+    slice of a wider buffer (the engine's [dQ | dK] layout).  With the ordering off the values still agree to bf16
+    rounding of the partial sums."""
+    ops = _ops()
+    from pixel_heal_thyself_b200 import _lib
+    B, C, H, W = 8, 256, 128, 128
+    torch.manual_seed(9)
+    mk = lambda s=1.0: (torch.randn(B, H, W, C, device=DEV) * s).to(torch.bfloat16)
+    q, k, v, do = mk(0.3), mk(0.3), mk(), mk()
+    rel_h, rel_w = torch.randn(1, 14, 1, 32, device=DEV), torch.randn(1, 1, 14, 32, device=DEV)
+    out = torch.empty_like(q)
+    lse = torch.empty(B, H, W, 4, device=DEV)
+    ops.attn_fwd(q, k, v, rel_h, rel_w, out, lse=lse)
+    ws = torch.empty(max(ops.attn_bwd_workspace_bytes(q), 16) // 4, device=DEV)
+
+    def run():
+        dqk = torch.full((B, H, W, 2 * C), float("nan"), device=DEV, dtype=torch.bfloat16)
+        dv = torch.full((B, H, W, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+        drh, drw = torch.empty_like(rel_h), torch.empty_like(rel_w)
+        ops.attn_bwd(q, k, v, rel_h, rel_w, lse, do, dqk[..., :C], dqk[..., C:], dv, drh, drw, ws)
+        torch.cuda.synchronize()
+        return dqk, dv, drh, drw
+
+    a, b = run(), run()
+    for x, y in zip(a, b):
+        assert torch.isfinite(x.float()).all()
+        assert torch.equal(x, y)
+    assert _lib.lib.pht_set_option(b"attn_ordered", 0) == 0
+    try:
+        c = run()
+    finally:
+        _lib.lib.pht_set_option(b"attn_ordered", 1)
+    for x, y in zip(a, c):
+        assert rel_err(y, x) < 2e-2

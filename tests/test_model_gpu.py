@@ -365,8 +365,9 @@ def test_device_prefetcher_yields_the_same_batches():
 @pytest.mark.parametrize("dtype", ["bf16", "fp32"])
 def test_graph_replayed_train_step_is_bit_identical_to_eager(dtype):
     """BaseTrainer.train_step replayed from CUDA graphs (two eager warm-up steps, capture, replays) == the same steps
-    launched eagerly: same kernels, same order, deterministic reductions -> identical losses and weights, and the launch
-    counters account for the replayed launches."""
+    launched eagerly: same kernels in the same order.  The bf16 production path is deterministic (fixed-order reductions
+    everywhere), so losses and weights are bit-identical; the fp32 parity path's CUDA-core weight-gradient / attention
+    kernels accumulate with atomics, so it is held to fp32 round-off.  The launch counters account for the replays."""
     from pixel_heal_thyself_b200 import _lib
     from pixel_heal_thyself_b200.config import load_config
     from pixel_heal_thyself_b200.models.afgsa.train import AFGSATrainer
@@ -389,10 +390,15 @@ def test_graph_replayed_train_step_is_bit_identical_to_eager(dtype):
         with torch.no_grad():                                  # an eager forward after replays sees the current weights
             y = tr.G.eval()(batches[0][0], batches[0][2])
         runs[graph] += (y,)
-    assert runs[False][0] == runs[True][0], (runs[False][0], runs[True][0])
-    assert torch.equal(runs[False][1], runs[True][1])
+    if dtype == "bf16":
+        assert runs[False][0] == runs[True][0], (runs[False][0], runs[True][0])
+        assert torch.equal(runs[False][1], runs[True][1])
+        assert torch.equal(runs[False][3], runs[True][3])
+    else:
+        assert max(abs(a - b) / b for a, b in zip(runs[False][0], runs[True][0])) < 1e-5, (runs[False][0], runs[True][0])
+        assert float((runs[False][1] - runs[True][1]).norm() / runs[True][1].norm()) < 1e-5
+        assert float((runs[False][3] - runs[True][3]).abs().max() / runs[True][3].abs().max()) < 1e-4
     assert runs[False][2] == runs[True][2] > 0, (runs[False][2], runs[True][2])
-    assert torch.equal(runs[False][3], runs[True][3])
 
 
 def test_graph_replayed_full_gan_step_trains():
@@ -406,6 +412,7 @@ def test_graph_replayed_full_gan_step_trains():
                 torch.rand(4, 7, 32, 32, generator=g).to(DEV))
     tr = AFGSATrainer(cfg)
     tr.setup()
+    tr.G._flatten()
     w0, d0 = tr.G.flat_param.clone(), next(tr.D.parameters()).detach().clone()
     out = [tr.train_step(n, gt, a) for _ in range(8)]
     torch.cuda.synchronize()
