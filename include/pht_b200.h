@@ -196,13 +196,14 @@ int pht_attn_fwd(const pht_attn_args* args, void* stream);
 /* Recompute-based backward of the op above (autograd of model.py:474-516):
  * given d_out, recomputes P from q, k, lse and produces dq, dk, dv (views in
  * the activations' dtype, OVERWRITTEN; the up-to-4 overlapping window
- * contributions of a key pixel are summed inside the op, in a fixed order) and
+ * contributions of a key pixel are summed inside the op) and
  * d_rel_h / d_rel_w fp32 [win][d/2] (OVERWRITTEN).
- * workspace: pht_attn_bwd_workspace_bytes() bytes (relative-position partial sums and
- * per-block ordering flags; fp32 accumulators for the CUDA-core path).
- * The tcgen05 path accumulates the window contributions straight into dk / dv with TMA reduce-adds, so they must be
- * zero when the kernel starts: pht_attn_bwd does that itself unless `prezeroed` is set, in which case the caller has
- * already run pht_attn_bwd_zero with the same arguments (e.g. on a side stream, overlapped with earlier kernels). */
+ * workspace: pht_attn_bwd_workspace_bytes() bytes (relative-position partial sums; window-major dK/dV scratch when the
+ * "attn_bwd_direct" option is 0; fp32 accumulators for the CUDA-core path).
+ * With "attn_bwd_direct" = 1 (default) the tcgen05 path accumulates the window contributions straight into dk / dv
+ * with vector reductions, so they must be zero when the kernel starts: pht_attn_bwd does that itself unless `prezeroed`
+ * is set, in which case the caller has already run pht_attn_bwd_zero with the same arguments (e.g. on a side stream,
+ * overlapped with earlier kernels). */
 typedef struct pht_attn_bwd_args {
   pht_attn_args fwd;        /* q, k, v, rel_*, lse as in the forward; out/resid unused */
   pht_view d_out;
@@ -240,6 +241,16 @@ int pht_dec_tail_bwd_weight(const float* dout_nchw, const pht_view* h, float* dw
  * grad[i] = grad_scale * sign(a[i]-b[i]) / n  (grad may be NULL).  The block partials of the deterministic
  * two-level reduction live in library scratch private to (device, stream): launches on different streams may overlap. */
 int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, float* loss, float* grad, void* stream);
+
+/* Optional MS-SSIM + L1 image loss, fused forward + backward (SSIMLoss, losses.py:248-263, used at
+ * base_trainer.py:450-452 with weight 0.1): per-pixel scale = max(channel-max of gt, 1); kornia 0.8.0
+ * MS_SSIMLoss(reduction="mean") arithmetic on out / scale, gt / scale (kornia is a third-party dependency that is not
+ * vendored with the reference: PARITY UNPINNED, the checker is oracle/msssim_oracle.py).  out / gt: fp32 NCHW
+ * [B][3][H][W]; loss[0] OVERWRITTEN; grad (may be NULL) = grad_scale * d loss / d out, fp32 NCHW, OVERWRITTEN.
+ * workspace >= pht_msssim_ws_bytes(B, H, W), 16-byte aligned. */
+size_t pht_msssim_ws_bytes(int32_t B, int32_t H, int32_t W);
+int pht_msssim_loss(const float* out_nchw, const float* gt_nchw, int32_t B, int32_t H, int32_t W, float grad_scale, float* loss,
+                    float* grad, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Batch preprocessing (base_trainer.py:373-383; preprocessing.py:19-22,34-38):
  * NHWC fp32 patches -> NCHW fp32: noisy/gt = log(v+1); aux[0:3] =
@@ -389,8 +400,11 @@ void pht_set_force_simple(int on);
  * tiles (fewer, fuller tiles); none of these three changes a result bit;
  * "conv_trace" = 1: CTA 0 of pht_conv_gemm records clock64 stamps per tile (diagnostics);
  * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics);
- * "attn_ordered" = 0 / 1 (default 1): pht_attn_bwd adds the overlapping window contributions to dk / dv in a fixed
- * order (bit-reproducible); 0 = first come, first added (A/B: the cost of the ordering);
+ * "attn_bwd_direct" = 0 / 1 (default 1): 1 = the tcgen05 pht_attn_bwd adds the (up to four) overlapping window
+ * contributions of a key pixel straight into dk / dv with vector reductions, in arrival order (fastest; every add rounds
+ * to bf16, so the last bits depend on the order: not bit-reproducible from run to run); 0 = window-major bf16 scratch + a
+ * fold kernel that sums them in a fixed order in fp32 (bit-reproducible; needs the larger workspace that
+ * pht_attn_bwd_workspace_bytes reports while the option is 0);
  * "bf16_fallback" = 0 / 1 (default 0): a PHT_BF16 launch of pht_conv_gemm / pht_wgrad / pht_attn_fwd / pht_attn_bwd whose
  * shape or views the tcgen05 kernels do not take returns PHT_ERR_UNSUPPORTED instead of silently running the ~20x slower
  * CUDA-core kernel; 1 re-enables that fallback (pht_set_force_simple(1) always selects the CUDA-core kernels) */

@@ -124,6 +124,9 @@ class AFGSAModelConfig:
     losses: LossesConfig = field(default_factory=LossesConfig)
     self_attention: SelfAttentionConfig = field(default_factory=SelfAttentionConfig)
     compute_dtype: str = "bf16"
+    # bit-reproducible attention backward (window-major scratch + fixed-order fold) instead of the default arrival-order
+    # vector reductions into dK / dV (library option "attn_bwd_direct"; process-wide)
+    reproducible_attention_backward: bool = False
 
 
 @dataclass

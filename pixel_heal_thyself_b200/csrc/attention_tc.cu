@@ -503,33 +503,37 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
 //   dV = P^T dO, dK = dS^T Q             (A operands MN-major: the [query x key] tiles are read transposed)
 //   dREL = sum over the CTA's iterations of dK, accumulated in fp32 registers by the read-out threads (its
 //          window-row / window-column sums are d rel_h / d rel_w)
-// Warps: 0 TMA producer, 1 MMA issuer, 2..9 softmax + read-out, 10 dK / dV reduce-store.  Two warps share each TMEM sub-partition: they split
+// Warps: 0 TMA producer, 1 MMA issuer, 2..9 softmax + read-out.  Two warps share each TMEM sub-partition: they split
 // the S / dP columns of a query row between them (partial deltas exchanged through smem) and the dV / dK key tiles.
 // Pipeline: the operands of iteration i+1 are prefetched (Q, dO, K double-buffered; V reloaded as soon as dP(i) is
 // done), S/dP(i+1) is issued right behind dQ/dV/dK(i) on the tensor pipe, and the dV/dK read-out of iteration i
 // runs while S/dP(i+1) is being computed.  TMEM: S [0,104) dP [104,208) (dQ re-uses [0,64)), dV [208,336), dK [336,464).
-// dK / dV: every (block, head) iteration stages its 14x14-window x 64-channel contribution as one bf16 smem tile (the
-// TMA box layout) and ADDS it into the final NHWC gradient with one TMA reduce (cp.reduce.async.bulk.tensor .add, the
-// read-modify-write happens in L2; the part of the window outside the image is clipped by the tensor map).  The <= 4
-// overlapping windows of a key pixel are added in a FIXED order -- priority (iteration index of the block in its CTA,
-// then the parity colour (by & 1, bx & 1)): a block issues its reduce only after the 8-neighbours that precede it have
-// published theirs (per-block head counters in global memory, release / acquire) -- so the bf16 result is bit-reproducible.
-// The outputs must be zero when the kernel starts (attn_bwd_zero_tc).  No window-major scratch, no fold kernel.
+// dK / dV: every read-out warp transposes its 32 key rows x 32 channels through a small smem tile so that each memory
+// instruction covers eight complete 64-byte row segments, and then either
+//   P.direct = 1 (default)  ADDS them straight into the final NHWC gradient with vector reductions
+//                (red.global.add.noftz.v4.bf16x2; the read-modify-write happens in L2, window pixels outside the image are
+//                skipped; the outputs are zeroed beforehand, attn_bwd_zero_tc).  No scratch, no second pass.  The <= 4
+//                overlapping windows of a key pixel are added in arrival order, each add rounding to bf16: the result
+//                is NOT bit-reproducible from run to run (it differs by the rounding order of at most four terms);
+//   P.direct = 0 ("attn_bwd_direct" = 0, the bit-reproducible mode) stores them window-major in a bf16 scratch and a fold
+//                kernel sums the <= 4 windows of every pixel in a fixed order in fp32 (round 1's scheme).
+// Tried and dropped (measured, see profiles/README.md): the direct adds in a FIXED order (per-block flags in global
+// memory, priority = (iteration, parity colour), polled / published by helper warps): the GPU-scope fence + flag
+// round trip costs ~4 us per (head, tensor) against a 3.7 us iteration -- 566 us per layer; and one TMA reduce
+// (cp.reduce.async.bulk.tensor .add on a bf16 tensor map) per window tile, which faults ("illegal instruction") here.
 // =================================================================================================
 #ifndef PHT_AB_DK_EARLY
 #define PHT_AB_DK_EARLY 0
 #endif
 constexpr bool AB_DK_EARLY = PHT_AB_DK_EARLY != 0;   // A/B: dK rows read out right behind the dV rows (under S/dP(i+1)) instead of behind the next softmax
-constexpr int AB_THREADS = 352;
+constexpr int AB_THREADS = 320;
 constexpr int AB_HALF = 104;                                    // keys per lane half (2 x 104 = 208 >= 196)
 constexpr int AB_ROWS = 2 * AB_HALF;                            // K / V / REL tile rows
 constexpr int AB_Q_BYTES = 8192, AB_K_BYTES = AB_ROWS * 128;
 constexpr int AB_P_BYTES = 4 * 8192, AB_DS_BYTES = 4 * 8192;
 constexpr int AB_STAGE_BYTES = 2 * AB_Q_BYTES + AB_K_BYTES;     // Q, dO, K
-constexpr int AB_TILE_BYTES = 25 * 1024;                         // dV / dK window tile [196 keys][64 ch] bf16 (25088 B), 128B-swizzled TMA box
-// (no alignment slack: the dynamic shared memory base of a kernel without static shared memory is 1024-byte aligned on
-// sm_100; the kernel traps if it ever is not)
-constexpr int AB_SMEM = 2 * AB_STAGE_BYTES + 2 * AB_K_BYTES + AB_P_BYTES + AB_DS_BYTES + AB_TILE_BYTES + 1024;
+constexpr int AB_STG_BYTES = 32 * 64;                            // per-warp read-out staging tile: 32 key rows x 32 ch bf16
+constexpr int AB_SMEM = 2 * AB_STAGE_BYTES + 2 * AB_K_BYTES + AB_P_BYTES + AB_DS_BYTES + 8 * AB_STG_BYTES + 1024 + 1024;
 static_assert(AB_SMEM <= 232448, "attn_bwd_tc: shared memory budget");
 constexpr int AB_COL_DP = AB_HALF, AB_COL_DQ = 0, AB_COL_DV = 2 * AB_HALF, AB_COL_DK = 2 * AB_HALF + 128;
 static_assert(AB_COL_DK + 128 <= 512, "attn_bwd_tc: TMEM budget");
@@ -538,30 +542,15 @@ constexpr int AB_REL_PART = AT_NK * 64;  // floats per CTA partial: dREL [196 ke
 
 struct AbP {
   int B, H, W, nbx, nby, nblocks, trace;
-  int ordered;        // 1: overlapping windows are added in a fixed order (bit-reproducible); 0: first come, first added
-  int dkOx, dkOy, dvOx, dvOy;
-  View dq;
+  int direct;         // 1: vector reductions straight into dk / dv; 0: window-major scratch + fold kernel
+  View dq, dk, dv;
   const float* rel_h;
   const float* rel_w;
   const float* lse;
-  unsigned* flags;    // [nblocks] heads whose dK / dV reduces have completed (zero at kernel start)
+  bf16* dk_scratch;   // [nblocks][4][196][64] (direct == 0)
+  bf16* dv_scratch;
   float* rel_part;    // [gridDim.x][196][64]
 };
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// smem tile (TMA box layout) += into the tensor: the reduction is performed in L2, out-of-range box parts are skipped
-__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 
 __device__ __forceinline__ void st_row32_bf16(bf16* dst, const uint32_t* r) {
 #pragma unroll
@@ -576,21 +565,16 @@ __device__ __forceinline__ void st_row32_bf16(bf16* dst, const uint32_t* r) {
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                   const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, const AbP P) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  if (smem_u32(smem_raw) & 1023u) {   // SWIZZLE_128B tiles need 1024-byte aligned bases (see AB_SMEM)
-    if (threadIdx.x == 0) printf("pht_b200: attn_bwd_tc dynamic shared memory base is not 1024-byte aligned\n");
-    __trap();
-  }
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AbP P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the .shared address space
   uint8_t* St = smem;                                   // [2 stages][Q 8K | dO 8K | K 26K]
   uint8_t* RELs = St + 2 * AB_STAGE_BYTES;
   uint8_t* Vs = RELs + AB_K_BYTES;
   uint8_t* Ps = Vs + AB_K_BYTES;
   uint8_t* dSs = Ps + AB_P_BYTES;
-  uint8_t* TILE = dSs + AB_DS_BYTES;                     // [196 keys][64 ch] bf16: dV, then dK, of the iteration
-  float* dpart = reinterpret_cast<float*>(TILE + AB_TILE_BYTES);   // [2 parts][64 queries] partial deltas
+  uint8_t* STG = dSs + AB_DS_BYTES;                      // [8 warps][32 rows x 64 B]
+  float* dpart = reinterpret_cast<float*>(STG + 8 * AB_STG_BYTES);   // [2 parts][64 queries] partial deltas
   uint64_t* bars = reinterpret_cast<uint64_t*>(dpart + 128);
   uint64_t* qk_full = bars + 0;    // [2]
   uint64_t* qk_empty = bars + 2;   // [2]
@@ -602,9 +586,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* dq_free = bars + 9;
   uint64_t* out_full = bars + 10;
   uint64_t* dvk_free = bars + 11;
-  uint64_t* tile_full = bars + 12;   // 256 arrivals: the read-out threads have written their rows of the dV / dK tile
-  uint64_t* tile_free = bars + 13;   // the reduce-store has finished reading the tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time smem constants that need no global memory ----------------------------------------------------
@@ -620,10 +602,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
     prefetch_tmap(&tmDO);
-    prefetch_tmap(&tmDK);
-    prefetch_tmap(&tmDV);
-    mbar_init(tile_full, 256);
-    mbar_init(tile_free, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&qk_full[s], 1);
       mbar_init(&qk_empty[s], 1);
@@ -764,55 +742,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
-  } else if (warp == 10) {
-    // ================================ dV / dK reduce-store ================================
-    if (lane == 0) {
-      const int G = (int)gridDim.x;
-      int nb[8], n_nb = 0;
-      for (int it = 0; it < n_it; ++it) {
-        const int blk = blockIdx.x + (it >> 2) * G, head = it & 3;
-        const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
-        if (head == 0 && P.ordered) {   // the neighbours whose windows overlap this one and that go first
-          n_nb = 0;
-          const int kx = blk / G, cx = ((by & 1) << 1) | (bx & 1);
-          for (int dy = -1; dy <= 1; ++dy)
-            for (int dx = -1; dx <= 1; ++dx) {
-              const int yy = by + dy, xx = bx + dx;
-              if ((dy | dx) == 0 || yy < 0 || yy >= P.nby || xx < 0 || xx >= P.nbx) continue;
-              const int o = blk + dy * P.nbx + dx, ko = o / G, co = ((yy & 1) << 1) | (xx & 1);
-              if (ko < kx || (ko == kx && co < cx)) nb[n_nb++] = o;
-            }
-        }
-        for (int w = 0; w < 2; ++w) {   // 0: dV tile, 1: dK tile
-          mbar_wait(tile_full, (2 * it + w) & 1);
-          if (w == 0 && P.ordered) {
-            for (int j = 0; j < n_nb; ++j) {
-              const unsigned* f = P.flags + nb[j];
-              if (ld_acquire_u32(f) > (unsigned)head) continue;
-              const long long t0 = clock64();
-              while (ld_acquire_u32(f) <= (unsigned)head) {
-                if (clock64() - t0 > 4000000000ll) {
-                  printf("pht_b200: attn_bwd_tc neighbour-order wait timed out (block %d waits for %d)\n", blk, nb[j]);
-                  __trap();
-                }
-              }
-            }
-            fence_proxy_async();   // the neighbours' reduces (acquired above) are ordered before the ones issued below
-          }
-          if (w == 0) tma_reduce_add_4d(&tmDV, TILE, head * 64, bx * 8 - 3 + P.dvOx, by * 8 - 3 + P.dvOy, b);
-          else tma_reduce_add_4d(&tmDK, TILE, head * 64, bx * 8 - 3 + P.dkOx, by * 8 - 3 + P.dkOy, b);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the tile may be overwritten
-          mbar_arrive(tile_free);
-        }
-        if (P.ordered) {
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // both reduces of this head are performed
-          fence_proxy_async();
-          st_release_u32(P.flags + blk, (unsigned)head + 1u);
-        }
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // everything written before the CTA exits
-    }
   } else {
     // ================================ softmax / dS / read-out (warps 2..9) ================================
     const int sp = warp & 3;                     // TMEM sub-partition of this warp
@@ -832,10 +761,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       goff[g] = (uint32_t)((key0 >> 6) * 8192 + ((((key0 & 63) >> 3) ^ qsw) * 16));
     }
     const int row0 = part * 128 + sp * 32;            // first key row of dV / dK read out by this warp
-    const int krow = row0 + lane;                     // this thread's key row (window position wy * 14 + wx)
-    const bool row_valid = krow < AT_NK;
-    const uint32_t tile_row = smem_u32(TILE) + krow * 128;
-    const int tsw = krow & 7;
+    const bool rows_valid = row0 < AT_NK;             // warp-uniform (the last warp's rows are all padding)
+    uint8_t* stage = STG + (warp - 2) * AB_STG_BYTES; // [32 rows][64 B] bf16, 64B-swizzled
+    const uint32_t stage_row = smem_u32(stage) + lane * 64;
+    const int ssw = (lane >> 1) & 3;
     float racc[64];                                   // dREL row accumulator (== sum of this thread's dK rows)
 #pragma unroll
     for (int j = 0; j < 64; ++j) racc[j] = 0.f;
@@ -919,20 +848,46 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     };
 
-    // read-out helper: 32 channels (64 B) of this thread's dV / dK key row -> the window tile (row = key, the 16-byte
-    // chunk index XOR-swizzled with the row like a 128B-swizzled TMA box)
-    auto tile_store = [&](const uint32_t* r, int ch0) {
-      if (row_valid) {
+    // (block, head) -> coordinates; the block index only changes every 4th iteration
+    int cbx = 0, cby = 0, cb = 0;
+    auto coords = [&](int it) {
+      const int blk = blockIdx.x + (it >> 2) * gridDim.x;
+      cbx = blk % P.nbx; cby = (blk / P.nbx) % P.nby; cb = blk / (P.nbx * P.nby);
+    };
+    // read-out helper: one 32-column chunk of this warp's dV / dK rows (thread = key row) is transposed through a
+    // swizzled 2 KB smem tile so that every reduction instruction covers eight complete 64-byte row segments of the
+    // NHWC gradient (a row-per-thread access would touch 32 different lines per instruction)
+    auto stage_red = [&](const uint32_t* r, const View& o, bf16* scratch, int zrow, int bx, int by, int b, int ch) {
+      if (rows_valid) {
+        __syncwarp();                            // the previous chunk's reads of the tile are done
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          st_shared_v4(tile_row + ((((ch0 >> 3) + g) ^ tsw) * 16), pack_bf16x2(__uint_as_float(r[g * 8]), __uint_as_float(r[g * 8 + 1])),
+          st_shared_v4(stage_row + ((g ^ ssw) * 16), pack_bf16x2(__uint_as_float(r[g * 8]), __uint_as_float(r[g * 8 + 1])),
                        pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
                        pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])),
                        pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2);    // tile row handled by this lane in pass i
+          const int key = row0 + rr, wy = key / 14, wx = key - wy * 14;
+          const int y = by * 8 - 3 + wy, x = bx * 8 - 3 + wx;
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(smem_u32(stage) + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4)));
+          if (!P.direct) {   // window-major scratch [block * 4 + head][key][64]
+            if (key < AT_NK)
+              *reinterpret_cast<uint4*>(scratch + ((long long)zrow * AT_NK + key) * 64 + (ch & 63) + (lane & 3) * 8) = v;
+          } else if (key < AT_NK && (unsigned)y < (unsigned)P.H && (unsigned)x < (unsigned)P.W) {
+            bf16* dst = (bf16*)o.ptr + view_off(o, b, y + o.oy, x + o.ox) + ch + (lane & 3) * 8;
+            asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};"
+                         ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+          }
+        }
       }
     };
-    // dK rows of iteration `it` (+ dREL accumulation); releases the dV / dK columns to the MMA warp
-    auto readout_dk = [&](int it, int it_dbg) {
+    // dK rows of a finished iteration (+ dREL accumulation); releases the dV / dK columns to the MMA warp
+    auto readout_dk = [&](int zrow, int head, int bx, int by, int b, int it_dbg) {
       uint32_t a[32], c[32];
       tmem_ld32(lane_addr + AB_COL_DK + part * 64, a);
       tmem_ld_wait();
@@ -940,25 +895,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld32(lane_addr + AB_COL_DK + part * 64 + 32, c);
 #pragma unroll
       for (int j = 0; j < 32; ++j) racc[j] += __uint_as_float(a[j]);
-      mbar_wait(tile_free, ((2 * it + 1) & 1) ^ 1);   // the dV tile of this iteration has been read by the reduce-store
-      tile_store(a, 0);
+      stage_red(a, P.dk, P.dk_scratch, zrow, bx, by, b, head * 64);
       stamp(it_dbg, 6);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dvk_free);
 #pragma unroll
       for (int j = 0; j < 32; ++j) racc[32 + j] += __uint_as_float(c[j]);
-      tile_store(c, 32);
-      fence_proxy_async();
-      mbar_arrive(tile_full);
+      stage_red(c, P.dk, P.dk_scratch, zrow, bx, by, b, head * 64 + 32);
     };
 
-    // (block, head) -> coordinates; the block index only changes every 4th iteration
-    int cbx = 0, cby = 0, cb = 0;
-    auto coords = [&](int it) {
-      const int blk = blockIdx.x + (it >> 2) * gridDim.x;
-      cbx = blk % P.nbx; cby = (blk / P.nbx) % P.nby; cb = blk / (P.nbx * P.nby);
-    };
+    int pz = 0, phead = 0, pbx = 0, pby = 0, pb = 0;   // the iteration whose dK rows are still to be read out
     if (n_it > 0) coords(0);
     for (int it = 0; it < n_it; ++it) {
       const int blk = blockIdx.x + (it >> 2) * gridDim.x, head = it & 3;
@@ -975,7 +922,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       stamp(it, 3);
       // While the tensor core computes dQ(it): the deferred half of the previous iteration's read-out (dK rows), the
       // next iteration's coordinates and lse.  dV/dK(it) are issued behind dQ(it) and wait for dvk_free.
-      if (!AB_DK_EARLY && it > 0) readout_dk(it - 1, it);
+      if (!AB_DK_EARLY && it > 0) readout_dk(pz, phead, pbx, pby, pb, it);
       stamp(it, 10);
       if (it + 1 < n_it) {
         if (((it + 1) & 3) == 0) coords(it + 1);
@@ -993,7 +940,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_arrive(dq_free);
         if (hf == 0) st_row32_bf16((bf16*)P.dq.ptr + view_off(P.dq, b, by * 8 + qy, bx * 8 + qx) + head * 64 + part * 32, a);
       }
-      // ---- read-out: dV rows -> the window tile -> TMA reduce-add into the NHWC gradient by warp 10 (the dK rows
+      // ---- read-out: dV rows -> 64B-swizzled smem tile -> vector reductions into the NHWC gradient (the dK rows
       //      follow after the next softmax) ----
       mbar_wait(out_full, it & 1);
       tc_fence_after();
@@ -1003,18 +950,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(lane_addr + AB_COL_DV + part * 64, a);
         tmem_ld_wait();
         tmem_ld32(lane_addr + AB_COL_DV + part * 64 + 32, c);
-        mbar_wait(tile_free, ((2 * it) & 1) ^ 1);     // the dK tile of the previous iteration has been read
-        tile_store(a, 0);
+        stage_red(a, P.dv, P.dv_scratch, blk * 4 + head, bx, by, b, head * 64);
         tmem_ld_wait();
-        tile_store(c, 32);
-        fence_proxy_async();
-        mbar_arrive(tile_full);
+        stage_red(c, P.dv, P.dv_scratch, blk * 4 + head, bx, by, b, head * 64 + 32);
       }
-      if (AB_DK_EARLY) readout_dk(it, it + 1);
+      pz = blk * 4 + head; phead = head; pbx = bx; pby = by; pb = b;
+      if (AB_DK_EARLY) readout_dk(pz, phead, pbx, pby, pb, it + 1);
     }
-    if (!AB_DK_EARLY && n_it > 0) readout_dk(n_it - 1, AB_TRACE_ITERS);
+    if (!AB_DK_EARLY && n_it > 0) readout_dk(pz, phead, pbx, pby, pb, AB_TRACE_ITERS);
     // relative-position gradient partial of this CTA
-    const int rkey = krow;
+    const int rkey = row0 + lane;
     if (rkey < AT_NK) {
       float4* dst = reinterpret_cast<float4*>(P.rel_part + (long long)blockIdx.x * AB_REL_PART + rkey * 64);
 #pragma unroll
@@ -1029,8 +974,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-// zero the dK / dV outputs (any strided NHWC view, 16 bytes per thread) and the per-block order flags
-__global__ void attn_bwd_zero_kernel(View dk, View dv, int B, int H, int W, int C, unsigned* __restrict__ flags, int nflags) {
+// zero the dK / dV outputs (any strided NHWC view, 16 bytes per thread): the direct mode accumulates into them
+__global__ void attn_bwd_zero_kernel(View dk, View dv, int B, int H, int W, int C) {
   const int cv = C / 8;
   const long long per = (long long)B * H * W * cv, total = 2 * per;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1043,7 +988,52 @@ __global__ void attn_bwd_zero_kernel(View dk, View dv, int B, int H, int W, int 
     const int y = (int)(r % H), b = (int)(r / H);
     *reinterpret_cast<uint4*>((bf16*)v.ptr + view_off(v, b, y + v.oy, x + v.ox) + c) = make_uint4(0, 0, 0, 0);
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nflags; i += gridDim.x * blockDim.x) flags[i] = 0u;
+}
+
+// sum the (up to 4) window-major contributions of every key pixel; one thread per (pixel, head, 8 channels)
+__global__ void attn_bwd_fold_kernel(const bf16* __restrict__ dks, const bf16* __restrict__ dvs, View dk, View dv, int B,
+                                     int H, int W, int nby, int nbx) {
+  long long total = (long long)B * H * W * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i & 7), head = (int)((i >> 3) & 3);
+    long long p = i >> 5;
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H), b = (int)(p / H);
+    float ak[8], av[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ak[j] = av[j] = 0.f;
+    const int by0 = y >> 3, bx0 = x >> 3;
+    for (int by = by0 - 1; by <= by0 + 1; ++by) {
+      const int wy = y - (by * 8 - 3);
+      if (by < 0 || by >= nby || wy < 0 || wy >= 14) continue;
+      for (int bx = bx0 - 1; bx <= bx0 + 1; ++bx) {
+        const int wx = x - (bx * 8 - 3);
+        if (bx < 0 || bx >= nbx || wx < 0 || wx >= 14) continue;
+        const long long off = (((((long long)b * nby + by) * nbx + bx) * 4 + head) * AT_NK + wy * 14 + wx) * 64 + cg * 8;
+        const uint4 uk = *reinterpret_cast<const uint4*>(dks + off);
+        const uint4 uv = *reinterpret_cast<const uint4*>(dvs + off);
+        const __nv_bfloat162* hk = reinterpret_cast<const __nv_bfloat162*>(&uk);
+        const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&uv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fk = __bfloat1622float2(hk[j]), fv = __bfloat1622float2(hv[j]);
+          ak[2 * j] += fk.x; ak[2 * j + 1] += fk.y;
+          av[2 * j] += fv.x; av[2 * j + 1] += fv.y;
+        }
+      }
+    }
+    uint4 ok, ov;
+    __nv_bfloat162* hk = reinterpret_cast<__nv_bfloat162*>(&ok);
+    __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hk[j] = __floats2bfloat162_rn(ak[2 * j], ak[2 * j + 1]);
+      hv[j] = __floats2bfloat162_rn(av[2 * j], av[2 * j + 1]);
+    }
+    *reinterpret_cast<uint4*>((bf16*)dk.ptr + view_off(dk, b, y, x) + head * 64 + cg * 8) = ok;
+    *reinterpret_cast<uint4*>((bf16*)dv.ptr + view_off(dv, b, y, x) + head * 64 + cg * 8) = ov;
+  }
 }
 
 // d rel_h[r][j] = sum_parts sum_c dREL[(r,c)][j] (j < 32);  d rel_w[c][j] = sum_parts sum_r dREL[(r,c)][32 + j].
@@ -1076,15 +1066,15 @@ static int at_grid(int nblocks) {
   const int sms = sm_count();
   return nblocks < sms ? nblocks : sms;
 }
+static std::atomic<int> g_attn_bwd_direct{1};
+void set_attn_bwd_direct(int v) { g_attn_bwd_direct.store(v ? 1 : 0, std::memory_order_relaxed); }
 
-static std::atomic<int> g_attn_ordered{1};
-void set_attn_ordered(int v) { g_attn_ordered.store(v ? 1 : 0, std::memory_order_relaxed); }
-
-// workspace: [grid][196][64] fp32 relative-position partials | [nblocks] order flags
+// workspace: [grid][196][64] fp32 relative-position partials | (scratch mode) window-major bf16 dK, dV
 size_t attn_bwd_tc_ws_bytes(const pht_attn_args& f) {
   if (f.heads != 4 || f.head_dim != 64 || f.block != 8 || f.halo != 3) return 0;
   size_t nblk = (size_t)f.B * (f.H / 8) * (f.W / 8);
-  return (size_t)at_grid((int)nblk) * AB_REL_PART * sizeof(float) + nblk * sizeof(unsigned) + 256;
+  size_t scratch = g_attn_bwd_direct.load(std::memory_order_relaxed) ? 0 : 2 * nblk * 4 * AT_NK * 64 * sizeof(bf16);
+  return (size_t)at_grid((int)nblk) * AB_REL_PART * sizeof(float) + scratch + 256;
 }
 
 static bool attn_bwd_tc_eligible(const pht_attn_bwd_args* a) {
@@ -1097,24 +1087,19 @@ static bool attn_bwd_tc_eligible(const pht_attn_bwd_args* a) {
   return get_encode_fn() != nullptr;
 }
 
-static unsigned* ab_flags(const pht_attn_bwd_args* a, int grid) {
-  return reinterpret_cast<unsigned*>((float*)a->workspace + (size_t)grid * AB_REL_PART);
-}
-
-// dk / dv (and the order flags) := 0: the backward kernel accumulates into them
+// dk / dv := 0: in the direct mode the backward kernel accumulates into them (nothing to do in the scratch mode)
 int attn_bwd_zero_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
   *handled = false;
   if (!attn_bwd_tc_eligible(a)) return PHT_OK;
+  *handled = true;
+  if (!g_attn_bwd_direct.load(std::memory_order_relaxed)) return PHT_OK;
   const pht_attn_args& f = a->fwd;
-  const int nblocks = f.B * (f.W / 8) * (f.H / 8);
   const long long items = 2ll * f.B * f.H * f.W * 32;
   int grid = (int)((items + 255) / 256);
   if (grid > sm_count() * 16) grid = sm_count() * 16;
-  attn_bwd_zero_kernel<<<grid, 256, 0, st>>>(make_view(a->dk), make_view(a->dv), f.B, f.H, f.W, 256, ab_flags(a, at_grid(nblocks)),
-                                            nblocks);
+  attn_bwd_zero_kernel<<<grid, 256, 0, st>>>(make_view(a->dk), make_view(a->dv), f.B, f.H, f.W, 256);
   PHT_LAUNCH_CHECK();
   count_launch(CNT_OTHER);
-  *handled = true;
   return PHT_OK;
 }
 
@@ -1127,7 +1112,7 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
     int rc = attn_bwd_zero_tc(a, st, &z);
     if (rc) return rc;
   }
-  CUtensorMap tmQ, tmK, tmV, tmDO, tmDK, tmDV;
+  CUtensorMap tmQ, tmK, tmV, tmDO;
   int rc = at_tmap(&tmQ, f.q, f.B, 8, 8);
   if (rc) return rc;
   rc = at_tmap(&tmK, f.k, f.B, 14, 14);
@@ -1136,23 +1121,29 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
   if (rc) return rc;
   rc = at_tmap(&tmDO, a->d_out, f.B, 8, 8);
   if (rc) return rc;
-  rc = at_tmap(&tmDK, a->dk, f.B, 14, 14);
-  if (rc) return rc;
-  rc = at_tmap(&tmDV, a->dv, f.B, 14, 14);
-  if (rc) return rc;
   AbP P;
   P.B = f.B; P.H = f.H; P.W = f.W; P.nbx = f.W / 8; P.nby = f.H / 8; P.nblocks = f.B * P.nbx * P.nby;
   P.dq = make_view(a->dq);
   P.rel_h = f.rel_h; P.rel_w = f.rel_w; P.lse = f.lse;
   P.trace = g_attn_trace_on == 1;
-  P.ordered = g_attn_ordered.load(std::memory_order_relaxed);
-  P.dkOx = a->dk.ox; P.dkOy = a->dk.oy; P.dvOx = a->dv.ox; P.dvOy = a->dv.oy;
+  P.direct = g_attn_bwd_direct.load(std::memory_order_relaxed);
+  P.dk = make_view(a->dk); P.dv = make_view(a->dv);
   const int grid = at_grid(P.nblocks);
   P.rel_part = (float*)a->workspace;
-  P.flags = ab_flags(a, grid);
+  const size_t scratch = (size_t)P.nblocks * 4 * AT_NK * 64;
+  P.dk_scratch = (bf16*)(P.rel_part + (size_t)grid * AB_REL_PART);
+  P.dv_scratch = P.dk_scratch + scratch;
   PHT_SMEM_ATTR_ONCE(attn_bwd_tc_kernel, AB_SMEM);
-  PHT_CUDA(launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, tmDK, tmDV, P));
+  PHT_CUDA(launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(AB_THREADS), AB_SMEM, st, tmQ, tmK, tmV, tmDO, P));
   PHT_LAUNCH_CHECK();
+  if (!P.direct) {
+    long long items = (long long)f.B * f.H * f.W * 32;
+    int fgrid = (int)((items + 255) / 256);
+    if (fgrid > sm_count() * 16) fgrid = sm_count() * 16;
+    attn_bwd_fold_kernel<<<fgrid, 256, 0, st>>>(P.dk_scratch, P.dv_scratch, make_view(a->dk), make_view(a->dv), f.B, f.H, f.W,
+                                               P.nby, P.nbx);
+    count_launch(CNT_OTHER);
+  }
   attn_bwd_rel_reduce_kernel<<<896, 64, 0, st>>>(P.rel_part, grid, a->d_rel_h, a->d_rel_w);
   PHT_LAUNCH_CHECK();
   walk_dir_set(a->dq.ptr, 0);

@@ -30,7 +30,7 @@ void set_strips(int v);  // igemm_tc.cu
 void set_conv_trace(int v);  // igemm_tc.cu
 int read_conv_trace(long long* host, int n);  // igemm_tc.cu
 void set_attn_trace(int v);  // attention_tc.cu
-void set_attn_ordered(int v);  // attention_tc.cu
+void set_attn_bwd_direct(int v);  // attention_tc.cu
 int read_attn_trace(long long* host, int n);  // attention_tc.cu
 bool force_simple() { return g_force_simple.load(std::memory_order_relaxed) != 0; }
 bool bf16_fallback_allowed() { return g_bf16_fallback.load(std::memory_order_relaxed) != 0; }
@@ -94,7 +94,7 @@ int pht_set_option(const char* name, int value) {
   if (name && !strcmp(name, "serpentine")) { pht::set_serpentine(value); return PHT_OK; }
   if (name && !strcmp(name, "pdl")) { pht::g_pdl.store(value ? 1 : 0, std::memory_order_relaxed); return PHT_OK; }
   if (name && !strcmp(name, "attn_trace")) { pht::set_attn_trace(value); return PHT_OK; }
-  if (name && !strcmp(name, "attn_ordered")) { pht::set_attn_ordered(value); return PHT_OK; }
+  if (name && !strcmp(name, "attn_bwd_direct")) { pht::set_attn_bwd_direct(value); return PHT_OK; }
   if (name && !strcmp(name, "bf16_fallback")) { pht::g_bf16_fallback.store(value ? 1 : 0, std::memory_order_relaxed); return PHT_OK; }
   pht::set_error("pht_set_option: unknown option");
   return PHT_ERR_INVALID;

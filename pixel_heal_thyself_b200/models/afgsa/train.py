@@ -10,6 +10,9 @@ class AFGSATrainer(BaseTrainer):
     def create_generator(self) -> AFGSANet:
         m = self.cfg.model
         assert isinstance(m, AFGSAModelConfig)
+        if m.reproducible_attention_backward:       # (process-wide library option; the default is left as configured)
+            from ... import _lib
+            _lib.lib.pht_set_option(b"attn_bwd_direct", 0)
         return AFGSANet(
             m.input_channels,
             m.aux_input_channels,

@@ -35,7 +35,7 @@ from ..config import Config
 from ..data import PatchDataset, synthetic_frames
 from ..optim import FlatAdam
 from .afgsa.discriminator import DiscriminatorVGG
-from .losses import GANLoss, GradientPenaltyLoss, L1ReconstructionLoss
+from .losses import GANLoss, GradientPenaltyLoss, L1ReconstructionLoss, SSIMLoss
 
 logger = logging.getLogger("pht")
 
@@ -131,11 +131,12 @@ class BaseTrainer(ABC):
     def create_losses(self):
         """(l1_loss, gan_loss, gp_loss, lpips_loss, ssim_loss) as in base_trainer.py:127-154."""
         lc = self.cfg.model.losses
-        if lc.use_lpips_loss or lc.use_ssim_loss:
-            raise NotImplementedError("LPIPS / MS-SSIM losses need third-party weights/arithmetic that are not "
-                                      "available offline (SURVEY 8c: parity unpinned)")
+        if lc.use_lpips_loss:
+            raise NotImplementedError("the LPIPS loss needs the lpips package and its downloaded VGG weights, which are "
+                                      "not available offline (SURVEY 8c: out of scope)")
+        ssim = SSIMLoss(window_size=11).to(self.device) if lc.use_ssim_loss else None     # base_trainer.py:149-153
         return (L1ReconstructionLoss().to(self.device), GANLoss("wgan").to(self.device),
-                GradientPenaltyLoss(self.device).to(self.device), None, None)
+                GradientPenaltyLoss(self.device).to(self.device), None, ssim)
 
     def create_optimizers(self, G, D):  # noqa: N803
         """Adam x2 + MultiStepLR(gamma 0.5) with the reference's milestones (base_trainer.py:177-204)."""
@@ -153,7 +154,7 @@ class BaseTrainer(ABC):
         self.g_only = g_only
         self.G = self.create_generator()
         self.D = None if g_only else self.create_discriminator()
-        self.l1_loss, self.gan_loss, self.gp_loss, _, _ = self.create_losses()
+        self.l1_loss, self.gan_loss, self.gp_loss, _, self.ssim_loss = self.create_losses()
         if g_only:
             t = self.cfg.trainer
             self.opt_g = FlatAdam(self.G, lr=t.lr_g, grad_scale=1.0 / self.world)
@@ -283,6 +284,8 @@ class BaseTrainer(ABC):
             g_loss = lw.gan_loss_w * self.gan_loss(self.D(output), True) + g_loss
             for p in d_params:
                 p.requires_grad_(True)
+        if self.ssim_loss is not None:                      # base_trainer.py:450-452
+            g_loss = g_loss + lw.ssim_loss_w * self.ssim_loss(output, gt)
         g_loss.backward()
         if self.bucketer is not None:
             # gather first: the all-reduce must act on the arena the optimiser reads (p.grad may not alias the arena

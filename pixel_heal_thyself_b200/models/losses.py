@@ -37,6 +37,43 @@ class L1ReconstructionLoss(nn.Module):
         return _L1Fn.apply(input_data, target)
 
 
+class _SSIMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, target, module):
+        a = inp.detach().contiguous().float()
+        b = target.detach().contiguous().float()
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        grad = torch.empty_like(a) if inp.requires_grad else None
+        ops.msssim_loss(a, b, loss, grad, module._workspace(a))
+        ctx.grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        return (ctx.grad * go if ctx.grad is not None else None), None, None
+
+
+class SSIMLoss(nn.Module):
+    """MS-SSIM + L1 loss on scale-normalised images (reference: losses.py:248-263, kornia 0.8.0 ``MS_SSIMLoss`` with its
+    defaults; see ``pht_msssim_loss`` -- parity unpinned, kornia is not available to check against).  Fused
+    forward + backward CUDA kernels; ``_window_size`` is accepted and ignored exactly like the reference's."""
+
+    def __init__(self, _window_size: int = 11, window_size: int | None = None) -> None:
+        super().__init__()
+        self._ws = None
+
+    def _workspace(self, a: torch.Tensor) -> torch.Tensor:
+        B, _, H, W = a.shape
+        n = (ops.msssim_ws_bytes(B, H, W) + 3) // 4
+        if self._ws is None or self._ws.numel() < n or self._ws.device != a.device:
+            self._ws = torch.empty(n, dtype=torch.float32, device=a.device)
+        return self._ws
+
+    def forward(self, input_data: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return _SSIMFn.apply(input_data, target, self)
+
+
 class GANLoss(nn.Module):
     """Adversarial loss on critic scores (reference: losses.py:103-172).  The AFGSA trainer uses "wgan"
     (base_trainer.py:141); "nsgan" (BCE on probabilities), "lsgan" (MSE) and "hinge" follow the reference's

@@ -298,6 +298,22 @@ def l1_loss(a, b, loss, grad=None, grad_scale=1.0):
                             L.stream_ptr()), "pht_l1_loss")
 
 
+def msssim_ws_bytes(B, H, W) -> int:
+    return int(lib.pht_msssim_ws_bytes(B, H, W))
+
+
+def msssim_loss(out, gt, loss, grad, workspace, grad_scale=1.0):
+    """pht_msssim_loss: out / gt fp32 NCHW [B,3,H,W]; loss fp32 [1]; grad fp32 like out or None."""
+    L.require_cuda(out, gt, loss, workspace)
+    assert out.is_contiguous() and gt.is_contiguous() and out.dtype == torch.float32 and gt.dtype == torch.float32
+    B, Cc, H, W = out.shape
+    if Cc != 3:
+        raise ValueError("msssim_loss: 3-channel images only (the reference's grouped window bank is built for RGB)")
+    L.check(lib.pht_msssim_loss(out.data_ptr(), gt.data_ptr(), B, H, W, float(grad_scale), loss.data_ptr(), L.ptr(grad),
+                                workspace.data_ptr(), workspace.numel() * workspace.element_size(), L.stream_ptr()),
+            "pht_msssim_loss")
+
+
 def preprocess(noisy_nhwc, gt_nhwc, aux_nhwc, noisy_out, gt_out, aux_out):
     L.require_cuda(noisy_nhwc, aux_nhwc, noisy_out, aux_out)
     B, H, W, _ = noisy_nhwc.shape

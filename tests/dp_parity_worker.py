@@ -23,7 +23,9 @@ from pixel_heal_thyself_b200.optim import FlatAdam  # noqa: E402
 from make_golden_shapes import shape_inputs  # noqa: E402
 
 dtype = os.environ.get("PHT_DP_DTYPE", "fp32")
-cfg = load_config("dev", ["trainer.batch_size=4", f"model.afgsa.compute_dtype={dtype}"])
+# (a small learning rate keeps the two runs' weights -- and with them the ReLU / L1 kink patterns -- close enough for the
+# later steps to be comparable at all: Adam's first updates are +-lr per element whatever the gradient's size)
+cfg = load_config("dev", ["trainer.batch_size=4", f"model.afgsa.compute_dtype={dtype}", "trainer.lr_g=1e-6"])
 tr = AFGSATrainer(cfg)
 rank, world, dev = tr.rank, tr.world, tr.device
 assert world == 2

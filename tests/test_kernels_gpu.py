@@ -530,12 +530,13 @@ def test_validation_metrics_match_reference_golden():
         M.image_metrics(ref_out, ref_gt[:, :-1])
 
 
-def test_attention_backward_window_accumulation_is_ordered_and_reproducible():
-    """The tcgen05 attention backward adds the <= 4 overlapping 14x14-window contributions of a key pixel into dK / dV
-    with TMA reduce-adds in a FIXED order (option "attn_ordered", default on): two runs are bit-identical, at a size
-    where every CTA walks several blocks (8 x 128 x 128 = 2048 blocks on 148 CTAs) and with dK living in a channel
-    slice of a wider buffer (the engine's [dQ | dK] layout).  With the ordering off the values still agree to bf16
-    rounding of the partial sums."""
+def test_attention_backward_accumulation_modes():
+    """The tcgen05 attention backward has two ways of summing the <= 4 overlapping 14x14-window contributions of a key
+    pixel into dK / dV (option "attn_bwd_direct"): 1 (default) = vector reductions straight into the NHWC gradient, in
+    arrival order; 0 = window-major scratch + fold kernel, fixed order.  At a size where every CTA walks several blocks
+    (8 x 128 x 128 = 2048 blocks on 148 CTAs), with dK living in a channel slice of a wider buffer (the engine's
+    [dQ | dK] layout): the fold mode is bit-reproducible, the direct mode agrees with it to the bf16 rounding of the
+    partial sums, and dQ / d rel (which do not go through the accumulation) are bit-identical in both."""
     ops = _ops()
     from pixel_heal_thyself_b200 import _lib
     B, C, H, W = 8, 256, 128, 128
@@ -546,9 +547,9 @@ def test_attention_backward_window_accumulation_is_ordered_and_reproducible():
     out = torch.empty_like(q)
     lse = torch.empty(B, H, W, 4, device=DEV)
     ops.attn_fwd(q, k, v, rel_h, rel_w, out, lse=lse)
-    ws = torch.empty(max(ops.attn_bwd_workspace_bytes(q), 16) // 4, device=DEV)
 
     def run():
+        ws = torch.empty(max(ops.attn_bwd_workspace_bytes(q), 16) // 4, device=DEV)
         dqk = torch.full((B, H, W, 2 * C), float("nan"), device=DEV, dtype=torch.bfloat16)
         dv = torch.full((B, H, W, C), float("nan"), device=DEV, dtype=torch.bfloat16)
         drh, drw = torch.empty_like(rel_h), torch.empty_like(rel_w)
@@ -556,14 +557,41 @@ def test_attention_backward_window_accumulation_is_ordered_and_reproducible():
         torch.cuda.synchronize()
         return dqk, dv, drh, drw
 
-    a, b = run(), run()
-    for x, y in zip(a, b):
-        assert torch.isfinite(x.float()).all()
-        assert torch.equal(x, y)
-    assert _lib.lib.pht_set_option(b"attn_ordered", 0) == 0
+    direct = run()
+    assert _lib.lib.pht_set_option(b"attn_bwd_direct", 0) == 0
     try:
-        c = run()
+        fold_a, fold_b = run(), run()
     finally:
-        _lib.lib.pht_set_option(b"attn_ordered", 1)
-    for x, y in zip(a, c):
-        assert rel_err(y, x) < 2e-2
+        _lib.lib.pht_set_option(b"attn_bwd_direct", 1)
+    for x, y in zip(fold_a, fold_b):
+        assert torch.isfinite(x.float()).all() and torch.equal(x, y)
+    for x, y in zip(direct, fold_a):
+        assert torch.isfinite(x.float()).all() and rel_err(x, y) < 2e-2
+    C2 = C
+    assert torch.equal(direct[0][..., :C2], fold_a[0][..., :C2])        # dQ
+    assert torch.equal(direct[2], fold_a[2]) and torch.equal(direct[3], fold_a[3])   # d rel_h, d rel_w
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 64), (1, 40, 56), (3, 16, 24)])
+def test_msssim_loss_matches_oracle(B, H, W):
+    """pht_msssim_loss (SSIMLoss, losses.py:248-263 over kornia 0.8.0's MS_SSIMLoss -- parity unpinned, see the oracle's
+    header) against oracle.msssim_oracle: loss value and the full gradient w.r.t. the network output; images smaller
+    than the 33-tap window (16 x 24) exercise the zero padding on every side."""
+    from oracle import msssim_oracle as M
+    from pixel_heal_thyself_b200.models.losses import SSIMLoss
+    torch.manual_seed(21)
+    gt = torch.rand(B, 3, H, W) * 2.5                       # log-radiance-like, some pixels above 1 (scale > 1)
+    out = (gt + 0.15 * torch.randn(B, 3, H, W)).requires_grad_(True)
+    ref = M.ssim_loss(out.double(), gt.double())
+    (gref,) = torch.autograd.grad(ref, out)
+    od = out.detach().to(DEV).requires_grad_(True)
+    crit = SSIMLoss(window_size=11)
+    loss = crit(od, gt.to(DEV))
+    (0.1 * loss).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel_err(od.grad.cpu(), 0.1 * gref) < 1e-4
+    # same images -> zero loss, finite gradient
+    z = gt.to(DEV).clone().requires_grad_(True)
+    l0 = crit(z, gt.to(DEV))
+    l0.backward()
+    assert abs(float(l0)) < 1e-4 and torch.isfinite(z.grad).all()

