@@ -379,20 +379,22 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] += s_bias[n0 + c0 + j];
-        if (MODE == 2 && (P.flags & PHT_EPI_PADFOLD)) {
+        if (MODE != 0 && (P.flags & PHT_EPI_PADFOLD)) {
           // backward of replicate padding, fused: the tile lives on the padded domain; every border pixel's value is
-          // added to the interior pixel it was replicated from (always inside the same tile, see the host check)
+          // added to the interior pixel it was replicated from (always inside the same tile, see the host check).
+          // Runs per epilogue group on the group's own staging tile.
+          uint8_t* ftile = stg + part * STG_BYTES;
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          uint8_t* srow = stg + row * 128;
+          group_sync();
+          uint8_t* srow = ftile + row * 128;
 #pragma unroll
           for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(srow + ((g ^ rsw) * 16)) = pack8(v + g * 8);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          group_sync();
           const int ey = y == 1 ? -1 : (y == P.Ho - 2 ? 1 : 0), ex = x == 1 ? -1 : (x == P.Wo - 2 ? 1 : 0);
           const bool interior = y >= 1 && y <= P.Ho - 2 && x >= 1 && x <= P.Wo - 2;
           if (interior && (ey | ex)) {
             auto add_row = [&](int r2) {
-              const uint8_t* nrow = stg + r2 * 128;
+              const uint8_t* nrow = ftile + r2 * 128;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 float t[8];
@@ -639,11 +641,9 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   const int force = g_tc_cfg.load(std::memory_order_relaxed);
   const bool fused = has_resid || has_mask || (a->out1.ptr && a->out2.ptr) || padfold;
   int mode = a->ksize == 1 ? 1 : (fused ? 2 : 0);
-  if (mode == 2 && a->N > TcCfg<256, 2>::VEC_N) {
-    if (padfold) return PHT_OK;   // (the dispatcher reports PHT_ERR_UNSUPPORTED)
-    mode = 1;
-  }
+  if (mode == 2 && a->N > TcCfg<256, 2>::VEC_N) mode = 1;   // (the slope vectors do not fit beside the deep ring)
   if (force == 2 && !padfold) mode = 1;
+  if (force == 4 && a->ksize == 3 && fused) mode = 1;   // A/B: fused 3x3 (pad-fold included) on the two-group "wide" config
   if (force == 1 && !fused) mode = 0;
   if (force == 3 && a->ksize == 1 && a->N <= TcCfg<256, 2>::VEC_N) mode = fused ? 2 : 0;
   if (BN == 256) rc = mode == 0 ? launch_tc<256, 0>(P, m, st) : (mode == 1 ? launch_tc<256, 1>(P, m, st) : launch_tc<256, 2>(P, m, st));
