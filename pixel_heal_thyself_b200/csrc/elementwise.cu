@@ -689,6 +689,49 @@ __global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs) {
   }
 }
 
+// Tiled version (the default): one CTA per 32 (o) x 32 (i) x taps tile of one job.  The tile's OIHW rows are read as
+// contiguous runs (a row o holds ni * taps consecutive floats) into shared memory; the packed layout is then written
+// tap by tap with the lanes of a warp on the layout's fastest index (i for the forward [tap][N][K] pack, o for the
+// transposed / tap-folded packs): both sides are coalesced, and no thread walks 9 strided addresses.  PackJob.pad_
+// holds the job's first tile index (ascending), the kernel finds its job by binary search.
+constexpr int PK_TILE = 32;
+__global__ void __launch_bounds__(256) pack_weights_tiled_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  extern __shared__ float pk_tile[];
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].pad_ <= (int)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const PackP a = j.p;
+  const int T = a.ks * a.ks;
+  const int tiles_i = (a.i_count + PK_TILE - 1) / PK_TILE;
+  const int tl = (int)blockIdx.x - j.pad_;
+  const int o0 = (tl / tiles_i) * PK_TILE, i0 = (tl % tiles_i) * PK_TILE;
+  const int no = min(PK_TILE, a.O - o0), ni = min(PK_TILE, a.i_count - i0);
+  const int rowlen = ni * T, pitch = min(PK_TILE, a.i_count) * T + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < no; r += 8) {
+    const float* src = j.w + ((long long)(o0 + r) * a.I + a.i_begin + i0) * T;
+    for (int c = lane; c < rowlen; c += 32) pk_tile[r * pitch + c] = __ldg(src + c) * a.scale;
+  }
+  __syncthreads();
+  const bool o_fast = a.transpose != 0 && a.grid <= 0;
+  const int nf = o_fast ? no : ni, ns = o_fast ? ni : no;
+  for (int r = warp; r < T * ns; r += 8) {
+    const int t = r / ns, sl = r - t * ns;
+    if (lane < nf) {
+      const int ol = o_fast ? lane : sl, il = o_fast ? sl : lane;
+      const float v = pk_tile[ol * pitch + il * T + t];
+      const int ky = t / a.ks, kx = t - ky * a.ks;
+      const long long di = packed_index(a, o0 + ol, i0 + il, ky, kx);
+      if (j.dtype == PHT_F32) ((float*)j.dst)[di] = v;
+      else ((bf16*)j.dst)[di] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 __global__ void unpack_wgrads_batched_kernel(const PackJob* __restrict__ jobs) {
   const PackJob j = jobs[blockIdx.y];
   const PackP a = j.p;
@@ -1157,7 +1200,8 @@ int pht_pack_weights_batched(const pht_pack_args* jobs, int32_t n, void* table_d
                              void* stream) {
   PHT_CHECK_ARG(jobs && n > 0 && table_dev && table_bytes >= pht_pack_table_bytes(n), "pack_batched: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  long long max_total = 0;
+  long long max_total = 0, tiles = 0;
+  int max_pitch = 1;
   static thread_local std::vector<PackJob> host;
   host.resize(n);
   for (int i = 0; i < n; ++i) {
@@ -1165,11 +1209,22 @@ int pht_pack_weights_batched(const pht_pack_args* jobs, int32_t n, void* table_d
     int rc = check_pack(&jobs[i], &p);
     if (rc) return rc;
     PHT_CHECK_ARG(jobs[i].dtype == PHT_F32 || jobs[i].dtype == PHT_BF16, "pack_batched: bad dtype");
-    host[i].w = jobs[i].w; host[i].dst = jobs[i].packed; host[i].p = p; host[i].dtype = jobs[i].dtype; host[i].pad_ = 0;
+    host[i].w = jobs[i].w; host[i].dst = jobs[i].packed; host[i].p = p; host[i].dtype = jobs[i].dtype;
+    host[i].pad_ = (int)tiles;                       // first tile of this job (tiled kernel)
+    tiles += (long long)((p.O + PK_TILE - 1) / PK_TILE) * ((p.i_count + PK_TILE - 1) / PK_TILE);
+    const int pitch = (p.i_count < PK_TILE ? p.i_count : PK_TILE) * p.ks * p.ks + 1;
+    if (pitch > max_pitch) max_pitch = pitch;
     long long total = (long long)p.O * p.i_count;   // one thread per (o, i) pair
     if (total > max_total) max_total = total;
   }
   if (upload) PHT_CUDA(cudaMemcpyAsync(table_dev, host.data(), (size_t)n * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+  const size_t smem = (size_t)PK_TILE * max_pitch * sizeof(float);
+  if (smem <= 48 * 1024 && tiles < (1ll << 30)) {
+    pack_weights_tiled_kernel<<<(unsigned)tiles, 256, smem, st>>>((const PackJob*)table_dev, n);
+    count_launch(CNT_OTHER);
+    PHT_LAUNCH_CHECK();
+    return PHT_OK;
+  }
   int gx = (int)((max_total + 255) / 256);
   if (gx > 592) gx = 592;
   dim3 grid(gx, n);
