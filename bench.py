@@ -481,10 +481,12 @@ def run_ours(args):
         sus = (float(t[3]), sus[1])
     if full:
         full = (float(t[4]), float(t[5]), full[2], full[3])
+    if world > 1:
+        # tear the process group down BEFORE the CPU baseline: ranks > 0 exit here, so rank 0's host threads are not
+        # fighting seven ranks spinning in a barrier
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.barrier()       # (rank 0 is timing the CPU baseline)
-            dist.destroy_process_group()
         return
     clk = clocks.stop()
 
@@ -568,9 +570,6 @@ def run_ours(args):
                          if cpu_sec else None),
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 def main():
