@@ -242,6 +242,28 @@ int pht_dec_tail_bwd_weight(const float* dout_nchw, const pht_view* h, float* dw
  * two-level reduction live in library scratch private to (device, stream): launches on different streams may overlap. */
 int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, float* loss, float* grad, void* stream);
 
+/* BatchNorm2d (training mode, affine) + LeakyReLU of the WGAN-GP critic's conv blocks (DiscriminatorVGG,
+ * model.py:264-344; norm :52-61, act :64-83), with the first- and the second-order backward that the gradient penalty
+ * (losses.py:12-57) needs.  All tensors fp32, channels-last: x / z / gz / gx / h [m = B*H*W][C]; gamma / beta /
+ * run_mean / run_var [C]; stat [2][C] = batch mean and 1/sqrt(var + eps), written by the forward and read by both backward
+ * passes.  C = 4 x a power of two, <= 1024.  workspace >= pht_bn_act_ws_bytes(C), 16-byte aligned.
+ *   fwd      z = leaky(gamma (x - mean) rstd + beta); run_mean / run_var (may be NULL) updated like nn.BatchNorm2d
+ *   bwd      gx, g_gamma, g_beta (the latter two may be NULL) from gz
+ *   bwd_bwd  cotangent h of gx -> h_gz (w.r.t. gz), h_x (w.r.t. x, the dependence of mean / rstd on x included),
+ *            h_gamma (may be NULL).  Per-channel sums accumulate in fp64 in a fixed order (deterministic). */
+size_t pht_bn_act_ws_bytes(int32_t C);
+/* out[c] = sum over m rows of x[m][C] (fp32): the conv bias gradients of the critic; same workspace / channel rules */
+int pht_colsum_f32(const float* x, float* out, int64_t m, int32_t C, void* workspace, size_t workspace_bytes, void* stream);
+int pht_bn_act_fwd(const float* x, const float* gamma, const float* beta, float* run_mean, float* run_var, float* stat, float* z,
+                   int64_t m, int32_t C, float eps, float momentum, float slope, void* workspace, size_t workspace_bytes,
+                   void* stream);
+int pht_bn_act_bwd(const float* x, const float* gz, const float* gamma, const float* beta, const float* stat, float* gx,
+                   float* g_gamma, float* g_beta, int64_t m, int32_t C, float slope, void* workspace, size_t workspace_bytes,
+                   void* stream);
+int pht_bn_act_bwd_bwd(const float* x, const float* gz, const float* h, const float* gamma, const float* beta, const float* stat,
+                       float* h_gz, float* h_x, float* h_gamma, int64_t m, int32_t C, float slope, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Optional MS-SSIM + L1 image loss, fused forward + backward (SSIMLoss, losses.py:248-263, used at
  * base_trainer.py:450-452 with weight 0.1): per-pixel scale = max(channel-max of gt, 1); kornia 0.8.0
  * MS_SSIMLoss(reduction="mean") arithmetic on out / scale, gt / scale (kornia is a third-party dependency that is not

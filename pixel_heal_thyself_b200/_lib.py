@@ -94,6 +94,11 @@ SYMBOLS = {
     "pht_dec_tail_ws_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "pht_dec_tail_bwd_weight": (C.c_int, [_vp, _PV, _vp, _vp, _vp, _sz, _i32, _i32, _i32, _vp]),
     "pht_l1_loss": (C.c_int, [_vp, _vp, _i64, _f32, _vp, _vp, _vp]),
+    "pht_bn_act_ws_bytes": (_sz, [_i32]),
+    "pht_colsum_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _sz, _vp]),
+    "pht_bn_act_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _sz, _vp]),
+    "pht_bn_act_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _sz, _vp]),
+    "pht_bn_act_bwd_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _sz, _vp]),
     "pht_msssim_ws_bytes": (_sz, [_i32, _i32, _i32]),
     "pht_msssim_loss": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "pht_preprocess": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

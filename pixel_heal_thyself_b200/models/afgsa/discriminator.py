@@ -1,8 +1,10 @@
 """VGG-style WGAN critic (reference: pht/models/afgsa/model.py:264-344).
 
-Adjacent to the hot path: it stays stock PyTorch / cuDNN in
-this round and exists so a full GAN training step (base_trainer.py:388-457)
-can run and be timed.  Same parameter names and init order as the reference.
+Adjacent to the hot path.  Its convolutions and linear layers stay stock PyTorch / cuDNN; the
+BatchNorm2d + LeakyReLU of every conv block -- whose second-order backward (the gradient penalty differentiates the
+critic's input gradient) PyTorch unrolls into hundreds of small launches, ~45 % of the critic step's GPU time -- runs on
+hand-written kernels (``pht_bn_act_fwd / _bwd / _bwd_bwd``) through a twice-differentiable autograd function.  Same
+parameter names, buffers and init order as the reference.
 """
 from __future__ import annotations
 
@@ -11,6 +13,41 @@ import math
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+
+# Set by GradientPenaltyLoss around its ``torch.autograd.grad(pred, x_hat, create_graph=True)``: that pass only wants the
+# INPUT gradient, but a Python autograd function cannot see which of its outputs the engine needs, so without the hint
+# every convolution would also compute (and throw away) its weight and bias gradients there.
+_input_grad_only = False
+
+
+class input_grad_only:
+    def __enter__(self):
+        global _input_grad_only
+        self.prev, _input_grad_only = _input_grad_only, True
+
+    def __exit__(self, *exc):
+        global _input_grad_only
+        _input_grad_only = self.prev
+
+
+_colsum_ws: dict = {}
+
+
+def _bias_grad(g: torch.Tensor) -> torch.Tensor:
+    """sum over (batch, rows, cols); outside a differentiable pass on the deterministic column-sum kernel"""
+    C = g.shape[1]
+    if (not torch.is_grad_enabled() and g.is_cuda and g.dtype == torch.float32 and C % 4 == 0 and C <= 1024
+            and (C // 4) & (C // 4 - 1) == 0 and g.is_contiguous(memory_format=torch.channels_last)):
+        from ... import ops
+        key = (C, str(g.device))
+        ws = _colsum_ws.get(key)
+        if ws is None:
+            ws = _colsum_ws[key] = ops.bn_act_ws(C, g.device)
+        out = torch.empty(C, dtype=torch.float32, device=g.device)
+        ops.colsum_nhwc(g, out, ws)
+        return out
+    return g.sum((0, 2, 3))
 
 
 class _Conv2dForGP(torch.autograd.Function):
@@ -37,11 +74,66 @@ class _Conv2dForGP(torch.autograd.Function):
             gx = F.conv_transpose2d(g, w, None, stride=ctx.stride, padding=ctx.padding)
             if gx.shape[2:] != x.shape[2:]:     # (sizes the stride does not divide: pad the tail like conv2d's backward)
                 gx = F.pad(gx, (0, x.shape[3] - gx.shape[3], 0, x.shape[2] - gx.shape[2]))
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and not _input_grad_only:
             gw = torch.nn.grad.conv2d_weight(x, w.shape, g, stride=ctx.stride, padding=ctx.padding)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum((0, 2, 3))
+        if ctx.has_bias and ctx.needs_input_grad[2] and not _input_grad_only:
+            gb = _bias_grad(g)
         return gx, gw, gb, None, None
+
+
+class _BNActBwdFn(torch.autograd.Function):
+    """First-order backward of BatchNorm2d(train) + LeakyReLU as a differentiable op: (gz, x, gamma) -> (gx, g_gamma,
+    g_beta); its own backward (the gradient-penalty pass) is ``pht_bn_act_bwd_bwd``."""
+
+    @staticmethod
+    def forward(ctx, gz, x, gamma, beta, stat, slope, ws):
+        from ... import ops
+        gz = gz.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty_like(x, memory_format=torch.channels_last)
+        gg, gb = torch.empty_like(gamma), torch.empty_like(beta)
+        ops.bn_act_bwd(x, gz, gamma, beta, stat, gx, gg, gb, ws, slope=slope)
+        ctx.save_for_backward(gz, x, gamma, beta, stat)
+        ctx.slope, ctx.ws = slope, ws
+        ctx.set_materialize_grads(False)
+        return gx, gg, gb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, h_gx, h_gg, h_gb):
+        from ... import ops
+        if h_gg is not None or h_gb is not None:
+            raise NotImplementedError("second-order gradients through d/d gamma, d/d beta of the critic's BatchNorm are "
+                                      "not needed by WGAN-GP (the penalty differentiates the INPUT gradient) and not built")
+        gz, x, gamma, beta, stat = ctx.saved_tensors
+        if h_gx is None:
+            return None, None, None, None, None, None, None
+        h = h_gx.contiguous(memory_format=torch.channels_last)
+        h_gz, h_x = torch.empty_like(h), torch.empty_like(h)
+        h_gamma = torch.empty_like(gamma)
+        ops.bn_act_bwd_bwd(x, gz, h, gamma, beta, stat, h_gz, h_x, h_gamma, ctx.ws, slope=ctx.slope)
+        return h_gz, h_x, h_gamma, None, None, None, None
+
+
+class _BNActFn(torch.autograd.Function):
+    """z = LeakyReLU(BatchNorm2d_train(x)) on channels-last fp32 CUDA tensors; running statistics updated in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, run_mean, run_var, eps, momentum, slope, ws):
+        from ... import ops
+        # (the caller passes a channels-last tensor: a copy made here would cut x out of the double-backward graph)
+        assert x.is_contiguous(memory_format=torch.channels_last)
+        z = torch.empty_like(x, memory_format=torch.channels_last)
+        stat = torch.empty(2, x.shape[1], dtype=torch.float32, device=x.device)
+        ops.bn_act_fwd(x, gamma, beta, run_mean, run_var, stat, z, ws, eps=eps, momentum=momentum, slope=slope)
+        ctx.save_for_backward(x, gamma, beta, stat)
+        ctx.slope, ctx.ws = slope, ws
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, gamma, beta, stat = ctx.saved_tensors
+        gx, gg, gb = _BNActBwdFn.apply(gz, x, gamma, beta, stat, ctx.slope, ctx.ws)
+        return gx, gg, gb, None, None, None, None, None, None
 
 
 def _block(cin, cout, k, stride, bn):
@@ -66,6 +158,18 @@ class DiscriminatorVGG(nn.Module):
         self.features = nn.Sequential(*feats)
         side = input_size // 2 ** n_down
         self.classifier = nn.Sequential(nn.Linear(nc * side * side, 100), nn.LeakyReLU(0.2, True), nn.Linear(100, 1))
+        import os
+        self.fused_bn_act = os.environ.get("PHT_CRITIC_FUSED_BN", "1") != "0"
+        self._bn_workspaces: dict = {}
+
+    def _bn_ws(self, C, device):
+        """one reduction workspace per channel count (launches of a step are stream-ordered)"""
+        from ... import ops
+        key = (C, str(device))
+        ws = self._bn_workspaces.get(key)
+        if ws is None:
+            ws = self._bn_workspaces[key] = ops.bn_act_ws(C, device)
+        return ws
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.is_cuda:
@@ -82,7 +186,14 @@ class DiscriminatorVGG(nn.Module):
                     w = F.pad(w, (0, 0, 0, 0, 0, pad_c))
                 x = x.contiguous(memory_format=torch.channels_last)
                 x = _Conv2dForGP.apply(x, w.contiguous(memory_format=torch.channels_last), conv.bias, conv.stride, conv.padding)
-                x = block[1:](x)
+                bn = block[1] if isinstance(block[1], nn.BatchNorm2d) else None
+                if bn is not None and self.training and x.dtype == torch.float32 and self.fused_bn_act:
+                    # BatchNorm2d (batch statistics) + LeakyReLU(0.2) on the hand-written kernels, twice differentiable
+                    x = _BNActFn.apply(x.contiguous(memory_format=torch.channels_last), bn.weight, bn.bias, bn.running_mean,
+                                       bn.running_var, bn.eps, bn.momentum, 0.2, self._bn_ws(bn.num_features, x.device))
+                    bn.num_batches_tracked.add_(1)
+                else:
+                    x = block[1:](x)
         else:
             x = self.features(x)
         return self.classifier(x.reshape(x.size(0), -1))

@@ -116,6 +116,8 @@ class GradientPenaltyLoss(nn.Module):
         alpha = torch.rand((real_data.shape[0], 1, 1, 1), dtype=torch.float32, device=self.device)
         x_hat = (alpha * fake_data.detach() + (1 - alpha) * real_data).requires_grad_(True)
         pred = D(x_hat)
-        grad = torch.autograd.grad(pred, x_hat, torch.ones_like(pred), create_graph=True, retain_graph=True)[0]
+        from .afgsa.discriminator import input_grad_only
+        with input_grad_only():     # (this pass needs d pred / d x_hat only: skip the critic's parameter gradients in it)
+            grad = torch.autograd.grad(pred, x_hat, torch.ones_like(pred), create_graph=True, retain_graph=True)[0]
         norm = grad.reshape(grad.size(0), -1).norm(2, dim=1)
         return ((norm - 1) ** 2).mean()

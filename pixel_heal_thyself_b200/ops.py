@@ -298,6 +298,47 @@ def l1_loss(a, b, loss, grad=None, grad_scale=1.0):
                             L.stream_ptr()), "pht_l1_loss")
 
 
+def _nhwc_rows(t):
+    """logical NCHW channels-last fp32 tensor -> (data_ptr, m, C)"""
+    assert t.dim() == 4 and t.dtype == torch.float32 and t.permute(0, 2, 3, 1).is_contiguous(), "need channels-last fp32 NCHW"
+    return t.data_ptr(), t.shape[0] * t.shape[2] * t.shape[3], t.shape[1]
+
+
+def bn_act_ws(C, device):
+    return torch.empty((int(lib.pht_bn_act_ws_bytes(C)) + 3) // 4, dtype=torch.float32, device=device)
+
+
+def colsum_nhwc(x, out, ws):
+    """out[c] = sum over (b, y, x) of a channels-last fp32 NCHW tensor (pht_colsum_f32)."""
+    L.require_cuda(x, out, ws)
+    xp, m, Cc = _nhwc_rows(x)
+    L.check(lib.pht_colsum_f32(xp, out.data_ptr(), m, Cc, ws.data_ptr(), ws.numel() * 4, L.stream_ptr()), "pht_colsum_f32")
+
+
+def bn_act_fwd(x, gamma, beta, run_mean, run_var, stat, z, ws, *, eps=1e-5, momentum=0.1, slope=0.2):
+    L.require_cuda(x, gamma, beta, stat, z, ws)
+    xp, m, Cc = _nhwc_rows(x)
+    zp, _, _ = _nhwc_rows(z)
+    L.check(lib.pht_bn_act_fwd(xp, gamma.data_ptr(), beta.data_ptr(), L.ptr(run_mean), L.ptr(run_var), stat.data_ptr(), zp, m, Cc,
+                               eps, momentum, slope, ws.data_ptr(), ws.numel() * 4, L.stream_ptr()), "pht_bn_act_fwd")
+
+
+def bn_act_bwd(x, gz, gamma, beta, stat, gx, g_gamma, g_beta, ws, *, slope=0.2):
+    L.require_cuda(x, gz, gamma, beta, stat, gx, ws)
+    xp, m, Cc = _nhwc_rows(x)
+    L.check(lib.pht_bn_act_bwd(xp, _nhwc_rows(gz)[0], gamma.data_ptr(), beta.data_ptr(), stat.data_ptr(), _nhwc_rows(gx)[0],
+                               L.ptr(g_gamma), L.ptr(g_beta), m, Cc, slope, ws.data_ptr(), ws.numel() * 4, L.stream_ptr()),
+            "pht_bn_act_bwd")
+
+
+def bn_act_bwd_bwd(x, gz, h, gamma, beta, stat, h_gz, h_x, h_gamma, ws, *, slope=0.2):
+    L.require_cuda(x, gz, h, gamma, beta, stat, h_gz, h_x, ws)
+    xp, m, Cc = _nhwc_rows(x)
+    L.check(lib.pht_bn_act_bwd_bwd(xp, _nhwc_rows(gz)[0], _nhwc_rows(h)[0], gamma.data_ptr(), beta.data_ptr(), stat.data_ptr(),
+                                   _nhwc_rows(h_gz)[0], _nhwc_rows(h_x)[0], L.ptr(h_gamma), m, Cc, slope, ws.data_ptr(),
+                                   ws.numel() * 4, L.stream_ptr()), "pht_bn_act_bwd_bwd")
+
+
 def msssim_ws_bytes(B, H, W) -> int:
     return int(lib.pht_msssim_ws_bytes(B, H, W))
 

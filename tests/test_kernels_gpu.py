@@ -595,3 +595,81 @@ def test_msssim_loss_matches_oracle(B, H, W):
     l0 = crit(z, gt.to(DEV))
     l0.backward()
     assert abs(float(l0)) < 1e-4 and torch.isfinite(z.grad).all()
+
+
+@pytest.mark.parametrize("B,C,H,W", [(8, 64, 32, 32), (4, 128, 16, 24), (8, 512, 4, 4), (2, 256, 8, 8)])
+def test_bn_act_forward_backward_and_double_backward_match_torch(B, C, H, W):
+    """pht_bn_act_fwd / _bwd / _bwd_bwd (the critic's BatchNorm2d(train) + LeakyReLU(0.2), model.py:52-83, 264-344) against
+    stock torch modules: output, running statistics, first-order gradients, and the SECOND-order pass of a
+    gradient-penalty-shaped objective (losses.py:12-57: a function of the input gradient, differentiated w.r.t. the input,
+    gamma and the upstream gradient)."""
+    from pixel_heal_thyself_b200 import ops
+    from pixel_heal_thyself_b200.models.afgsa.discriminator import _BNActFn
+    torch.manual_seed(31)
+    x0 = (torch.randn(B, C, H, W, device=DEV) * 1.5 + 0.3).contiguous(memory_format=torch.channels_last)
+    wgt = torch.randn(B, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)   # stands in for the layers above
+    bn = torch.nn.BatchNorm2d(C).to(DEV)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.3)
+    act = torch.nn.LeakyReLU(0.2)
+    ws = ops.bn_act_ws(C, DEV)
+
+    def gp_objective(f, x, gamma, beta):
+        z = f(x, gamma, beta)
+        (gx,) = torch.autograd.grad((z * wgt).sum(), x, create_graph=True)
+        pen = ((gx.reshape(B, -1).norm(2, dim=1) - 1) ** 2).mean()
+        return z, gx, pen
+
+    # reference: stock modules (fresh running stats)
+    xr = x0.clone().requires_grad_(True)
+    gr, br = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    rm_r, rv_r = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    f_ref = lambda x, g, b: act(torch.nn.functional.batch_norm(x, rm_r, rv_r, g, b, True, 0.1, 1e-5))
+    z_r, gx_r, pen_r = gp_objective(f_ref, xr, gr, br)
+    d_r = torch.autograd.grad(pen_r + 0.01 * z_r.pow(2).mean(), [xr, gr, br])
+    # ours
+    xo = x0.clone().requires_grad_(True)
+    go, bo = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
+    rm_o, rv_o = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    f_our = lambda x, g, b: _BNActFn.apply(x, g, b, rm_o, rv_o, 1e-5, 0.1, 0.2, ws)
+    z_o, gx_o, pen_o = gp_objective(f_our, xo, go, bo)
+    d_o = torch.autograd.grad(pen_o + 0.01 * z_o.pow(2).mean(), [xo, go, bo])
+    assert rel_err(z_o, z_r) < 1e-5
+    assert rel_err(rm_o, rm_r) < 1e-5 and rel_err(rv_o, rv_r) < 1e-5
+    assert rel_err(gx_o, gx_r) < 1e-4
+    assert abs(float(pen_o) - float(pen_r)) < 1e-4 * max(1.0, abs(float(pen_r)))
+    for a, b, name in zip(d_o, d_r, ("d/dx", "d/dgamma", "d/dbeta")):
+        assert rel_err(a, b) < 2e-3, (name, rel_err(a, b))
+
+
+def test_critic_with_fused_bn_act_matches_stock_modules():
+    """DiscriminatorVGG at the prod shape with the hand-written BatchNorm + LeakyReLU kernels == the same critic on stock
+    torch modules: WGAN-GP critic loss (base_trainer.py:391-406) and every parameter gradient, same weights, same
+    interpolation coefficients."""
+    from pixel_heal_thyself_b200.models.afgsa.discriminator import DiscriminatorVGG
+    from pixel_heal_thyself_b200.models.losses import GANLoss, GradientPenaltyLoss
+    torch.manual_seed(5)
+    D = DiscriminatorVGG(3, 64, 64).to(DEV)
+    real, fake = torch.rand(4, 3, 64, 64, device=DEV), torch.rand(4, 3, 64, 64, device=DEV)
+    gan, gp = GANLoss("wgan").to(DEV), GradientPenaltyLoss(torch.device(DEV))
+    sd = {k: v.clone() for k, v in D.state_dict().items()}
+    res = {}
+    for fused in (False, True):
+        D.load_state_dict(sd)
+        D.fused_bn_act = fused
+        D.zero_grad(set_to_none=True)
+        torch.manual_seed(77)                                   # the gradient penalty draws its alphas from the global RNG
+        loss = (gan(D(fake), False) + gan(D(real), True)) / 2 + 10.0 * gp(D, real, fake)
+        loss.backward()
+        res[fused] = (float(loss), {n: p.grad.clone() for n, p in D.named_parameters()},
+                      {n: b.clone() for n, b in D.named_buffers()})
+    assert abs(res[True][0] - res[False][0]) < 1e-4 * max(1.0, abs(res[False][0])), (res[True][0], res[False][0])
+    # (a conv bias in front of a BatchNorm has a mathematically zero gradient -- the batch mean removes it -- so both sides
+    # hold only round-off there: errors are measured against the larger of the tensor's and the global gradient scale)
+    gmax = max(float(g.abs().max()) for g in res[False][1].values())
+    for n, g in res[False][1].items():
+        err = float((res[True][1][n] - g).abs().max()) / max(float(g.abs().max()), 1e-4 * gmax)
+        assert err < 5e-3, (n, err)
+    for n, b in res[False][2].items():
+        assert rel_err(res[True][2][n].float(), b.float()) < 1e-4, n
