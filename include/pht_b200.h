@@ -343,6 +343,11 @@ int pht_unpack_wgrads_batched(const pht_pack_args* jobs, int32_t n, void* table_
  *   out_nchw[b,co,y,x] = y[p][co] + bias[co] + x_nchw[b,co,y,x]. */
 int pht_tail_finish(const float* y, int32_t ldy, const float* bias, const float* x_nchw, float* out_nchw, int32_t B,
                     int32_t H, int32_t W, void* stream);
+/* The same decoder tail from a 1x1 GEMM: y fp32 [B][H][W][ldy] with y[p][t * 3 + co] = sum_c in(p)[c] w[co][c][t]
+ * (t = ky * 3 + kx) -> out_nchw(p)[co] = bias[co] + x_nchw(p)[co] + sum_t y[p + (ky - 1, kx - 1)][t * 3 + co], zero
+ * padding (model.py:707-714, 731-732).  The 256-channel decoder activation is read once instead of nine times. */
+int pht_tail_gather(const float* y, int32_t ldy, const float* bias, const float* x_nchw, float* out_nchw, int32_t B, int32_t H,
+                    int32_t W, void* stream);
 /* Backward side: a[p][t*3+co] = dout[p - tap_t][co] (bf16 [B*H*W][64], columns 27..63 zero) so that
  * d(decoder.1 output) = a @ Wt and d(decoder.2 weight) = h^T a are plain GEMMs; dbias[co] = sum_p dout[p][co]. */
 int pht_tail_im2col_bwd(const float* dout_nchw, void* a_bf16, float* dbias, int32_t B, int32_t H, int32_t W, void* stream);

@@ -113,6 +113,7 @@ SYMBOLS = {
     "pht_pack_table_bytes": (_sz, [_i32]),
     "pht_pack_weights_batched": (C.c_int, [C.POINTER(PackArgs), _i32, _vp, _sz, _i32, _vp]),
     "pht_tail_finish": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "pht_tail_gather": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pht_tail_im2col_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pht_cast": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
     "pht_cast2d": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),

@@ -1259,6 +1259,43 @@ int pht_unpack_wgrads_batched(const pht_pack_args* jobs, int32_t n, void* table_
   return PHT_OK;
 }
 
+// Decoder tail as a 1x1 GEMM + gather: y[p][t * 3 + co] = sum_c in(p)[c] w[co][c][t] (ONE pass over the 256-channel input
+// instead of nine shifted ones), then out(p)[co] = bias[co] + x(p)[co] + sum_t y[p + tap_t][t * 3 + co] (zero padding).
+// One thread per pixel: 27 floats from the 9 neighbouring rows of y (L2-resident), three coalesced NCHW stores.
+__global__ void tail_gather_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ bias, const float* __restrict__ x,
+                                   float* __restrict__ out, int B, int H, int W) {
+  const long long total = (long long)B * H * W;
+  const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(p % W);
+    const long long r = p / W;
+    const int py = (int)(r % H), b = (int)(r / H);
+    float a0 = b0, a1 = b1, a2 = b2;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) {
+        const float* q = y + (((long long)b * H + yy) * W + xx) * ldy + t * 3;
+        a0 += q[0]; a1 += q[1]; a2 += q[2];
+      }
+    }
+    const long long o = ((long long)b * 3 * H + py) * W + px, hw = (long long)H * W;
+    out[o] = a0 + x[o];
+    out[o + hw] = a1 + x[o + hw];
+    out[o + 2 * hw] = a2 + x[o + 2 * hw];
+  }
+}
+
+int pht_tail_gather(const float* y, int32_t ldy, const float* bias, const float* x_nchw, float* out_nchw, int32_t B, int32_t H,
+                    int32_t W, void* stream) {
+  PHT_CHECK_ARG(y && bias && x_nchw && out_nchw && ldy >= 27, "tail_gather: bad args");
+  long long n = (long long)B * H * W;
+  tail_gather_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, bias, x_nchw, out_nchw, B, H, W);
+  count_launch(CNT_OTHER);
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+
 int pht_tail_finish(const float* y, int32_t ldy, const float* bias, const float* x_nchw, float* out_nchw, int32_t B, int32_t H,
                     int32_t W, void* stream) {
   PHT_CHECK_ARG(y && bias && x_nchw && out_nchw && ldy >= 3, "tail_finish: bad args");

@@ -230,7 +230,8 @@ class AfgsaEngine:
         if tc_tail:
             # decoder tail on the tensor cores: 3 output channels padded to a 64-wide N tile (rows 3..63 stay zero);
             # backward operand [C][27 -> 64]: k = tap*3 + co
-            pw(w2, self._pk("dec2g", (9, 64, C)), ksize=3, Ntot=64, Ktot=C)
+            # forward as a 1x1 GEMM [27 -> 64][C] (row t*3 + co; rows 27..63 stay zero) + a 9-tap gather of its output
+            pw(w2, self._pk("dec2f", (1, 64, C)), ksize=3, Ntot=3, Ktot=C)
             if backward:
                 pw(w2, self._pk("dec2g.T", (1, C, 64)), ksize=3, Ntot=C, Ktot=64, transpose=2)
         else:
@@ -327,10 +328,11 @@ class AfgsaEngine:
                       out1=D2)
         out = torch.empty_like(x)
         if T == torch.bfloat16:
-            # 256->3 zero-padded conv as a 64-wide tensor-core GEMM (TMA zero-fills the border), then bias+residual+NCHW
+            # 256->3 zero-padded 3x3 conv: per-pixel products with all 27 (tap, channel) weight rows as ONE 64-wide 1x1
+            # tensor-core GEMM (D2 is read once, not nine times), then the 9-tap gather + bias + residual + NCHW
             Y = g("tailY", (B, H, W, 64), torch.float32)
-            ops.conv_gemm([D2], pk["dec2g"], 64, ksize=3, out1=Y)
-            ops.tail_finish(Y, P["decoder.2.0.bias"], x, out)
+            ops.conv_gemm([D2], pk["dec2f"], 64, ksize=1, out1=Y)
+            ops.tail_gather(Y, P["decoder.2.0.bias"], x, out)
         else:
             ops.dec_tail_fwd(D2, pk["dec2"], P["decoder.2.0.bias"], x, out)
         if save:

@@ -444,6 +444,15 @@ def tail_finish(y, bias, x_nchw, out_nchw):
                                 L.stream_ptr()), "pht_tail_finish")
 
 
+def tail_gather(y, bias, x_nchw, out_nchw):
+    """y fp32 [B,H,W,ldy] with y[p][t*3+co] (1x1 GEMM of the decoder tail) -> out_nchw = 9-tap gather + bias + x_nchw."""
+    L.require_cuda(y, bias, x_nchw, out_nchw)
+    B, H, W, ldy = y.shape
+    assert y.is_contiguous() and y.dtype == torch.float32
+    L.check(lib.pht_tail_gather(y.data_ptr(), ldy, bias.data_ptr(), x_nchw.data_ptr(), out_nchw.data_ptr(), B, H, W,
+                                L.stream_ptr()), "pht_tail_gather")
+
+
 def tail_im2col_bwd(dout_nchw, a, dbias):
     """dout fp32 [B,3,H,W] -> a bf16 [B,H,W,64] (27 shifted copies), dbias fp32 [3]."""
     L.require_cuda(dout_nchw, a, dbias)
