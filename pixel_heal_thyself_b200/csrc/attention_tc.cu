@@ -1037,29 +1037,30 @@ __global__ void attn_bwd_fold_kernel(const bf16* __restrict__ dks, const bf16* _
 }
 
 // d rel_h[r][j] = sum_parts sum_c dREL[(r,c)][j] (j < 32);  d rel_w[c][j] = sum_parts sum_r dREL[(r,c)][32 + j].
-// One block per output element, fixed summation order (deterministic).
-__global__ void attn_bwd_rel_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ d_rel_h,
-                                           float* __restrict__ d_rel_w) {
-  const int o = blockIdx.x;            // 0..447: rel_h[r][j], 448..895: rel_w[c][j]
-  const bool is_w = o >= 448;
-  const int rc = (is_w ? o - 448 : o) / 32, j = (is_w ? o - 448 : o) % 32;
+// Two small launches, fixed summation order (deterministic): (1) one block per key sums the CTA partials -- every
+// (part, key) row is one coalesced 256-byte read, four part-groups per block combined through shared memory; (2) one
+// thread per output adds its 14 keys.
+__global__ void __launch_bounds__(256) attn_bwd_rel_keysum_kernel(const float* __restrict__ part, int nparts, float* __restrict__ keysum) {
+  const int key = blockIdx.x, ch = threadIdx.x & 63, grp = threadIdx.x >> 6;
   float s = 0.f;
-  for (int p = threadIdx.x; p < nparts; p += blockDim.x) {
-    const float* base = part + (long long)p * AB_REL_PART;
-    for (int t = 0; t < 14; ++t) {
-      const int key = is_w ? t * 14 + rc : rc * 14 + t;
-      s += base[key * 64 + (is_w ? 32 + j : j)];
-    }
-  }
-  __shared__ float red[64];
+  for (int p = grp; p < nparts; p += 4) s += part[(long long)p * AB_REL_PART + key * 64 + ch];
+  __shared__ float red[256];
   red[threadIdx.x] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < (int)blockDim.x; ++i) t += red[i];
-    if (is_w) d_rel_w[o - 448] = t;
-    else d_rel_h[o] = t;
+  if (grp == 0) keysum[key * 64 + ch] = (red[ch] + red[64 + ch]) + (red[128 + ch] + red[192 + ch]);
+}
+__global__ void attn_bwd_rel_reduce_kernel(const float* __restrict__ keysum, float* __restrict__ d_rel_h, float* __restrict__ d_rel_w) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;     // 0..447: rel_h[r][j], 448..895: rel_w[c][j]
+  if (o >= 896) return;
+  const bool is_w = o >= 448;
+  const int rc = (is_w ? o - 448 : o) / 32, j = (is_w ? o - 448 : o) % 32;
+  float t = 0.f;
+  for (int u = 0; u < 14; ++u) {
+    const int key = is_w ? u * 14 + rc : rc * 14 + u;
+    t += keysum[key * 64 + (is_w ? 32 + j : j)];
   }
+  if (is_w) d_rel_w[o - 448] = t;
+  else d_rel_h[o] = t;
 }
 
 static int at_grid(int nblocks) {
@@ -1144,13 +1145,16 @@ int attn_bwd_tc(const pht_attn_bwd_args* a, cudaStream_t st, bool* handled) {
                                                P.nby, P.nbx);
     count_launch(CNT_OTHER);
   }
-  attn_bwd_rel_reduce_kernel<<<896, 64, 0, st>>>(P.rel_part, grid, a->d_rel_h, a->d_rel_w);
+  float* keysum = (float*)stream_scratch(st, 2, (size_t)AB_REL_PART * sizeof(float));
+  if (!keysum) return PHT_ERR_CUDA;
+  attn_bwd_rel_keysum_kernel<<<AT_NK, 256, 0, st>>>(P.rel_part, grid, keysum);
+  attn_bwd_rel_reduce_kernel<<<7, 128, 0, st>>>(keysum, a->d_rel_h, a->d_rel_w);
   PHT_LAUNCH_CHECK();
   walk_dir_set(a->dq.ptr, 0);
   walk_dir_set(a->dk.ptr, 0);
   walk_dir_set(a->dv.ptr, 0);
   count_launch(CNT_ATTN_TC);
-  count_launch(CNT_OTHER, 1);
+  count_launch(CNT_OTHER, 2);
   *handled = true;
   return PHT_OK;
 }
