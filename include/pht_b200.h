@@ -425,7 +425,12 @@ void pht_set_force_simple(int on);
  * written in (the most recently written part of the input is still in L2);
  * "strips" = 0 / 1 (default 1): PHT_EPI_PADFOLD launches cover the last two rows of the padded domain with 2 x 64-pixel
  * tiles (fewer, fuller tiles); none of these three changes a result bit;
- * "conv_trace" = 1: CTA 0 of pht_conv_gemm records clock64 stamps per tile (diagnostics);
+ * "cta_pairs" = 0 / 1 (default 0): 1 = pht_conv_gemm launches with 256-wide output tiles run as CTA pairs (2-CTA clusters,
+ * tcgen05 cta_group::2, M = 256): the two CTAs of a pair take adjacent pixel tiles, each loads only half of every weight
+ * tile, and the operand rings are 6 / 4 stages deep instead of 4 / 3.  Bit-identical results; measured no faster on the
+ * AFGSA shapes (see profiles/README.md), hence opt-in;
+ * "conv_trace" = 1: pht_conv_gemm records clock64 stamps per tile of CTA 0 and (start, end, SM, entry) times of every
+ * CTA (diagnostics, read with pht_conv_gemm_trace);
  * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics);
  * "attn_bwd_direct" = 0 / 1 (default 1): 1 = the tcgen05 pht_attn_bwd adds the (up to four) overlapping window
  * contributions of a key pixel straight into dk / dv with vector reductions, in arrival order (fastest; every add rounds
@@ -439,7 +444,8 @@ int pht_set_option(const char* name, int value);
 /* Copies the stamps recorded under "attn_trace" ([iteration][12 events], first 48 iterations of CTA 0) to host memory
  * after a device synchronise; returns the number of values copied or a negative status. */
 int pht_attn_bwd_trace(int64_t* host, int32_t n);
-/* Same for pht_conv_gemm under "conv_trace" = 1: [tile][8 events] of CTA 0 (first 32 tiles). */
+/* Same for pht_conv_gemm under "conv_trace" = 1: [tile][8 events] of CTA 0 (first 32 tiles = 256 values), followed by
+ * [cta][4] = (globaltimer ns after the dependency wait, ns at the end, SM id, ns at kernel entry) for up to 160 CTAs. */
 int pht_conv_gemm_trace(int64_t* host, int32_t n);
 
 #ifdef __cplusplus

@@ -40,6 +40,7 @@ struct TcGemmP {
   View out1;          // only used when out1_f32
   int has_out1, has_out2, has_resid, has_mask;
   int out1_f32;       // out1 is fp32 (direct stores; used by the 64-wide decoder-tail GEMM only)
+  int num_pairs;      // CTA-pair kernels: work units = (pair of pixel tiles, output tile)
   int rev;            // walk the tiles last-to-first
   int trace;          // diagnostics: CTA 0 records clock64 stamps of its pipeline events per tile
   int strip_rows;     // > 0: the last 2 output rows are covered by 2 x 64-pixel strip tiles (pad-fold domain, see conv_gemm_tc)
@@ -53,11 +54,15 @@ struct TcGemmP {
 // MODE 2 "deep+aux": 4-stage ring, one staging tile, one epilogue-input slot: 3x3 convolutions with a fused
 //                    residual / mask / second output / padding fold (their long K loop hides the serial epilogue);
 //                    slope vectors are read through the L1 instead of shared memory to fit in 227 KB.
-template <int BN, int MODE> struct TcCfg {
+// CG = 2 (BN = 256 only): the kernel runs as CTA pairs (2-CTA clusters, one TPC).  A pair computes two 128-pixel tiles
+//                    against the SAME 256 output channels with one M = 256 tcgen05.mma.cta_group::2 per K step: each
+//                    CTA loads its own activation tile and only HALF of the weight tile, so a stage is 32 KB instead of
+//                    48 KB, the rings are 6 / 4 deep instead of 4 / 3 and the weights cross L2 -> SM once per pair.
+template <int BN, int MODE, int CG = 1> struct TcCfg {
   static constexpr int A_BYTES = TILE_M * BK * 2;                  // 16 KB
-  static constexpr int B_BYTES = BN * BK * 2;                      // 32 KB @ BN=256
+  static constexpr int B_BYTES = BN / CG * BK * 2;                 // 32 KB @ BN=256 (16 KB per CTA of a pair)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? (MODE == 1 ? 3 : 4) : (BN == 128 ? 4 : 6);
+  static constexpr int STAGES = BN == 256 ? (CG == 2 ? (MODE == 1 ? 4 : 6) : (MODE == 1 ? 3 : 4)) : (BN == 128 ? 4 : 6);
   static constexpr int NSTG = MODE == 1 ? 2 : 1;
   static constexpr int PARTS = MODE == 1 ? 2 : 1;                  // epilogue warp groups (4 warps = 128 rows each)
   static constexpr int THREADS = PARTS == 2 ? TC_THREADS + 128 : TC_THREADS;
@@ -70,13 +75,17 @@ template <int BN, int MODE> struct TcCfg {
 };
 static_assert(TcCfg<256, 0>::SMEM_BYTES <= 232448 && TcCfg<256, 1>::SMEM_BYTES <= 232448 && TcCfg<256, 2>::SMEM_BYTES <= 232448,
               "conv_gemm_tc: shared memory budget");
+static_assert(TcCfg<256, 0, 2>::SMEM_BYTES <= 232448 && TcCfg<256, 1, 2>::SMEM_BYTES <= 232448 &&
+              TcCfg<256, 2, 2>::SMEM_BYTES <= 232448, "conv_gemm_tc (CTA pairs): shared memory budget");
 
 constexpr int CG_TRACE_TILES = 32, CG_TRACE_EVENTS = 8;
-__device__ long long g_conv_trace[CG_TRACE_TILES * CG_TRACE_EVENTS];
+constexpr int CG_TRACE_CTAS = 160;   // after the tile events: (start ns, end ns, SM id, entry ns) of every CTA
+constexpr int CG_TRACE_CTA_F = 4;
+__device__ long long g_conv_trace[CG_TRACE_TILES * CG_TRACE_EVENTS + CG_TRACE_CTA_F * CG_TRACE_CTAS];
 static int g_conv_trace_on = 0;
 void set_conv_trace(int v) { g_conv_trace_on = v; }
 int read_conv_trace(long long* host, int n) {
-  if (n > CG_TRACE_TILES * CG_TRACE_EVENTS) n = CG_TRACE_TILES * CG_TRACE_EVENTS;
+  if (n > CG_TRACE_TILES * CG_TRACE_EVENTS + CG_TRACE_CTA_F * CG_TRACE_CTAS) n = CG_TRACE_TILES * CG_TRACE_EVENTS + CG_TRACE_CTA_F * CG_TRACE_CTAS;
   PHT_CUDA(cudaDeviceSynchronize());
   PHT_CUDA(cudaMemcpyFromSymbol(host, g_conv_trace, (size_t)n * sizeof(long long)));
   return n;
@@ -88,11 +97,22 @@ int read_conv_trace(long long* host, int n) {
 struct TileXY {
   int b, x0, y0, nt, strip;
 };
-__device__ __forceinline__ TileXY decode_tile(const TcGemmP& P, int tile) {
-  const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
+// CG == 2: `tile` is the pair's work unit and `rank` the CTA's rank in the pair; the pair takes pixel tiles 2m and 2m+1
+// of ONE output tile (they share the weights).  A pixel tile past the end decodes to b == P.B: its loads are zero-filled
+// and its stores clipped by the TMA unit.
+template <int CG>
+__device__ __forceinline__ TileXY decode_tile(const TcGemmP& P, int tile, int rank) {
   TileXY t;
-  t.nt = te % P.n_tiles;
-  const int mt = te / P.n_tiles;
+  int mt;
+  if (CG == 2) {
+    const int u = P.rev ? P.num_pairs - 1 - tile : tile;
+    t.nt = u % P.n_tiles;
+    mt = (u / P.n_tiles) * 2 + rank;
+  } else {
+    const int te = P.rev ? P.num_tiles - 1 - tile : tile;   // serpentine launch order (see conv_gemm_tc)
+    t.nt = te % P.n_tiles;
+    mt = te / P.n_tiles;
+  }
   const int reg = P.tiles_x * P.reg_tiles_y, per_img = reg + P.n_strip;
   t.b = mt / per_img;
   const int r = mt - t.b * per_img;
@@ -128,8 +148,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <int BN, int MODE>
-__global__ void __launch_bounds__((TcCfg<BN, MODE>::THREADS), 1)
+template <int BN, int MODE, int CG>
+__global__ void __launch_bounds__((TcCfg<BN, MODE, CG>::THREADS), 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -137,7 +157,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     const __grid_constant__ CUtensorMap tmA0s, const __grid_constant__ CUtensorMap tmO1s,
                     const __grid_constant__ CUtensorMap tmO2s, const __grid_constant__ CUtensorMap tmRs,
                     const __grid_constant__ CUtensorMap tmMs, const TcGemmP P) {
-  using Cfg = TcCfg<BN, MODE>;
+  using Cfg = TcCfg<BN, MODE, CG>;
   constexpr int NCHUNK = BN / 64;
   constexpr bool AUX = Cfg::AUX_SLOTS > 0;
   constexpr int PARTS = Cfg::PARTS;
@@ -160,38 +180,54 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work units: tiles, or (CTA pairs) pairs of pixel tiles
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_units = CG == 2 ? P.num_pairs : P.num_tiles;
 
+  long long t_entry = 0;
+  if (P.trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
     if (P.n_src > 1) prefetch_tmap(&tmA1);
     if (P.n_src > 2) prefetch_tmap(&tmA2);
     prefetch_tmap(&tmW);
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 1);       // pairs: only the leader's barrier is used; it is armed for the bytes of both CTAs
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128 * PARTS);
+      // pairs: the leader's barrier also collects one arrival per epilogue WARP of the peer
+      mbar_init(&tempty_bar[a], CG == 2 ? 128 * PARTS + 4 * PARTS : 128 * PARTS);
       mbar_init(&afull_bar[a], 1);
       mbar_init(&aempty_bar[a], 128);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  griddep_wait();   // everything above overlapped the previous kernel's tail; global memory is read from here on
-  for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
-    s_bias[i] = P.bias ? P.bias[i] : 0.f;
-    if (Cfg::VEC_SMEM) {
-      s_slope[i] = P.slope ? P.slope[i] : 1.f;
-      s_mslope[i] = P.mslope ? P.mslope[i] : 0.f;
-    }
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
-  griddep_launch();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above ran while the previous kernel of the stream was still finishing (no global memory touched).  The
+  // loads start the moment it has completed; the bias / slope vectors are staged by the epilogue warps on their own
+  // (they have nothing to do until the first accumulator is complete), off the producer's critical path.
+  griddep_wait();
+  griddep_launch();
+  if (P.trace && threadIdx.x == 0 && blockIdx.x < CG_TRACE_CTAS) {
+    long long t;
+    uint32_t sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    long long* rec = g_conv_trace + CG_TRACE_TILES * CG_TRACE_EVENTS + CG_TRACE_CTA_F * blockIdx.x;
+    rec[0] = t; rec[2] = sm; rec[3] = t_entry;
+  }
 
   const int T = P.ks * P.ks, half = P.ks / 2;
   const int n_kinds = P.has_resid + P.has_mask;   // epilogue-input tiles per 64-channel chunk
@@ -206,8 +242,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int pit = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++pit) {
-        const TileXY tl = decode_tile(P, tile);
+      const uint32_t full_leader = CG == 2 ? mapa_u32(&full_bar[0], 0) : 0u;
+      for (int tile = unit0; tile < num_units; tile += unit_step, ++pit) {
+        const TileXY tl = decode_tile<CG>(P, tile, cta_rank);
         const int b = tl.b, x0 = tl.x0, y0 = tl.y0, n0 = tl.nt * BN;
         bool first = true;
         for (int t = 0; t < T; ++t) {
@@ -219,9 +256,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
               if (first) { stamp(pit, 0); first = false; }
               uint8_t* a_dst = stage_base + stage * Cfg::STAGE_BYTES;
               uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-              tma_load_4d(a_dst, tm, &full_bar[stage], kc, x0 + dx + P.srcOx[s], y0 + dy + P.srcOy[s], b);
-              tma_load_3d(b_dst, &tmW, &full_bar[stage], P.koff[s] + kc, n0, t);
+              if (CG == 2) {
+                // this CTA's pixel tile and its half of the weight tile; both signal the LEADER's barrier, which the
+                // leader arms for the bytes of both CTAs (the peer's bytes may land first: the count just goes negative)
+                const uint32_t fb = full_leader + stage * 8;
+                if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                tma_load_4d_2sm(a_dst, tm, fb, kc, x0 + dx + P.srcOx[s], y0 + dy + P.srcOy[s], b);
+                tma_load_3d_2sm(b_dst, &tmW, fb, P.koff[s] + kc, n0 + cta_rank * (BN / 2), t);
+              } else {
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_4d(a_dst, tm, &full_bar[stage], kc, x0 + dx + P.srcOx[s], y0 + dy + P.srcOy[s], b);
+                tma_load_3d(b_dst, &tmW, &full_bar[stage], P.koff[s] + kc, n0, t);
+              }
               if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -231,15 +277,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    {   // all 32 lanes run the loop (warp-converged); one elected lane issues each tcgen05 instruction
-      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, 0, 0);
+    if (CG == 1 || cta_rank == 0) {   // all 32 lanes run the loop (warp-converged); one elected lane issues each tcgen05 instruction
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M * CG, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int kiters = 0;
       for (int s = 0; s < P.n_src; ++s) kiters += P.srcC[s] / BK;
       kiters *= T;
       int it = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit0; tile < num_units; tile += unit_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -255,12 +301,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in the (>>4) address field
-            umma_bf16_elect(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) ? 1u : 0u);
+            if (CG == 2) umma_bf16_elect_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) ? 1u : 0u);
+            else umma_bf16_elect(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) ? 1u : 0u);
           }
-          umma_commit_elect(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) when the MMAs above have read it
+          if (CG == 2) umma_commit_elect_2sm(&empty_bar[stage]);
+          else umma_commit_elect(&empty_bar[stage]);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_elect(&tfull_bar[acc]);      // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CG == 2) umma_commit_elect_2sm(&tfull_bar[acc]);
+        else umma_commit_elect(&tfull_bar[acc]);
         stamp(it, 3);
       }
     }
@@ -275,8 +326,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       prefetch_tmap(&tmM);
       int j = 0;
       int fills[2] = {0, 0};   // PARTS == 2: slot p is a depth-1 FIFO feeding epilogue group p (chunks c with c % 2 == p)
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const TileXY tl = decode_tile(P, tile);
+      for (int tile = unit0; tile < num_units; tile += unit_step) {
+        const TileXY tl = decode_tile<CG>(P, tile, cta_rank);
         const int b = tl.b, x0 = tl.x0, y0 = tl.y0, n0 = tl.nt * BN;
         const CUtensorMap* tmRr = tl.strip ? &tmRs : &tmR;
         const CUtensorMap* tmMm = tl.strip ? &tmMs : &tmM;
@@ -298,6 +349,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int part = (PARTS == 2 && warp >= 7) ? 1 : 0;   // epilogue group: takes the 64-channel chunks c with c % PARTS == part
     const int row = quad * 32 + lane;      // accumulator row == pixel index inside the tile
     const bool issuer = ((warp == 2 || warp == 7) && lane == 0);
+    {   // stage the per-channel vectors (all epilogue threads; nobody else reads them)
+      const int eid = (warp >= 7 ? 128 + (warp - 7) * 32 : (warp - 2) * 32) + lane;
+      for (int i = eid; i < P.N; i += 128 * PARTS) {
+        s_bias[i] = P.bias ? P.bias[i] : 0.f;
+        if (Cfg::VEC_SMEM) {
+          s_slope[i] = P.slope ? P.slope[i] : 1.f;
+          s_mslope[i] = P.mslope ? P.mslope[i] : 0.f;
+        }
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(128 * PARTS) : "memory");
+    }
     auto group_sync = [&]() {
       if (part == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -340,25 +402,32 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       ++j_aux;
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x, ++it) {
-      const TileXY tl = decode_tile(P, tile);
+    const uint32_t tempty_leader = CG == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
+    auto release_acc = [&](int acc) {
+      tc_fence_before();
+      if (CG == 2 && cta_rank != 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + acc * 8);
+      } else {
+        mbar_arrive(&tempty_bar[acc]);
+      }
+    };
+    for (int tile = unit0; tile < num_units; tile += unit_step, ++it) {
+      const TileXY tl = decode_tile<CG>(P, tile, cta_rank);
       const int b = tl.b, x0 = tl.x0, y0 = tl.y0;
       const int tw = tl.strip ? 64 : TILE_W;               // tile width in pixels (rows of the tile are tw pixels apart)
       const int py = tl.strip ? (row >> 6) : row / TILE_W, px = tl.strip ? (row & 63) : row % TILE_W;
       const CUtensorMap* tmOut1 = tl.strip ? &tmO1s : &tmO1;
       const CUtensorMap* tmOut2 = tl.strip ? &tmO2s : &tmO2;
       const int x = x0 + px, y = y0 + py, n0 = tl.nt * BN;
-      const bool valid = x < P.Wo && y < P.Ho;
+      const bool valid = x < P.Wo && y < P.Ho && b < P.B;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (warp == 2 || warp == 7) stamp(it, warp == 2 ? 4 : 6);
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      if (part * 64 >= BN) {               // this group has no chunk of the tile
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[acc]);
-      }
+      if (part * 64 >= BN) release_acc(acc);   // this group has no chunk of the tile
 #pragma unroll 1
       for (int c0 = part * 64; c0 < BN; c0 += 64 * PARTS) {
         float v[64];
@@ -373,10 +442,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r[j]);
         }
-        if (c0 + 64 * PARTS >= BN) {       // this group's share of the accumulator is in registers: release it
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[acc]);
-        }
+        if (c0 + 64 * PARTS >= BN) release_acc(acc);   // this group's share of the accumulator is in registers: release it
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] += s_bias[n0 + c0 + j];
         if (MODE != 0 && (P.flags & PHT_EPI_PADFOLD)) {
@@ -433,14 +499,23 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       }
       if (warp == 2 || warp == 7) stamp(it, warp == 2 ? 5 : 7);
     }
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all tensor stores complete before exit
+    // the staging tiles may be released once the tensor stores have READ them; their global writes are complete (and
+    // visible to a dependent launch) when the grid is
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the leader's MMAs read the peer's shared memory and write its TMEM until here
+  else __syncthreads();
+  if (P.trace && threadIdx.x == 0 && blockIdx.x < CG_TRACE_CTAS) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_conv_trace[CG_TRACE_TILES * CG_TRACE_EVENTS + CG_TRACE_CTA_F * blockIdx.x + 1] = t;
+  }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -515,11 +590,23 @@ struct TcMaps {
 template <int BN, int MODE>
 static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
   using Cfg = TcCfg<BN, MODE>;
-  PHT_SMEM_ATTR_ONCE((conv_gemm_tc_kernel<BN, MODE>), Cfg::SMEM_BYTES);
+  PHT_SMEM_ATTR_ONCE((conv_gemm_tc_kernel<BN, MODE, 1>), Cfg::SMEM_BYTES);
   const int sms = sm_count();
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
-  PHT_CUDA(launch_pdl(conv_gemm_tc_kernel<BN, MODE>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1], m.A[2], m.W,
+  PHT_CUDA(launch_pdl(conv_gemm_tc_kernel<BN, MODE, 1>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1], m.A[2], m.W,
                       m.O[0], m.O[1], m.R, m.M, m.As, m.Os[0], m.Os[1], m.Rs, m.Ms, P));
+  PHT_LAUNCH_CHECK();
+  return PHT_OK;
+}
+// CTA-pair variant (BN = 256; m.W must have been encoded with a 128-row box)
+template <int MODE>
+static int launch_tc_pairs(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
+  using Cfg = TcCfg<256, MODE, 2>;
+  PHT_SMEM_ATTR_ONCE((conv_gemm_tc_kernel<256, MODE, 2>), Cfg::SMEM_BYTES);
+  const int pairs_max = sm_count() / 2;
+  const int grid = 2 * (P.num_pairs < pairs_max ? P.num_pairs : pairs_max);
+  PHT_CUDA(launch_pdl_pairs(conv_gemm_tc_kernel<256, MODE, 2>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1],
+                            m.A[2], m.W, m.O[0], m.O[1], m.R, m.M, m.As, m.Os[0], m.Os[1], m.Rs, m.Ms, P));
   PHT_LAUNCH_CHECK();
   return PHT_OK;
 }
@@ -539,6 +626,8 @@ void walk_dir_set(const void* p, int dir) {
   e.ptr = p; e.dir = dir;
 }
 static std::atomic<int> g_strips{1};
+static std::atomic<int> g_cta_pairs{0};   // BN = 256 GEMMs as CTA pairs (tcgen05 cta_group::2)
+void set_cta_pairs(int v) { g_cta_pairs.store(v, std::memory_order_relaxed); }
 void set_strips(int v) { g_strips.store(v, std::memory_order_relaxed); }
 void set_serpentine(int v) { g_serpentine.store(v, std::memory_order_relaxed); }
 void set_tc_cfg(int v) { g_tc_cfg.store(v, std::memory_order_relaxed); }
@@ -588,10 +677,12 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
     }
   }
   const int T = a->ksize * a->ksize;
+  const int force = g_tc_cfg.load(std::memory_order_relaxed);
+  const bool pairs = BN == 256 && g_cta_pairs.load(std::memory_order_relaxed) != 0;
   {
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)a->N, (uint64_t)T};
     uint64_t strides[2] = {(uint64_t)ktot * 2, (uint64_t)ktot * a->N * 2};
-    uint32_t box[3] = {BK, (uint32_t)BN, 1};
+    uint32_t box[3] = {BK, (uint32_t)(pairs ? BN / 2 : BN), 1};
     int rc = make_tmap_bf16(&m.W, const_cast<void*>(a->w), 3, dims, strides, box);
     if (rc) return rc;
   }
@@ -614,6 +705,7 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   P.reg_tiles_y = strips ? (a->Ho - 2) / TILE_H : P.tiles_y;
   P.n_strip = strips ? ceil_div(a->Wo, 64) : 0;
   P.num_tiles = a->B * (P.tiles_x * P.reg_tiles_y + P.n_strip) * P.n_tiles;
+  P.num_pairs = ceil_div(P.num_tiles / P.n_tiles, 2) * P.n_tiles;
   P.bias = a->bias; P.slope = a->slope; P.mslope = a->mslope;
   P.out1 = a->out1.ptr ? make_view(a->out1) : null_view();
   P.has_out1 = a->out1.ptr ? 1 : 0; P.has_out2 = a->out2.ptr ? 1 : 0;
@@ -638,7 +730,6 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   if (rc) return rc;
   // 1x1 GEMMs are HBM-bound: wide epilogue.  3x3: deep ring; with a fused epilogue (inputs, second output, fold) the
   // deep+aux variant.
-  const int force = g_tc_cfg.load(std::memory_order_relaxed);
   const bool fused = has_resid || has_mask || (a->out1.ptr && a->out2.ptr) || padfold;
   int mode = a->ksize == 1 ? 1 : (fused ? 2 : 0);
   if (mode == 2 && a->N > TcCfg<256, 2>::VEC_N) mode = 1;   // (the slope vectors do not fit beside the deep ring)
@@ -646,7 +737,8 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   if (force == 4 && a->ksize == 3 && fused) mode = 1;   // A/B: fused 3x3 (pad-fold included) on the two-group "wide" config
   if (force == 1 && !fused) mode = 0;
   if (force == 3 && a->ksize == 1 && a->N <= TcCfg<256, 2>::VEC_N) mode = fused ? 2 : 0;
-  if (BN == 256) rc = mode == 0 ? launch_tc<256, 0>(P, m, st) : (mode == 1 ? launch_tc<256, 1>(P, m, st) : launch_tc<256, 2>(P, m, st));
+  if (pairs) rc = mode == 0 ? launch_tc_pairs<0>(P, m, st) : (mode == 1 ? launch_tc_pairs<1>(P, m, st) : launch_tc_pairs<2>(P, m, st));
+  else if (BN == 256) rc = mode == 0 ? launch_tc<256, 0>(P, m, st) : (mode == 1 ? launch_tc<256, 1>(P, m, st) : launch_tc<256, 2>(P, m, st));
   else if (BN == 128) rc = mode == 0 ? launch_tc<128, 0>(P, m, st) : (mode == 1 ? launch_tc<128, 1>(P, m, st) : launch_tc<128, 2>(P, m, st));
   else rc = mode == 0 ? launch_tc<64, 0>(P, m, st) : (mode == 1 ? launch_tc<64, 1>(P, m, st) : launch_tc<64, 2>(P, m, st));
   if (rc) return rc;

@@ -84,6 +84,44 @@ def test_conv_gemm_zero_pad_matches_conv2d(dtype, ks, cin, cout, B, H, W):
     assert rel_err(nchw(out), ref) < tol(dtype)
 
 
+@pytest.mark.parametrize("ks,cin,cout,B,H,W,fused", [(3, 256, 256, 2, 32, 32, False), (1, 512, 256, 3, 24, 16, True),
+                                                      (3, 256, 512, 1, 24, 16, True), (1, 256, 256, 2, 128, 128, False)])
+def test_conv_gemm_cta_pairs_bit_identical(ks, cin, cout, B, H, W, fused):
+    """Option "cta_pairs" = 1 runs the 256-wide GEMMs as CTA pairs (tcgen05 cta_group::2, M = 256).  Same K order, same
+    epilogue: the outputs must be bit-identical to the single-CTA kernel, an odd number of pixel tiles (one CTA of the
+    last pair has no tile) and two output tiles (N = 512) included."""
+    ops = _ops()
+    from pixel_heal_thyself_b200 import _lib
+    torch.manual_seed(5)
+    dtype = torch.bfloat16
+    x = torch.randn(B, H, W, cin, device=DEV).to(dtype)
+    wp = pack(torch.randn(cout, cin, ks, ks, device=DEV) / (cin * ks * ks) ** 0.5, dtype)
+    bias = torch.randn(cout, device=DEV)
+    slope = torch.full((cout,), 0.2, device=DEV)
+    resid = torch.randn(B, H, W, cout, device=DEV).to(dtype) if fused else None
+
+    def run():
+        o1 = torch.zeros(B, H, W, cout, dtype=dtype, device=DEV)
+        o2 = torch.zeros(B, H, W, cout, dtype=dtype, device=DEV) if fused else None
+        kw = dict(resid=resid, resid_mode="post", out2=o2) if fused else {}
+        before = _lib.counters()["gemm_tc"]
+        ops.conv_gemm([x], wp, cout, ksize=ks, bias=bias, slope=slope, out1=o1, **kw)
+        assert _lib.counters()["gemm_tc"] == before + 1
+        torch.cuda.synchronize()
+        return o1, o2
+
+    a = run()
+    _lib.lib.pht_set_option(b"cta_pairs", 1)
+    try:
+        b = run()
+    finally:
+        _lib.lib.pht_set_option(b"cta_pairs", 0)
+    assert torch.equal(a[0], b[0])
+    if fused:
+        assert torch.equal(a[1], b[1])
+    assert float(a[0].float().abs().max()) > 0
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode", ["replicate", "reflect"])
 def test_padded_conv_forward_and_backward(dtype, mode, cuda_core_bf16_allowed):

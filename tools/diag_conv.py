@@ -39,10 +39,19 @@ print(f"conv_gemm K={args.k} N={args.n} ks={args.ks}: median {sorted(ts)[5]:.1f}
 _lib.lib.pht_set_option(b"conv_trace", 1)
 flush.zero_()
 fn()
-buf = (C.c_int64 * (32 * 8))()
-n = _lib.lib.pht_conv_gemm_trace(buf, 32 * 8)
+buf = (C.c_int64 * (32 * 8 + 4 * 160))()
+n = _lib.lib.pht_conv_gemm_trace(buf, 32 * 8 + 4 * 160)
 _lib.lib.pht_set_option(b"conv_trace", 0)
-t = torch.tensor(list(buf)[:n]).view(-1, 8)
+ctas = torch.tensor(list(buf)[32 * 8:n]).view(-1, 4)[:148]
+t = torch.tensor(list(buf)[:32 * 8]).view(-1, 8)
+g0 = int(ctas[:, 0].min())
+st, en = (ctas[:, 0] - g0).float() / 1e3, (ctas[:, 1] - g0).float() / 1e3
+q = lambda v: " ".join(f"{float(x):7.1f}" for x in torch.quantile(v, torch.tensor([0.0, 0.1, 0.5, 0.9, 1.0])))
+print(f"per-CTA start us (min p10 p50 p90 max): {q(st)}")
+print(f"per-CTA end   us (min p10 p50 p90 max): {q(en)}")
+print(f"per-CTA busy  us (min p10 p50 p90 max): {q(en - st)}")
+order = torch.argsort(en, descending=True)[:8]
+print("slowest CTAs (cta, sm, end us): " + " ".join(f"({int(i)},{int(ctas[i, 2])},{float(en[i]):.1f})" for i in order))
 t0 = int(t[0, 0])
 print("per tile: 0=first stage issued 1=last stage issued 2=first MMA 3=MMAs issued 4=epi0 sees acc 5=epi0 done 6=epi1 sees acc 7=epi1 done")
 for i in range(8):

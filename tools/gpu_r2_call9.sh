@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for o in "" cta_pairs=1; do for ks in 3 1; do echo "== opt=$o ks=$ks"; PHT_OPTIONS=$o timeout 120 python tools/diag_conv.py --ks $ks 2>&1 | grep -v Warn | head -6; done; done
+PHT_OPTIONS=cta_pairs=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "conv_gemm or padded_conv or padfold or encoder or decoder_tail" > gpurun_out/r2k_ops.log 2>&1; rc=$?; echo "pairs op tests rc=$rc"; tail -2 gpurun_out/r2k_ops.log
+for opt in "" "cta_pairs=1" "" "cta_pairs=1"; do
+  PHT_OPTIONS=$opt timeout 600 python bench.py --no-stock --no-cpu-baseline --no-inference --no-sustained --no-gan-extra > gpurun_out/r2k_bench.json 2> gpurun_out/r2k_bench.err; python - "$opt" <<'PY'
+import json,sys
+d=json.loads([l for l in open('gpurun_out/r2k_bench.json') if l.startswith('{')][-1])
+print('opt=%r value %.1f ms %.3f e2e %.1f' % (sys.argv[1], d['value'], d['ms_per_step'], d['e2e']['value']))
+PY
+done

@@ -76,7 +76,72 @@ __global__ void __launch_bounds__(160, 1) rate_kernel(const Shape* shapes, int n
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tm, 512); }
 }
 
-int main() {
+// CTA-pair rate: a 2-CTA cluster, the leader issues tcgen05.mma.cta_group::2 (M = 256 over both CTAs), operands are
+// whatever the (zeroed) shared memory of the two CTAs holds.
+__global__ void __launch_bounds__(160, 1) rate2_kernel(int M, int N, int reps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) tmem_alloc_2sm(&slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tm = slot;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x < 32) {
+    uint32_t ph = 0;
+    const uint32_t idesc = umma_idesc_bf16(M, N, 0, 0);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 64 * 1024);
+    for (int pass = 0; pass < 2; ++pass) {
+      const long long t0 = clock64();
+      if (rank == 0) {
+#pragma unroll 1
+        for (int r = 0; r < reps; r += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) umma_bf16_elect_2sm(tm, umma_desc_k_sw128(a0) + 2 * u, umma_desc_k_sw128(b0) + 2 * u, idesc, 1u);
+        }
+        umma_commit_elect_2sm(&bar);
+      }
+      mbar_wait(&bar, ph);
+      ph ^= 1;
+      const long long t1 = clock64();
+      if (pass && threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc_2sm(tm, 512); }
+}
+
+static void run_pairs(long long* dout, int grid, int reps) {
+  cudaFuncSetAttribute(rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  printf("---- CTA pairs: tcgen05.mma.cta_group::2, K-major bf16 operands ----\n%5s %5s %12s %18s\n", "M", "N", "clk/MMA", "MAC/clk/SM");
+  const int shapes[][2] = {{256, 256}, {256, 128}, {256, 64}, {128, 256}, {128, 128}};
+  for (auto& sh : shapes) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(160); cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rate2_kernel, sh[0], sh[1], reps, dout);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return; }
+    long long* h = (long long*)malloc(sizeof(long long) * grid);
+    cudaMemcpy(h, dout, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int b = 0; b < grid; ++b) mx = h[b] > mx ? h[b] : mx;
+    const double c = (double)mx / reps;
+    printf("%5d %5d %12.1f %18.0f\n", sh[0], sh[1], c, (double)sh[0] / 2 * sh[1] * 16 / c);
+    free(h);
+  }
+}
+
+int main(int argc, char** argv) {
   const Shape hs[] = {
       {128, 256, 0, 0, 1}, {128, 256, 0, 0, 2}, {128, 128, 0, 0, 1}, {128, 128, 0, 0, 2}, {128, 64, 0, 0, 1}, {128, 64, 0, 0, 2},
       {128, 64, 0, 0, 4},  {128, 64, 1, 1, 4},  {128, 32, 0, 0, 4},  {128, 16, 0, 0, 4},  {64, 256, 0, 0, 1}, {64, 256, 0, 0, 2},
@@ -94,6 +159,8 @@ int main() {
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   long long* dstats;
   cudaMalloc(&dstats, sizeof(long long) * 16);
+  run_pairs(dout, grid, reps);
+  if (argc > 1) return 0;   // any argument: the CTA-pair table only
   for (int ldw : {0, 4, 104}) {
     const int g = grid;
     const int ld_warps = ldw % 100, ld_cols = ldw >= 100 ? 0 : 384;
