@@ -49,7 +49,7 @@ def _traffic():
     n = t["launches_per_step"]
     mean = (t["conv3x3_deep_bytes"] * n["deep"] + t["conv3x3_fused_bytes"] * n["fused"]) / (n["deep"] + n["fused"])
     return mean, {"deep": t["conv3x3_deep_bytes"], "fused_epilogue": t["conv3x3_fused_bytes"], "unit": "bytes/launch",
-                  "source": "profiles/r1_ncu_full_conv_final.txt"}
+                  "source": t.get("source", "profiles/r2_ncu_full_conv.txt")}
 
 
 def _peaks():
