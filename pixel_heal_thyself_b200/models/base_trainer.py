@@ -274,6 +274,23 @@ class BaseTrainer(ABC):
         if not self.g_only:
             d_loss = self._critic_step(output.detach(), gt)
         self.opt_g.zero_grad()
+        if (self.g_only and self.ssim_loss is None and output.is_cuda and output.dtype == torch.float32
+                and type(self.l1_loss) is L1ReconstructionLoss):
+            # G-only step, L1 term only (the BASELINE configuration): the fused loss kernel already produces
+            # d(l1_loss_w * L1) / d(output), so the generator's backward starts from it directly -- no scalar
+            # ones-fill / multiply launches between the loss kernel and the first gradient kernel
+            from .. import ops
+            a, b = output.detach().contiguous(), gt.contiguous().float()
+            loss = torch.empty(1, dtype=torch.float32, device=a.device)
+            d_out = torch.empty_like(a)
+            ops.l1_loss(a, b, loss, d_out, grad_scale=float(lw.l1_loss_w))
+            g_loss = loss.reshape(()) if float(lw.l1_loss_w) == 1.0 else loss.reshape(()) * float(lw.l1_loss_w)
+            output.backward(d_out)
+            if self.bucketer is not None:
+                _, aliased = self.opt_g.gather_grads()
+                self.bucketer.finish(aliased)
+            self.opt_g.step()
+            return g_loss.detach(), None
         g_loss = lw.l1_loss_w * self.l1_loss(output, gt)
         if not self.g_only:
             # the generator's adversarial term only needs d D / d input: skip the critic's weight gradients (the reference
