@@ -429,6 +429,9 @@ void pht_set_force_simple(int on);
  * tcgen05 cta_group::2, M = 256): the two CTAs of a pair take adjacent pixel tiles, each loads only half of every weight
  * tile, and the operand rings are 6 / 4 stages deep instead of 4 / 3.  Bit-identical results; measured no faster on the
  * AFGSA shapes (see profiles/README.md), hence opt-in;
+ * "half_ring" = 0 / 1 (default 0): 1 = the 3x3 launches of pht_conv_gemm use an operand ring of 8 half stages (32 channels
+ * deep, 64-byte swizzle rows) instead of 4 full ones.  Bit-identical; measured slower (the tensor core reads 64-byte swizzle
+ * rows at about half the rate), kept for the record; "conv_grid_cap" = n: at most n CTAs per pht_conv_gemm launch (diagnostics);
  * "conv_trace" = 1: pht_conv_gemm records clock64 stamps per tile of CTA 0 and (start, end, SM, entry) times of every
  * CTA (diagnostics, read with pht_conv_gemm_trace);
  * "attn_trace" = 1 / 2: CTA 0 of pht_attn_bwd / pht_attn_fwd records clock64 stamps of its pipeline events (diagnostics);

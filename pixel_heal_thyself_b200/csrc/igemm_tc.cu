@@ -58,11 +58,17 @@ struct TcGemmP {
 //                    against the SAME 256 output channels with one M = 256 tcgen05.mma.cta_group::2 per K step: each
 //                    CTA loads its own activation tile and only HALF of the weight tile, so a stage is 32 KB instead of
 //                    48 KB, the rings are 6 / 4 deep instead of 4 / 3 and the weights cross L2 -> SM once per pair.
-template <int BN, int MODE, int CG = 1> struct TcCfg {
-  static constexpr int A_BYTES = TILE_M * BK * 2;                  // 16 KB
-  static constexpr int B_BYTES = BN / CG * BK * 2;                 // 32 KB @ BN=256 (16 KB per CTA of a pair)
+// BKS = 32 (BN = 256, CG = 1, MODE 0 / 2): the operand ring is cut into 32-deep half stages (24 KB, 64-byte swizzle
+//                    rows), 8 of them.  The K loop of the 3x3 convolutions is bound by the refill latency of the ring
+//                    (measured: tile period independent of the number of CTAs, 586 clk per 64-deep step with 4 stages,
+//                    703 with 3): with half stages 7 x 24 KB instead of 3 x 48 KB are in flight behind the one being
+//                    consumed.
+template <int BN, int MODE, int CG = 1, int BKS_ = BK> struct TcCfg {
+  static constexpr int BKS = BKS_;                                 // K depth of one ring stage
+  static constexpr int A_BYTES = TILE_M * BKS * 2;                 // 16 KB
+  static constexpr int B_BYTES = BN / CG * BKS * 2;                // 32 KB @ BN=256 (16 KB per CTA of a pair)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? (CG == 2 ? (MODE == 1 ? 4 : 6) : (MODE == 1 ? 3 : 4)) : (BN == 128 ? 4 : 6);
+  static constexpr int STAGES = BKS == 32 ? 8 : (BN == 256 ? (CG == 2 ? (MODE == 1 ? 4 : 6) : (MODE == 1 ? 3 : 4)) : (BN == 128 ? 4 : 6));
   static constexpr int NSTG = MODE == 1 ? 2 : 1;
   static constexpr int PARTS = MODE == 1 ? 2 : 1;                  // epilogue warp groups (4 warps = 128 rows each)
   static constexpr int THREADS = PARTS == 2 ? TC_THREADS + 128 : TC_THREADS;
@@ -75,6 +81,7 @@ template <int BN, int MODE, int CG = 1> struct TcCfg {
 };
 static_assert(TcCfg<256, 0>::SMEM_BYTES <= 232448 && TcCfg<256, 1>::SMEM_BYTES <= 232448 && TcCfg<256, 2>::SMEM_BYTES <= 232448,
               "conv_gemm_tc: shared memory budget");
+static_assert(TcCfg<256, 0, 1, 32>::SMEM_BYTES <= 232448 && TcCfg<256, 2, 1, 32>::SMEM_BYTES <= 232448, "conv_gemm_tc (half stages)");
 static_assert(TcCfg<256, 0, 2>::SMEM_BYTES <= 232448 && TcCfg<256, 1, 2>::SMEM_BYTES <= 232448 &&
               TcCfg<256, 2, 2>::SMEM_BYTES <= 232448, "conv_gemm_tc (CTA pairs): shared memory budget");
 
@@ -148,8 +155,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <int BN, int MODE, int CG>
-__global__ void __launch_bounds__((TcCfg<BN, MODE, CG>::THREADS), 1)
+template <int BN, int MODE, int CG, int BKS>
+__global__ void __launch_bounds__((TcCfg<BN, MODE, CG, BKS>::THREADS), 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -157,7 +164,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     const __grid_constant__ CUtensorMap tmA0s, const __grid_constant__ CUtensorMap tmO1s,
                     const __grid_constant__ CUtensorMap tmO2s, const __grid_constant__ CUtensorMap tmRs,
                     const __grid_constant__ CUtensorMap tmMs, const TcGemmP P) {
-  using Cfg = TcCfg<BN, MODE, CG>;
+  using Cfg = TcCfg<BN, MODE, CG, BKS>;
   constexpr int NCHUNK = BN / 64;
   constexpr bool AUX = Cfg::AUX_SLOTS > 0;
   constexpr int PARTS = Cfg::PARTS;
@@ -251,7 +258,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           const int dy = t / P.ks - half, dx = t % P.ks - half;
           for (int s = 0; s < P.n_src; ++s) {
             const CUtensorMap* tm = tl.strip ? &tmA0s : (s == 0 ? &tmA0 : (s == 1 ? &tmA1 : &tmA2));
-            for (int kc = 0; kc < P.srcC[s]; kc += BK) {
+            for (int kc = 0; kc < P.srcC[s]; kc += BKS) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               if (first) { stamp(pit, 0); first = false; }
               uint8_t* a_dst = stage_base + stage * Cfg::STAGE_BYTES;
@@ -282,7 +289,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int kiters = 0;
-      for (int s = 0; s < P.n_src; ++s) kiters += P.srcC[s] / BK;
+      for (int s = 0; s < P.n_src; ++s) kiters += P.srcC[s] / BKS;
       kiters *= T;
       int it = 0;
       for (int tile = unit0; tile < num_units; tile += unit_step, ++it) {
@@ -296,11 +303,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           tc_fence_after();
           if (ki == 0) stamp(it, 2);
           const uint32_t a_addr = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_k_sw128(a_addr);
-          const uint64_t bdesc = umma_desc_k_sw128(a_addr + Cfg::A_BYTES);
+          const uint64_t adesc = BKS == 32 ? umma_desc_k_sw64(a_addr) : umma_desc_k_sw128(a_addr);
+          const uint64_t bdesc = BKS == 32 ? umma_desc_k_sw64(a_addr + Cfg::A_BYTES) : umma_desc_k_sw128(a_addr + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128B swizzle row: +2 in the (>>4) address field
+          for (int k = 0; k < BKS / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (>>4) address field
             if (CG == 2) umma_bf16_elect_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) ? 1u : 0u);
             else umma_bf16_elect(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ki | k) ? 1u : 0u);
           }
@@ -575,11 +582,12 @@ static bool view_tma_ok(const pht_view& v) {
   return true;
 }
 
-static int make_src_tmap(CUtensorMap* tm, const pht_view& v, int B, bool strip = false) {
+// bk = channels per box: 64 (128-byte swizzle rows) or 32 (64-byte swizzle rows, half-stage operand ring)
+static int make_src_tmap(CUtensorMap* tm, const pht_view& v, int B, bool strip = false, int bk = BK) {
   uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)v.sx * 2, (uint64_t)v.sy * 2, (uint64_t)v.sb * 2};
-  uint32_t box[4] = {BK, strip ? 64u : (uint32_t)TILE_W, strip ? 2u : (uint32_t)TILE_H, 1};
-  return make_tmap_bf16(tm, v.ptr, 4, dims, strides, box);
+  uint32_t box[4] = {(uint32_t)bk, strip ? 64u : (uint32_t)TILE_W, strip ? 2u : (uint32_t)TILE_H, 1};
+  return make_tmap_bf16(tm, v.ptr, 4, dims, strides, box, bk * 2);
 }
 
 struct TcMaps {
@@ -587,13 +595,19 @@ struct TcMaps {
   CUtensorMap As, Os[2], Rs, Ms;   // 2 x 64-pixel strip boxes (pad-fold domain only)
 };
 
-template <int BN, int MODE>
+static std::atomic<int> g_grid_cap{0};    // diagnostics: at most this many CTAs per launch (0 = one per SM)
+void set_conv_grid_cap(int v) { g_grid_cap.store(v, std::memory_order_relaxed); }
+static inline int conv_sms() {
+  const int cap = g_grid_cap.load(std::memory_order_relaxed), sms = sm_count();
+  return cap > 0 && cap < sms ? cap : sms;
+}
+template <int BN, int MODE, int BKS = BK>
 static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
-  using Cfg = TcCfg<BN, MODE>;
-  PHT_SMEM_ATTR_ONCE((conv_gemm_tc_kernel<BN, MODE, 1>), Cfg::SMEM_BYTES);
-  const int sms = sm_count();
+  using Cfg = TcCfg<BN, MODE, 1, BKS>;
+  PHT_SMEM_ATTR_ONCE((conv_gemm_tc_kernel<BN, MODE, 1, BKS>), Cfg::SMEM_BYTES);
+  const int sms = conv_sms();
   int grid = P.num_tiles < sms ? P.num_tiles : sms;
-  PHT_CUDA(launch_pdl(conv_gemm_tc_kernel<BN, MODE, 1>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1], m.A[2], m.W,
+  PHT_CUDA(launch_pdl(conv_gemm_tc_kernel<BN, MODE, 1, BKS>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1], m.A[2], m.W,
                       m.O[0], m.O[1], m.R, m.M, m.As, m.Os[0], m.Os[1], m.Rs, m.Ms, P));
   PHT_LAUNCH_CHECK();
   return PHT_OK;
@@ -602,10 +616,10 @@ static int launch_tc(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
 template <int MODE>
 static int launch_tc_pairs(const TcGemmP& P, const TcMaps& m, cudaStream_t st) {
   using Cfg = TcCfg<256, MODE, 2>;
-  PHT_SMEM_ATTR_ONCE((conv_gemm_tc_kernel<256, MODE, 2>), Cfg::SMEM_BYTES);
-  const int pairs_max = sm_count() / 2;
+  PHT_SMEM_ATTR_ONCE((conv_gemm_tc_kernel<256, MODE, 2, BK>), Cfg::SMEM_BYTES);
+  const int pairs_max = conv_sms() / 2;
   const int grid = 2 * (P.num_pairs < pairs_max ? P.num_pairs : pairs_max);
-  PHT_CUDA(launch_pdl_pairs(conv_gemm_tc_kernel<256, MODE, 2>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1],
+  PHT_CUDA(launch_pdl_pairs(conv_gemm_tc_kernel<256, MODE, 2, BK>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, m.A[0], m.A[1],
                             m.A[2], m.W, m.O[0], m.O[1], m.R, m.M, m.As, m.Os[0], m.Os[1], m.Rs, m.Ms, P));
   PHT_LAUNCH_CHECK();
   return PHT_OK;
@@ -627,6 +641,8 @@ void walk_dir_set(const void* p, int dir) {
 }
 static std::atomic<int> g_strips{1};
 static std::atomic<int> g_cta_pairs{0};   // BN = 256 GEMMs as CTA pairs (tcgen05 cta_group::2)
+static std::atomic<int> g_half_ring{0};   // deep configs (3x3 convolutions) on the 8 x 24 KB half-stage operand ring
+void set_half_ring(int v) { g_half_ring.store(v, std::memory_order_relaxed); }
 void set_cta_pairs(int v) { g_cta_pairs.store(v, std::memory_order_relaxed); }
 void set_strips(int v) { g_strips.store(v, std::memory_order_relaxed); }
 void set_serpentine(int v) { g_serpentine.store(v, std::memory_order_relaxed); }
@@ -661,6 +677,21 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   if (((uintptr_t)a->w & 15) != 0) return PHT_OK;
   if (!get_encode_fn()) return PHT_OK;
 
+  // 1x1 GEMMs are HBM-bound: wide epilogue.  3x3: deep ring; with a fused epilogue (inputs, second output, fold) the
+  // deep+aux variant.
+  const int force = g_tc_cfg.load(std::memory_order_relaxed);
+  const bool fused = has_resid || has_mask || (a->out1.ptr && a->out2.ptr) || padfold;
+  int mode = a->ksize == 1 ? 1 : (fused ? 2 : 0);
+  if (mode == 2 && a->N > TcCfg<256, 2>::VEC_N) mode = 1;   // (the slope vectors do not fit beside the deep ring)
+  if (force == 2 && !padfold) mode = 1;
+  if (force == 4 && a->ksize == 3 && fused) mode = 1;   // A/B: fused 3x3 (pad-fold included) on the two-group "wide" config
+  if (force == 1 && !fused) mode = 0;
+  if (force == 3 && a->ksize == 1 && a->N <= TcCfg<256, 2>::VEC_N) mode = fused ? 2 : 0;
+  const bool pairs = BN == 256 && g_cta_pairs.load(std::memory_order_relaxed) != 0;
+  // latency-bound K loops (the deep configs) on the half-stage ring
+  const bool half = BN == 256 && !pairs && mode != 1 && g_half_ring.load(std::memory_order_relaxed) != 0;
+  const int bk = half ? 32 : BK;
+
   TcGemmP P;
   P.B = a->B; P.Ho = a->Ho; P.Wo = a->Wo; P.N = a->N; P.ks = a->ksize; P.n_src = a->n_src; P.flags = flags;
   TcMaps m;
@@ -669,7 +700,7 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
     if (s < a->n_src) {
       P.srcC[s] = a->src[s].C; P.srcOy[s] = a->src[s].oy; P.srcOx[s] = a->src[s].ox; P.koff[s] = k;
       k += a->src[s].C;
-      int rc = make_src_tmap(&m.A[s], a->src[s], a->B);
+      int rc = make_src_tmap(&m.A[s], a->src[s], a->B, false, bk);
       if (rc) return rc;
     } else {
       P.srcC[s] = 0; P.srcOy[s] = P.srcOx[s] = 0; P.koff[s] = 0;
@@ -677,13 +708,11 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
     }
   }
   const int T = a->ksize * a->ksize;
-  const int force = g_tc_cfg.load(std::memory_order_relaxed);
-  const bool pairs = BN == 256 && g_cta_pairs.load(std::memory_order_relaxed) != 0;
   {
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)a->N, (uint64_t)T};
     uint64_t strides[2] = {(uint64_t)ktot * 2, (uint64_t)ktot * a->N * 2};
-    uint32_t box[3] = {BK, (uint32_t)(pairs ? BN / 2 : BN), 1};
-    int rc = make_tmap_bf16(&m.W, const_cast<void*>(a->w), 3, dims, strides, box);
+    uint32_t box[3] = {(uint32_t)bk, (uint32_t)(pairs ? BN / 2 : BN), 1};
+    int rc = make_tmap_bf16(&m.W, const_cast<void*>(a->w), 3, dims, strides, box, bk * 2);
     if (rc) return rc;
   }
   // Serpentine tile order: consecutive launches walk their tiles in opposite directions, so a kernel starts on the
@@ -721,23 +750,15 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   if (!rc && has_mask) rc = make_src_tmap(&m.M, a->mask, a->B);
   m.As = m.Os[0] = m.Os[1] = m.Rs = m.Ms = m.W;
   if (!rc && strips) {
-    rc = make_src_tmap(&m.As, a->src[0], a->B, true);
+    rc = make_src_tmap(&m.As, a->src[0], a->B, true, bk);
     if (!rc && a->out1.ptr && !out1_f32) rc = make_src_tmap(&m.Os[0], a->out1, a->B, true);
     if (!rc && a->out2.ptr) rc = make_src_tmap(&m.Os[1], a->out2, a->B, true);
     if (!rc && has_resid) rc = make_src_tmap(&m.Rs, a->resid, a->B, true);
     if (!rc && has_mask) rc = make_src_tmap(&m.Ms, a->mask, a->B, true);
   }
   if (rc) return rc;
-  // 1x1 GEMMs are HBM-bound: wide epilogue.  3x3: deep ring; with a fused epilogue (inputs, second output, fold) the
-  // deep+aux variant.
-  const bool fused = has_resid || has_mask || (a->out1.ptr && a->out2.ptr) || padfold;
-  int mode = a->ksize == 1 ? 1 : (fused ? 2 : 0);
-  if (mode == 2 && a->N > TcCfg<256, 2>::VEC_N) mode = 1;   // (the slope vectors do not fit beside the deep ring)
-  if (force == 2 && !padfold) mode = 1;
-  if (force == 4 && a->ksize == 3 && fused) mode = 1;   // A/B: fused 3x3 (pad-fold included) on the two-group "wide" config
-  if (force == 1 && !fused) mode = 0;
-  if (force == 3 && a->ksize == 1 && a->N <= TcCfg<256, 2>::VEC_N) mode = fused ? 2 : 0;
-  if (pairs) rc = mode == 0 ? launch_tc_pairs<0>(P, m, st) : (mode == 1 ? launch_tc_pairs<1>(P, m, st) : launch_tc_pairs<2>(P, m, st));
+  if (half) rc = mode == 0 ? launch_tc<256, 0, 32>(P, m, st) : launch_tc<256, 2, 32>(P, m, st);
+  else if (pairs) rc = mode == 0 ? launch_tc_pairs<0>(P, m, st) : (mode == 1 ? launch_tc_pairs<1>(P, m, st) : launch_tc_pairs<2>(P, m, st));
   else if (BN == 256) rc = mode == 0 ? launch_tc<256, 0>(P, m, st) : (mode == 1 ? launch_tc<256, 1>(P, m, st) : launch_tc<256, 2>(P, m, st));
   else if (BN == 128) rc = mode == 0 ? launch_tc<128, 0>(P, m, st) : (mode == 1 ? launch_tc<128, 1>(P, m, st) : launch_tc<128, 2>(P, m, st));
   else rc = mode == 0 ? launch_tc<64, 0>(P, m, st) : (mode == 1 ? launch_tc<64, 1>(P, m, st) : launch_tc<64, 2>(P, m, st));

@@ -28,6 +28,8 @@ void set_wgrad_split_div(int v);  // wgrad_tc.cu
 void set_serpentine(int v);  // igemm_tc.cu
 void set_strips(int v);  // igemm_tc.cu
 void set_cta_pairs(int v);  // igemm_tc.cu
+void set_conv_grid_cap(int v);  // igemm_tc.cu
+void set_half_ring(int v);  // igemm_tc.cu
 void set_conv_trace(int v);  // igemm_tc.cu
 int read_conv_trace(long long* host, int n);  // igemm_tc.cu
 void set_attn_trace(int v);  // attention_tc.cu
@@ -93,6 +95,8 @@ int pht_set_option(const char* name, int value) {
   if (name && !strcmp(name, "conv_trace")) { pht::set_conv_trace(value); return PHT_OK; }
   if (name && !strcmp(name, "strips")) { pht::set_strips(value); return PHT_OK; }
   if (name && !strcmp(name, "cta_pairs")) { pht::set_cta_pairs(value); return PHT_OK; }
+  if (name && !strcmp(name, "conv_grid_cap")) { pht::set_conv_grid_cap(value); return PHT_OK; }
+  if (name && !strcmp(name, "half_ring")) { pht::set_half_ring(value); return PHT_OK; }
   if (name && !strcmp(name, "serpentine")) { pht::set_serpentine(value); return PHT_OK; }
   if (name && !strcmp(name, "pdl")) { pht::g_pdl.store(value ? 1 : 0, std::memory_order_relaxed); return PHT_OK; }
   if (name && !strcmp(name, "attn_trace")) { pht::set_attn_trace(value); return PHT_OK; }

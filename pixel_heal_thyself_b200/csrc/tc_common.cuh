@@ -81,6 +81,10 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major SW64: rows of 64 B (32 bf16), 8-row swizzle atoms 512 B apart (SBO); layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
 // MN-major SW128: 64 MN-elements (128 B) contiguous, K rows 128 B apart in 8-row atoms; SBO = distance
 // between 8-row K groups, LBO = distance between 64-element MN groups.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

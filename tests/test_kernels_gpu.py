@@ -84,12 +84,15 @@ def test_conv_gemm_zero_pad_matches_conv2d(dtype, ks, cin, cout, B, H, W):
     assert rel_err(nchw(out), ref) < tol(dtype)
 
 
+@pytest.mark.parametrize("option", [b"cta_pairs", b"half_ring"])
 @pytest.mark.parametrize("ks,cin,cout,B,H,W,fused", [(3, 256, 256, 2, 32, 32, False), (1, 512, 256, 3, 24, 16, True),
-                                                      (3, 256, 512, 1, 24, 16, True), (1, 256, 256, 2, 128, 128, False)])
-def test_conv_gemm_cta_pairs_bit_identical(ks, cin, cout, B, H, W, fused):
-    """Option "cta_pairs" = 1 runs the 256-wide GEMMs as CTA pairs (tcgen05 cta_group::2, M = 256).  Same K order, same
-    epilogue: the outputs must be bit-identical to the single-CTA kernel, an odd number of pixel tiles (one CTA of the
-    last pair has no tile) and two output tiles (N = 512) included."""
+                                                      (3, 256, 512, 1, 24, 16, True), (1, 256, 256, 2, 128, 128, False),
+                                                      (3, 256, 256, 1, 40, 48, True)])
+def test_conv_gemm_pipeline_variants_bit_identical(ks, cin, cout, B, H, W, fused, option):
+    """Option "cta_pairs" = 1 runs the 256-wide GEMMs as CTA pairs (tcgen05 cta_group::2, M = 256); "half_ring" = 1 runs
+    the 3x3 ones on the 8 x 24 KB half-stage operand ring (64-byte swizzle rows).  Same K order, same epilogue: the
+    outputs must be bit-identical to the default kernel, an odd number of pixel tiles (one CTA of the last pair has no
+    tile) and two output tiles (N = 512) included."""
     ops = _ops()
     from pixel_heal_thyself_b200 import _lib
     torch.manual_seed(5)
@@ -111,11 +114,11 @@ def test_conv_gemm_cta_pairs_bit_identical(ks, cin, cout, B, H, W, fused):
         return o1, o2
 
     a = run()
-    _lib.lib.pht_set_option(b"cta_pairs", 1)
+    _lib.lib.pht_set_option(option, 1)
     try:
         b = run()
     finally:
-        _lib.lib.pht_set_option(b"cta_pairs", 0)
+        _lib.lib.pht_set_option(option, 0)
     assert torch.equal(a[0], b[0])
     if fused:
         assert torch.equal(a[1], b[1])

@@ -255,6 +255,8 @@ def test_launch_options_are_bitwise_neutral(reproducible_attention_backward):
         for on in (1, 0, 1):
             for name in (b"pdl", b"serpentine", b"strips"):
                 assert _lib.lib.pht_set_option(name, on) == 0
+            # (the CTA-pair GEMMs -- tcgen05 cta_group::2, default off -- ride along with the "off" pass: same arithmetic)
+            assert _lib.lib.pht_set_option(b"cta_pairs", 1 - on) == 0
             net = make_net("replicate", "bf16", num_sa=2)
             out = net(x, aux)
             loss = L1ReconstructionLoss()(out, gt)
@@ -264,6 +266,7 @@ def test_launch_options_are_bitwise_neutral(reproducible_attention_backward):
     finally:
         for name in (b"pdl", b"serpentine", b"strips"):
             _lib.lib.pht_set_option(name, 1)
+        _lib.lib.pht_set_option(b"cta_pairs", 0)
     for other in results[1:]:
         assert torch.equal(results[0][0], other[0])
         assert results[0][1] == other[1]
