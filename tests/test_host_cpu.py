@@ -55,6 +55,21 @@ def test_invalid_arguments_return_error_not_crash():
         _lib.check(rc, "pht_conv_gemm")
 
 
+def test_every_documented_option_is_accepted_and_unknown_ones_are_refused():
+    """pht_set_option: every option name the header documents is accepted (host-side state only, no GPU needed), an
+    unknown name returns PHT_ERR_INVALID with a message."""
+    from pixel_heal_thyself_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pht_b200.h")).read()
+    doc = hdr[hdr.index("Runtime options"):hdr.index("int pht_set_option")] if "Runtime options" in hdr else hdr
+    names = set(re.findall(r'\* "([a-z0-9_]+)" =', doc))
+    assert {"pdl", "serpentine", "strips", "cta_pairs", "half_ring", "attn_bwd_direct", "bf16_fallback"} <= names, names
+    defaults = {"pdl": 1, "serpentine": 1, "strips": 1, "attn_bwd_direct": 1, "wgrad_split_div": 2}   # (leave the defaults set)
+    for n in sorted(names):
+        assert _lib.lib.pht_set_option(n.encode(), defaults.get(n, 0)) == 0, n
+    assert _lib.lib.pht_set_option(b"no_such_option", 1) == -1
+    assert b"unknown option" in _lib.lib.pht_last_error()
+
+
 def test_view_memo_follows_the_tensor_not_its_id():
     """pht_view structs are memoised per tensor object; a new tensor (even at a recycled id), a different slice or a
     different origin must get its own struct."""
