@@ -246,7 +246,9 @@ int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, flo
  * model.py:264-344; norm :52-61, act :64-83), with the first- and the second-order backward that the gradient penalty
  * (losses.py:12-57) needs.  All tensors fp32, channels-last: x / z / gz / gx / h [m = B*H*W][C]; gamma / beta /
  * run_mean / run_var [C]; stat [2][C] = batch mean and 1/sqrt(var + eps), written by the forward and read by both backward
- * passes.  C = 4 x a power of two, <= 1024.  workspace >= pht_bn_act_ws_bytes(C), 16-byte aligned.
+ * passes.  C = 4 x a power of two, <= 1024.  workspace >= pht_bn_act_ws_bytes(C), 16-byte aligned, ZEROED by the
+ * caller before its first use (it holds the "last block done" ticket of the deterministic reduction, which every call leaves
+ * at zero again; calls sharing a workspace must be stream-ordered).
  *   fwd      z = leaky(gamma (x - mean) rstd + beta); run_mean / run_var (may be NULL) updated like nn.BatchNorm2d
  *   bwd      gx, g_gamma, g_beta (the latter two may be NULL) from gz
  *   bwd_bwd  cotangent h of gx -> h_gz (w.r.t. gz), h_x (w.r.t. x, the dependence of mean / rstd on x included),

@@ -44,6 +44,8 @@ struct BnP {
   float* run_mean;     // mode 0 (may be null)
   float* run_var;
   float* sums;         // modes 1, 2: [NS][C] finished sums (fp32)
+  float* g_beta;       // mode 1 (may be null): copies of sums[0] / sums[1] = d beta / d gamma
+  float* g_gamma;
   double* partials;    // [blocks][NS][C]
   unsigned* ticket;
 };
@@ -169,6 +171,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_colsum_kernel(BnP P) {
     } else {
 #pragma unroll
       for (int s = 0; s < NS; ++s) P.sums[s * P.C + c] = (float)t[s];
+      if (MODE == 1) {
+        if (P.g_beta) P.g_beta[c] = (float)t[0];
+        if (P.g_gamma) P.g_gamma[c] = (float)t[1];
+      }
     }
   }
   if (threadIdx.x == 0) *P.ticket = 0u;
@@ -298,7 +304,6 @@ int pht_bn_act_fwd(const float* x, const float* gamma, const float* beta, float*
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   BN_WS(workspace, C);
-  PHT_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   BnP P = {};
   P.x = x; P.gamma = gamma; P.beta = beta; P.m = m; P.C = C; P.slope = slope; P.eps = eps; P.momentum = momentum;
   P.out_stat = stat; P.run_mean = run_mean; P.run_var = run_var; P.sums = sums; P.partials = partials; P.ticket = ticket;
@@ -318,7 +323,6 @@ int pht_colsum_f32(const float* x, float* out, int64_t m, int32_t C, void* works
   cudaStream_t st = (cudaStream_t)stream;
   BN_WS(workspace, C);
   (void)sums;
-  PHT_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   BnP P = {};
   P.x = x; P.m = m; P.C = C; P.out_stat = out; P.partials = partials; P.ticket = ticket;
   bn_colsum_kernel<3><<<bn_blocks(m, C), BN_THREADS, 0, st>>>(P);
@@ -335,15 +339,13 @@ int pht_bn_act_bwd(const float* x, const float* gz, const float* gamma, const fl
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   BN_WS(workspace, C);
-  PHT_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   BnP P = {};
   P.x = x; P.g = gz; P.gamma = gamma; P.beta = beta; P.stat = stat; P.m = m; P.C = C; P.slope = slope;
   P.sums = sums; P.partials = partials; P.ticket = ticket;
+  P.g_beta = g_beta; P.g_gamma = g_gamma;
   bn_colsum_kernel<1><<<bn_blocks(m, C), BN_THREADS, 0, st>>>(P);
   const long long n4 = m * C / 4;
   bn_act_bwd_kernel<<<ew_blocks(n4), 256, 0, st>>>(x, gz, stat, gamma, beta, sums, gx, n4, C, slope, 1.0f / (float)m);
-  if (g_beta) PHT_CUDA(cudaMemcpyAsync(g_beta, sums, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (g_gamma) PHT_CUDA(cudaMemcpyAsync(g_gamma, sums + C, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
   count_launch(CNT_OTHER, 2);
   PHT_LAUNCH_CHECK();
   return PHT_OK;
@@ -357,7 +359,6 @@ int pht_bn_act_bwd_bwd(const float* x, const float* gz, const float* h, const fl
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   BN_WS(workspace, C);
-  PHT_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
   BnP P = {};
   P.x = x; P.g = gz; P.h = h; P.gamma = gamma; P.beta = beta; P.stat = stat; P.m = m; P.C = C; P.slope = slope;
   P.sums = sums; P.partials = partials; P.ticket = ticket;

@@ -305,7 +305,9 @@ def _nhwc_rows(t):
 
 
 def bn_act_ws(C, device):
-    return torch.empty((int(lib.pht_bn_act_ws_bytes(C)) + 3) // 4, dtype=torch.float32, device=device)
+    """workspace of the pht_bn_act_* / pht_colsum_f32 calls; must be ZERO on first use (its last word is the
+    "last block done" ticket, which every call leaves at zero again)"""
+    return torch.zeros((int(lib.pht_bn_act_ws_bytes(C)) + 3) // 4, dtype=torch.float32, device=device)
 
 
 def colsum_nhwc(x, out, ws):
