@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PHT_ABI_VERSION 2
+#define PHT_ABI_VERSION 3
 
 enum pht_status {
   PHT_OK = 0,
@@ -249,16 +249,19 @@ int pht_l1_loss(const float* a, const float* b, int64_t n, float grad_scale, flo
  * passes.  C = 4 x a power of two, <= 1024.  workspace >= pht_bn_act_ws_bytes(C), 16-byte aligned, ZEROED by the
  * caller before its first use (it holds the "last block done" ticket of the deterministic reduction, which every call leaves
  * at zero again; calls sharing a workspace must be stream-ordered).
- *   fwd      z = leaky(gamma (x - mean) rstd + beta); run_mean / run_var (may be NULL) updated like nn.BatchNorm2d
+ *   fwd      z = leaky(gamma (x - mean) rstd + beta); run_mean / run_var (may be NULL) updated like nn.BatchNorm2d.
+ *            pre_bias (may be NULL): the bias [C] of the convolution in front, NOT added to x by the caller -- batch
+ *            normalisation cancels a per-channel constant exactly (z, stat and every gradient are those of x), only the
+ *            running mean sees it: run_mean tracks mean(x) + pre_bias, as nn.Conv2d(bias=True) + nn.BatchNorm2d would
  *   bwd      gx, g_gamma, g_beta (the latter two may be NULL) from gz
  *   bwd_bwd  cotangent h of gx -> h_gz (w.r.t. gz), h_x (w.r.t. x, the dependence of mean / rstd on x included),
  *            h_gamma (may be NULL).  Per-channel sums accumulate in fp64 in a fixed order (deterministic). */
 size_t pht_bn_act_ws_bytes(int32_t C);
 /* out[c] = sum over m rows of x[m][C] (fp32): the conv bias gradients of the critic; same workspace / channel rules */
 int pht_colsum_f32(const float* x, float* out, int64_t m, int32_t C, void* workspace, size_t workspace_bytes, void* stream);
-int pht_bn_act_fwd(const float* x, const float* gamma, const float* beta, float* run_mean, float* run_var, float* stat, float* z,
-                   int64_t m, int32_t C, float eps, float momentum, float slope, void* workspace, size_t workspace_bytes,
-                   void* stream);
+int pht_bn_act_fwd(const float* x, const float* gamma, const float* beta, const float* pre_bias, float* run_mean, float* run_var,
+                   float* stat, float* z, int64_t m, int32_t C, float eps, float momentum, float slope, void* workspace,
+                   size_t workspace_bytes, void* stream);
 int pht_bn_act_bwd(const float* x, const float* gz, const float* gamma, const float* beta, const float* stat, float* gx,
                    float* g_gamma, float* g_beta, int64_t m, int32_t C, float slope, void* workspace, size_t workspace_bytes,
                    void* stream);

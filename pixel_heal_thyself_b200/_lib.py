@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("PHT_LIB_PATH") or os.path.join(_PKG, "libpht_b200.so"
 PHT_F32, PHT_BF16 = 0, 1
 PAD_REPLICATE, PAD_REFLECT = 0, 1
 EPI_RESID_PRE, EPI_RESID_POST, EPI_MASK, EPI_PADFOLD = 1, 2, 4, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 PAD_MODES = {"replicate": PAD_REPLICATE, "reflect": PAD_REFLECT}
 DTYPES = {torch.float32: PHT_F32, torch.bfloat16: PHT_BF16}
@@ -96,7 +96,7 @@ SYMBOLS = {
     "pht_l1_loss": (C.c_int, [_vp, _vp, _i64, _f32, _vp, _vp, _vp]),
     "pht_bn_act_ws_bytes": (_sz, [_i32]),
     "pht_colsum_f32": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _sz, _vp]),
-    "pht_bn_act_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _sz, _vp]),
+    "pht_bn_act_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _vp, _sz, _vp]),
     "pht_bn_act_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _sz, _vp]),
     "pht_bn_act_bwd_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _sz, _vp]),
     "pht_msssim_ws_bytes": (_sz, [_i32, _i32, _i32]),

@@ -44,6 +44,7 @@ struct BnP {
   float* run_mean;     // mode 0 (may be null)
   float* run_var;
   float* sums;         // modes 1, 2: [NS][C] finished sums (fp32)
+  const float* pre_bias;  // mode 0 (may be null): per-channel constant the producer did NOT add to x (see pht_bn_act_fwd)
   float* g_beta;       // mode 1 (may be null): copies of sums[0] / sums[1] = d beta / d gamma
   float* g_gamma;
   double* partials;    // [blocks][NS][C]
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_colsum_kernel(BnP P) {
       P.out_stat[P.C + c] = (float)(1.0 / sqrt(var + (double)P.eps));
       if (P.run_mean) {   // nn.BatchNorm2d: running = (1 - momentum) running + momentum batch (unbiased variance)
         const double unb = P.m > 1 ? var * (double)P.m / (double)(P.m - 1) : var;
-        P.run_mean[c] = (float)((1.0 - P.momentum) * (double)P.run_mean[c] + P.momentum * mean);
+        const double shift = P.pre_bias ? (double)P.pre_bias[c] : 0.0;
+        P.run_mean[c] = (float)((1.0 - P.momentum) * (double)P.run_mean[c] + P.momentum * (mean + shift));
         P.run_var[c] = (float)((1.0 - P.momentum) * (double)P.run_var[c] + P.momentum * unb);
       }
     } else if (MODE == 3) {
@@ -296,9 +298,9 @@ size_t pht_bn_act_ws_bytes(int32_t C) { return (size_t)BN_MAX_BLOCKS * 5 * C * s
   float* sums = (float*)(partials + (size_t)BN_MAX_BLOCKS * 5 * (C));                 \
   unsigned* ticket = (unsigned*)(sums + 5 * (C))
 
-int pht_bn_act_fwd(const float* x, const float* gamma, const float* beta, float* run_mean, float* run_var, float* stat, float* z,
-                   int64_t m, int32_t C, float eps, float momentum, float slope, void* workspace, size_t workspace_bytes,
-                   void* stream) {
+int pht_bn_act_fwd(const float* x, const float* gamma, const float* beta, const float* pre_bias, float* run_mean, float* run_var,
+                   float* stat, float* z, int64_t m, int32_t C, float eps, float momentum, float slope, void* workspace,
+                   size_t workspace_bytes, void* stream) {
   PHT_CHECK_ARG(x && gamma && beta && stat && z, "bn_act_fwd: null arg");
   int rc = bn_check(m, C, workspace, workspace_bytes);
   if (rc) return rc;
@@ -307,6 +309,7 @@ int pht_bn_act_fwd(const float* x, const float* gamma, const float* beta, float*
   BnP P = {};
   P.x = x; P.gamma = gamma; P.beta = beta; P.m = m; P.C = C; P.slope = slope; P.eps = eps; P.momentum = momentum;
   P.out_stat = stat; P.run_mean = run_mean; P.run_var = run_var; P.sums = sums; P.partials = partials; P.ticket = ticket;
+  P.pre_bias = pre_bias;
   bn_colsum_kernel<0><<<bn_blocks(m, C), BN_THREADS, 0, st>>>(P);
   const long long n4 = m * C / 4;
   bn_act_fwd_kernel<<<ew_blocks(n4), 256, 0, st>>>(x, stat, gamma, beta, z, n4, C, slope);

@@ -115,16 +115,21 @@ class _BNActBwdFn(torch.autograd.Function):
 
 
 class _BNActFn(torch.autograd.Function):
-    """z = LeakyReLU(BatchNorm2d_train(x)) on channels-last fp32 CUDA tensors; running statistics updated in place."""
+    """z = LeakyReLU(BatchNorm2d_train(x + conv_bias)) on channels-last fp32 CUDA tensors; running statistics updated in
+    place.  ``conv_bias`` (may be None) is the bias of the convolution in front, which the caller did NOT add: batch
+    normalisation cancels a per-channel constant exactly, so z and every gradient are those of x alone; only the running
+    mean sees the bias (``pht_bn_act_fwd``'s ``pre_bias``).  Its gradient -- analytically zero, rounding noise in the
+    reference -- is the column sum of the input gradient, as autograd would compute it."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, run_mean, run_var, eps, momentum, slope, ws):
+    def forward(ctx, x, gamma, beta, conv_bias, run_mean, run_var, eps, momentum, slope, ws):
         from ... import ops
         # (the caller passes a channels-last tensor: a copy made here would cut x out of the double-backward graph)
         assert x.is_contiguous(memory_format=torch.channels_last)
         z = torch.empty_like(x, memory_format=torch.channels_last)
         stat = torch.empty(2, x.shape[1], dtype=torch.float32, device=x.device)
-        ops.bn_act_fwd(x, gamma, beta, run_mean, run_var, stat, z, ws, eps=eps, momentum=momentum, slope=slope)
+        ops.bn_act_fwd(x, gamma, beta, run_mean, run_var, stat, z, ws, eps=eps, momentum=momentum, slope=slope,
+                       pre_bias=None if conv_bias is None else conv_bias.detach())
         ctx.save_for_backward(x, gamma, beta, stat)
         ctx.slope, ctx.ws = slope, ws
         return z
@@ -133,7 +138,8 @@ class _BNActFn(torch.autograd.Function):
     def backward(ctx, gz):
         x, gamma, beta, stat = ctx.saved_tensors
         gx, gg, gb = _BNActBwdFn.apply(gz, x, gamma, beta, stat, ctx.slope, ctx.ws)
-        return gx, gg, gb, None, None, None, None, None, None
+        g_cb = _bias_grad(gx) if ctx.needs_input_grad[3] and not _input_grad_only else None
+        return gx, gg, gb, g_cb, None, None, None, None, None, None
 
 
 def _block(cin, cout, k, stride, bn):
@@ -160,7 +166,13 @@ class DiscriminatorVGG(nn.Module):
         self.classifier = nn.Sequential(nn.Linear(nc * side * side, 100), nn.LeakyReLU(0.2, True), nn.Linear(100, 1))
         import os
         self.fused_bn_act = os.environ.get("PHT_CRITIC_FUSED_BN", "1") != "0"
+        self.fold_conv_bias = os.environ.get("PHT_CRITIC_FOLD_BIAS", "1") != "0"
         self._bn_workspaces: dict = {}
+        # The convolution weights LIVE in channels-last memory (same shapes, names and values: a stride property only):
+        # cuDNN's NHWC kernels take them as they are, instead of one layout-conversion kernel per weight per forward and
+        # another per weight gradient (~100 small launches per critic step).
+        for block in self.features:
+            block[0].weight.data = block[0].weight.data.contiguous(memory_format=torch.channels_last)
 
     def _bn_ws(self, C, device):
         """one reduction workspace per channel count (launches of a step are stream-ordered)"""
@@ -177,6 +189,7 @@ class DiscriminatorVGG(nn.Module):
             # (no NCHW<->NHWC conversion kernels around every conv), the 3-channel input of the first conv zero-padded to
             # 8 channels (the padded channels multiply zero weights), and convolutions whose second-order backward (the
             # gradient penalty) stays on cuDNN's regular kernels (_Conv2dForGP).  Parameters, names, state dict: untouched.
+            nbt = []
             for bi, block in enumerate(self.features):
                 conv = block[0]
                 w = conv.weight
@@ -185,15 +198,23 @@ class DiscriminatorVGG(nn.Module):
                     x = F.pad(x, (0, 0, 0, 0, 0, pad_c))
                     w = F.pad(w, (0, 0, 0, 0, 0, pad_c))
                 x = x.contiguous(memory_format=torch.channels_last)
-                x = _Conv2dForGP.apply(x, w.contiguous(memory_format=torch.channels_last), conv.bias, conv.stride, conv.padding)
                 bn = block[1] if isinstance(block[1], nn.BatchNorm2d) else None
-                if bn is not None and self.training and x.dtype == torch.float32 and self.fused_bn_act:
+                fused = bn is not None and self.training and x.dtype == torch.float32 and self.fused_bn_act
+                fold = fused and self.fold_conv_bias
+                # (in front of the fused BatchNorm the convolution's bias is not added: see _BNActFn)
+                x = _Conv2dForGP.apply(x, w.contiguous(memory_format=torch.channels_last), None if fold else conv.bias,
+                                       conv.stride, conv.padding)
+                if fused:
                     # BatchNorm2d (batch statistics) + LeakyReLU(0.2) on the hand-written kernels, twice differentiable
-                    x = _BNActFn.apply(x.contiguous(memory_format=torch.channels_last), bn.weight, bn.bias, bn.running_mean,
-                                       bn.running_var, bn.eps, bn.momentum, 0.2, self._bn_ws(bn.num_features, x.device))
-                    bn.num_batches_tracked.add_(1)
+                    x = _BNActFn.apply(x.contiguous(memory_format=torch.channels_last), bn.weight, bn.bias,
+                                       conv.bias if fold else None,
+                                       bn.running_mean, bn.running_var, bn.eps, bn.momentum, 0.2,
+                                       self._bn_ws(bn.num_features, x.device))
+                    nbt.append(bn.num_batches_tracked)
                 else:
                     x = block[1:](x)
+            if nbt:
+                torch._foreach_add_(nbt, 1)      # nn.BatchNorm2d's num_batches_tracked += 1, one launch for all layers
         else:
             x = self.features(x)
         return self.classifier(x.reshape(x.size(0), -1))

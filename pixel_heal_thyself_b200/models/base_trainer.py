@@ -381,7 +381,11 @@ class BaseTrainer(ABC):
         flat = torch.zeros(sum(p.numel() for p in params), device=fake.device)
         off = 0
         for p in params:                    # every gradient is a view of ONE flat buffer: one all-reduce, no copies
-            p.grad = flat[off:off + p.numel()].view_as(p)
+            g = flat[off:off + p.numel()]
+            if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+                p.grad = g.view(p.shape[0], p.shape[2], p.shape[3], p.shape[1]).permute(0, 3, 1, 2)   # the parameter's strides
+            else:
+                p.grad = g.view_as(p)
             off += p.numel()
 
         def fwd_bwd():

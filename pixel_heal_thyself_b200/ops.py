@@ -317,12 +317,13 @@ def colsum_nhwc(x, out, ws):
     L.check(lib.pht_colsum_f32(xp, out.data_ptr(), m, Cc, ws.data_ptr(), ws.numel() * 4, L.stream_ptr()), "pht_colsum_f32")
 
 
-def bn_act_fwd(x, gamma, beta, run_mean, run_var, stat, z, ws, *, eps=1e-5, momentum=0.1, slope=0.2):
+def bn_act_fwd(x, gamma, beta, run_mean, run_var, stat, z, ws, *, eps=1e-5, momentum=0.1, slope=0.2, pre_bias=None):
     L.require_cuda(x, gamma, beta, stat, z, ws)
     xp, m, Cc = _nhwc_rows(x)
     zp, _, _ = _nhwc_rows(z)
-    L.check(lib.pht_bn_act_fwd(xp, gamma.data_ptr(), beta.data_ptr(), L.ptr(run_mean), L.ptr(run_var), stat.data_ptr(), zp, m, Cc,
-                               eps, momentum, slope, ws.data_ptr(), ws.numel() * 4, L.stream_ptr()), "pht_bn_act_fwd")
+    L.check(lib.pht_bn_act_fwd(xp, gamma.data_ptr(), beta.data_ptr(), L.ptr(pre_bias), L.ptr(run_mean), L.ptr(run_var),
+                               stat.data_ptr(), zp, m, Cc, eps, momentum, slope, ws.data_ptr(), ws.numel() * 4, L.stream_ptr()),
+            "pht_bn_act_fwd")
 
 
 def bn_act_bwd(x, gz, gamma, beta, stat, gx, g_gamma, g_beta, ws, *, slope=0.2):

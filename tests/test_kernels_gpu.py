@@ -666,22 +666,25 @@ def test_bn_act_forward_backward_and_double_backward_match_torch(B, C, H, W):
     xr = x0.clone().requires_grad_(True)
     gr, br = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
     rm_r, rv_r = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
-    f_ref = lambda x, g, b: act(torch.nn.functional.batch_norm(x, rm_r, rv_r, g, b, True, 0.1, 1e-5))
+    cb = torch.randn(C, device=DEV) * 0.5     # bias of the convolution in front: added by the reference, folded by ours
+    f_ref = lambda x, g, b: act(torch.nn.functional.batch_norm(x + cb.view(1, C, 1, 1), rm_r, rv_r, g, b, True, 0.1, 1e-5))
     z_r, gx_r, pen_r = gp_objective(f_ref, xr, gr, br)
     d_r = torch.autograd.grad(pen_r + 0.01 * z_r.pow(2).mean(), [xr, gr, br])
     # ours
     xo = x0.clone().requires_grad_(True)
     go, bo = bn.weight.detach().clone().requires_grad_(True), bn.bias.detach().clone().requires_grad_(True)
     rm_o, rv_o = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
-    f_our = lambda x, g, b: _BNActFn.apply(x, g, b, rm_o, rv_o, 1e-5, 0.1, 0.2, ws)
+    f_our = lambda x, g, b: _BNActFn.apply(x, g, b, cb, rm_o, rv_o, 1e-5, 0.1, 0.2, ws)
     z_o, gx_o, pen_o = gp_objective(f_our, xo, go, bo)
     d_o = torch.autograd.grad(pen_o + 0.01 * z_o.pow(2).mean(), [xo, go, bo])
-    assert rel_err(z_o, z_r) < 1e-5
+    assert rel_err(z_o, z_r) < 2e-6
     assert rel_err(rm_o, rm_r) < 1e-5 and rel_err(rv_o, rv_r) < 1e-5
-    assert rel_err(gx_o, gx_r) < 1e-4
+    assert rel_err(gx_o, gx_r) < 2e-6
     assert abs(float(pen_o) - float(pen_r)) < 1e-4 * max(1.0, abs(float(pen_r)))
+    print(f"bn_act {B}x{C}x{H}x{W}: z {rel_err(z_o, z_r):.1e} gx {rel_err(gx_o, gx_r):.1e} "
+          + " ".join(f"{n} {rel_err(a, b):.1e}" for a, b, n in zip(d_o, d_r, ("d/dx", "d/dgamma", "d/dbeta"))))
     for a, b, name in zip(d_o, d_r, ("d/dx", "d/dgamma", "d/dbeta")):
-        assert rel_err(a, b) < 2e-3, (name, rel_err(a, b))
+        assert rel_err(a, b) < 1e-5, (name, rel_err(a, b))      # measured 1e-7 .. 5e-7
 
 
 def test_critic_with_fused_bn_act_matches_stock_modules():
@@ -708,9 +711,16 @@ def test_critic_with_fused_bn_act_matches_stock_modules():
     assert abs(res[True][0] - res[False][0]) < 1e-4 * max(1.0, abs(res[False][0])), (res[True][0], res[False][0])
     # (a conv bias in front of a BatchNorm has a mathematically zero gradient -- the batch mean removes it -- so both sides
     # hold only round-off there: errors are measured against the larger of the tensor's and the global gradient scale)
+    # The kernels themselves agree with torch to fp32 rounding (5e-7, test above).  At the critic level the penalty
+    # ((|grad| - 1)^2 with |grad| close to 1) cancels catastrophically: a 1e-6 relative difference of the input gradient
+    # (last-bit differences, cuDNN's choice of algorithm with / without a bias operand) becomes a UNIFORM ~5e-4 relative
+    # difference of every penalty gradient (tools/diag_critic.py: l2 5e-4 on all tensors, worst single element 5.8e-3 of
+    # its tensor's max; two stock runs differ by 1e-6 .. 2e-5).
     gmax = max(float(g.abs().max()) for g in res[False][1].values())
     for n, g in res[False][1].items():
-        err = float((res[True][1][n] - g).abs().max()) / max(float(g.abs().max()), 1e-4 * gmax)
-        assert err < 5e-3, (n, err)
+        d = res[True][1][n] - g
+        err = float(d.abs().max()) / max(float(g.abs().max()), 1e-4 * gmax)
+        l2 = float(d.norm()) / max(float(g.norm()), 1e-4 * gmax * g.numel() ** 0.5)
+        assert err < 2e-2 and l2 < 5e-3, (n, err, l2)
     for n, b in res[False][2].items():
         assert rel_err(res[True][2][n].float(), b.float()) < 1e-4, n
