@@ -331,3 +331,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "config"):
         assert key in line, key
+
+
+def test_gan_fixture_inputs_and_critic_init_reproduce_the_reference():
+    """tests/golden/gan_step.json (one full GAN iteration of the real reference): its inputs regenerate from the seed and
+    this package's DiscriminatorVGG draws the reference critic's random init (same modules in the same order) -- what the
+    GPU test of the iteration starts from."""
+    from conftest import GOLDEN, load_json
+    sys.path.insert(0, GOLDEN)
+    from make_golden_gan import P, gan_inputs, gp_alphas
+    from pixel_heal_thyself_b200.models.afgsa.discriminator import DiscriminatorVGG
+    m = load_json("gan_step.json")
+    x, gt, aux = gan_inputs()
+    assert abs(float(sum(t.double().abs().sum() for t in (x, gt, aux))) - m["inputs_checksum"]) < 1e-9 * m["inputs_checksum"]
+    torch.manual_seed(m["seed"] + 1)
+    D = DiscriminatorVGG(3, 64, P)
+    assert abs(float(sum(p.detach().double().abs().sum() for p in D.parameters())) - m["d_init_checksum"]) < 1e-9 * m["d_init_checksum"]
+    # the convolution weights live in channels-last memory: same values, names and shapes as the reference's
+    w = D.features[1][0].weight
+    assert w.shape == (128, 64, 3, 3) and w.is_contiguous(memory_format=torch.channels_last)
+    assert set(D.state_dict()) >= {"features.0.0.weight", "features.1.1.running_mean", "classifier.2.bias"}
+    a = gp_alphas()
+    assert a.shape == (m["B"], 1, 1, 1) and 0.0 <= float(a.min()) and float(a.max()) < 1.0
