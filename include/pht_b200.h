@@ -66,6 +66,13 @@ typedef struct pht_view {
  * their 1-pixel frame receives don't-care values.  bf16 tensor-core path only (ksize 3, N <= 256, H % 8 == 0,
  * W % 8 == 0); otherwise PHT_ERR_UNSUPPORTED. */
 #define PHT_EPI_PADFOLD    8u
+/* out1 (RING1) / out2 (RING2) is the INTERIOR view (H x W) of a padded buffer [B][H+2][W+2][C]: besides the interior,
+ * the kernel also writes the buffer's 1-pixel frame -- the replicate (default) or reflect (RING_REFLECT) padding that
+ * pht_border_fill would write afterwards (every frame pixel is a copy of one output pixel, stored by the thread that owns
+ * it).  bf16 tensor-core path only, H, W >= 4, not together with PHT_EPI_PADFOLD; otherwise PHT_ERR_UNSUPPORTED. */
+#define PHT_EPI_RING1        16u
+#define PHT_EPI_RING2        32u
+#define PHT_EPI_RING_REFLECT 64u
 
 /* Implicit-GEMM convolution over pixels with virtual concat:
  *   acc[p, n] = sum_t sum_s sum_k src[s](p + tap_t)[k] * w[t][n][koff_s + k]

@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("PHT_LIB_PATH") or os.path.join(_PKG, "libpht_b200.so"
 PHT_F32, PHT_BF16 = 0, 1
 PAD_REPLICATE, PAD_REFLECT = 0, 1
 EPI_RESID_PRE, EPI_RESID_POST, EPI_MASK, EPI_PADFOLD = 1, 2, 4, 8
+EPI_RING1, EPI_RING2, EPI_RING_REFLECT = 16, 32, 64
 ABI_VERSION = 3
 
 PAD_MODES = {"replicate": PAD_REPLICATE, "reflect": PAD_REFLECT}

@@ -482,6 +482,10 @@ int pht_conv_gemm(const pht_conv_gemm_args* a, void* stream) {
     set_error("conv_gemm: PHT_EPI_PADFOLD needs the bf16 tensor-core path (ksize 3, H and W multiples of 8, TMA-able views)");
     return PHT_ERR_UNSUPPORTED;
   }
+  if (a->flags & (PHT_EPI_RING1 | PHT_EPI_RING2)) {
+    set_error("conv_gemm: PHT_EPI_RING1 / RING2 need the bf16 tensor-core path (bf16 outputs, H, W >= 4, no PHT_EPI_PADFOLD)");
+    return PHT_ERR_UNSUPPORTED;
+  }
   if (a->dtype == PHT_BF16 && !force_simple() && !bf16_fallback_allowed()) {
     set_error("conv_gemm: bf16 launch (N=%d ksize=%d n_src=%d C0=%d) is not eligible for the tcgen05 kernel (channels must be "
               "multiples of 64, views 16-byte aligned) and the CUDA-core fallback is disabled (option bf16_fallback)",

@@ -37,7 +37,9 @@ struct TcGemmP {
   const float* bias;
   const float* slope;
   const float* mslope;
-  View out1;          // only used when out1_f32
+  View out1;          // used when out1_f32 and for the frame stores (ring)
+  View out2;          // frame stores (ring)
+  int ring;           // bit 0 / 1: out1 / out2 is the interior of a padded buffer whose 1-pixel frame is written too; bit 2: reflect
   int has_out1, has_out2, has_resid, has_mask;
   int out1_f32;       // out1 is fp32 (direct stores; used by the 64-wide decoder-tail GEMM only)
   int num_pairs;      // CTA-pair kernels: work units = (pair of pixel tiles, output tile)
@@ -408,6 +410,25 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       mbar_arrive(&aempty_bar[slot]);
       ++j_aux;
     };
+    // frame (padding ring) of a padded output buffer: every frame pixel is a copy of one output pixel -- the edge pixel
+    // (replicate) or the pixel next to it (reflect) -- stored straight from the registers of the thread that owns it
+    auto ring_store = [&](const float* v, const View& o, int c_abs, int b, int y, int x) {
+      const int e0 = (P.ring & 4) ? 1 : 0;
+      const int tx = x == e0 ? -1 : (x == P.Wo - 1 - e0 ? P.Wo : -2);
+      const int ty = y == e0 ? -1 : (y == P.Ho - 1 - e0 ? P.Ho : -2);
+      if (tx == -2 && ty == -2) return;
+      bf16* base = (bf16*)o.ptr + c_abs;
+      bf16* d0 = tx != -2 ? base + view_off(o, b, y + o.oy, tx + o.ox) : nullptr;
+      bf16* d1 = ty != -2 ? base + view_off(o, b, ty + o.oy, x + o.ox) : nullptr;
+      bf16* d2 = (tx != -2 && ty != -2) ? base + view_off(o, b, ty + o.oy, tx + o.ox) : nullptr;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 q = pack8(v + g * 8);
+        if (d0) *reinterpret_cast<uint4*>(d0 + g * 8) = q;
+        if (d1) *reinterpret_cast<uint4*>(d1 + g * 8) = q;
+        if (d2) *reinterpret_cast<uint4*>(d2 + g * 8) = q;
+      }
+    };
     int it = 0;
     const uint32_t tempty_leader = CG == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
     auto release_acc = [&](int acc) {
@@ -496,12 +517,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             }
           } else {
             stage_and_store(v, tmOut1, n0 + c0, x0 + P.out1Ox, y0 + P.out1Oy, b);
+            if ((P.ring & 1) && valid) ring_store(v, P.out1, n0 + c0, b, y, x);
           }
         }
         if (P.has_out2) {   // (the host clears RESID_POST / MASK when there is no out2)
           if (AUX && (P.flags & PHT_EPI_RESID_POST)) aux_apply(v, n0 + c0, false);
           if (AUX && (P.flags & PHT_EPI_MASK)) aux_apply(v, n0 + c0, true);
           stage_and_store(v, tmOut2, n0 + c0, x0 + P.out2Ox, y0 + P.out2Oy, b);
+          if ((P.ring & 2) && valid) ring_store(v, P.out2, n0 + c0, b, y, x);
         }
       }
       if (warp == 2 || warp == 7) stamp(it, warp == 2 ? 5 : 7);
@@ -667,6 +690,10 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   if (padfold && (a->ksize != 3 || (a->Ho - 2) % TILE_H || (a->Wo - 2) % 8 || a->Ho < 10 || a->Wo < 10 ||
                   (a->out1.ptr && a->out1.dtype != PHT_BF16)))
     return PHT_OK;
+  const unsigned ring_flags = flags & (PHT_EPI_RING1 | PHT_EPI_RING2);
+  if (ring_flags && (padfold || a->Ho < 4 || a->Wo < 4 || ((flags & PHT_EPI_RING1) && (!a->out1.ptr || a->out1.dtype != PHT_BF16)) ||
+                     ((flags & PHT_EPI_RING2) && !a->out2.ptr)))
+    return PHT_OK;
   const bool out1_f32 = a->out1.ptr && a->out1.dtype == PHT_F32;
   if (out1_f32) {
     if (((uintptr_t)a->out1.ptr & 15) || a->out1.sx % 4 || a->out1.sy % 4 || a->out1.sb % 4) return PHT_OK;
@@ -737,6 +764,8 @@ int conv_gemm_tc(const pht_conv_gemm_args* a, cudaStream_t st, bool* handled) {
   P.num_pairs = ceil_div(P.num_tiles / P.n_tiles, 2) * P.n_tiles;
   P.bias = a->bias; P.slope = a->slope; P.mslope = a->mslope;
   P.out1 = a->out1.ptr ? make_view(a->out1) : null_view();
+  P.out2 = a->out2.ptr ? make_view(a->out2) : null_view();
+  P.ring = ((flags & PHT_EPI_RING1) ? 1 : 0) | ((flags & PHT_EPI_RING2) ? 2 : 0) | ((flags & PHT_EPI_RING_REFLECT) ? 4 : 0);
   P.has_out1 = a->out1.ptr ? 1 : 0; P.has_out2 = a->out2.ptr ? 1 : 0;
   P.has_resid = has_resid ? 1 : 0; P.has_mask = has_mask ? 1 : 0;
   P.out1_f32 = out1_f32 ? 1 : 0;

@@ -263,6 +263,11 @@ class AfgsaEngine:
         slopeN = self._const("slopeN", [0.0] * 768)
         slopeA = self._const("slopeA", [0.0] * 256 + [LEAKY] * 512)
         mode = self.pad_mode
+        # bf16: the padding frame of a 3x3 convolution's input is written by the epilogue of the GEMM that produces it
+        # (PHT_EPI_RING*) instead of a pht_border_fill launch
+        ring = ("reflect" if net.padding_mode == "reflect" else "replicate") if (
+            T == torch.bfloat16 and H >= 4 and W >= 4 and not getattr(self, "no_fused_ring", False)
+            and os.environ.get("PHT_FUSED_RING", "1") != "0") else None
         nb = lambda i: i if save else 0          # per-block buffers only when saving for backward
         g = A.get
 
@@ -311,19 +316,23 @@ class AfgsaEngine:
                          heads=self.heads, block=self.block, halo=self.halo, resid=X, lse=lse)
             ops.border_fill(X1p, mode)
             ops.conv_gemm([X1p], pk[f"b{i}.ff0"], C, ksize=3, src_offsets=[(1, 1)],
-                          bias=P[pre + "feed_forward.0.0.bias"], slope=relu, out1=A.inner(H1p))
-            ops.border_fill(H1p, mode)
+                          bias=P[pre + "feed_forward.0.0.bias"], slope=relu, out1=A.inner(H1p), ring1=ring)
+            if ring is None:
+                ops.border_fill(H1p, mode)
+            last = i == self.num_sa - 1          # (only the decoder reads a block output through a 3x3 window)
             ops.conv_gemm([H1p], pk[f"b{i}.ff1"], C, ksize=3, src_offsets=[(1, 1)],
                           bias=P[pre + "feed_forward.1.0.bias"], slope=relu, resid=X1, resid_mode="post",
-                          out1=H2, out2=A.inner(Xn))
+                          out1=H2, out2=A.inner(Xn), ring2=ring if last else None)
             Xp, X = Xn, A.inner(Xn)
 
-        ops.border_fill(Xp, mode)
+        if ring is None or self.num_sa == 0:
+            ops.border_fill(Xp, mode)
         D1p = g("D1p", (B, H + 2, W + 2, C), T)
         D2 = g("D2", (B, H, W, C), T)
         ops.conv_gemm([Xp], pk["dec0"], C, ksize=3, src_offsets=[(1, 1)], bias=P["decoder.0.0.bias"], slope=relu,
-                      out1=A.inner(D1p))
-        ops.border_fill(D1p, mode)
+                      out1=A.inner(D1p), ring1=ring)
+        if ring is None:
+            ops.border_fill(D1p, mode)
         ops.conv_gemm([D1p], pk["dec1"], C, ksize=3, src_offsets=[(1, 1)], bias=P["decoder.1.0.bias"], slope=relu,
                       out1=D2)
         out = torch.empty_like(x)

@@ -26,12 +26,14 @@ def set_launch_profiler(sink, flt=None):
 
 
 def conv_gemm(srcs, w, N, *, ksize=1, out_domain=None, bias=None, slope=None, resid=None, resid_mode=None, mask=None,
-              mslope=None, out1=None, out2=None, src_offsets=None, padfold=False):
+              mslope=None, out1=None, out2=None, src_offsets=None, padfold=False, ring1=None, ring2=None):
     """pht_conv_gemm.  srcs: list of [B,H,W,C] tensors (virtual concat along C).
     out_domain: (B, Ho, Wo), default = shape of the first output.
     src_offsets: list of (oy, ox) per source (default 0,0).
     resid_mode: None | "pre" | "post".
-    padfold: out_domain is the padded domain, resid/mask/outputs are interior views (PHT_EPI_PADFOLD)."""
+    padfold: out_domain is the padded domain, resid/mask/outputs are interior views (PHT_EPI_PADFOLD).
+    ring1 / ring2: None | "replicate" | "reflect": out1 / out2 is the interior view of a padded buffer whose 1-pixel frame
+    is written too (PHT_EPI_RING1 / RING2; replaces a pht_border_fill launch)."""
     a = L.ConvGemmArgs()
     ref = out1 if out1 is not None else out2
     L.require_cuda(*srcs, w, ref)
@@ -54,6 +56,9 @@ def conv_gemm(srcs, w, N, *, ksize=1, out_domain=None, bias=None, slope=None, re
         flags |= L.EPI_MASK
     if padfold:
         flags |= L.EPI_PADFOLD
+    for ring, bit in ((ring1, L.EPI_RING1), (ring2, L.EPI_RING2)):
+        if ring is not None:
+            flags |= bit | (L.EPI_RING_REFLECT if ring == "reflect" else 0)
     a.flags = flags
     a.out1, a.out2 = L.view(out1), L.view(out2)
     if _profile_sink is not None:

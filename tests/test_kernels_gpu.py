@@ -125,6 +125,46 @@ def test_conv_gemm_pipeline_variants_bit_identical(ks, cin, cout, B, H, W, fused
     assert float(a[0].float().abs().max()) > 0
 
 
+@pytest.mark.parametrize("mode", ["replicate", "reflect"])
+@pytest.mark.parametrize("ks,B,H,W,two_out", [(3, 2, 32, 48, False), (3, 1, 24, 16, True), (1, 3, 8, 16, True), (3, 8, 128, 128, True)])
+def test_conv_gemm_ring_epilogue_equals_border_fill(mode, ks, B, H, W, two_out):
+    """PHT_EPI_RING1 / RING2: the GEMM's epilogue also writes the 1-pixel padding frame of a padded output buffer.  The
+    whole padded buffer must be bit-identical to (same GEMM into the interior) + pht_border_fill, for both outputs and both
+    padding modes; the flags are refused off the tensor-core path."""
+    ops = _ops()
+    torch.manual_seed(9)
+    dtype, C = torch.bfloat16, 256
+    x = torch.randn(B, H + 2, W + 2, C, device=DEV).to(dtype) if ks == 3 else torch.randn(B, H, W, C, device=DEV).to(dtype)
+    wp = pack(torch.randn(C, C, ks, ks, device=DEV) / (C * ks * ks) ** 0.5, dtype)
+    bias, slope = torch.randn(C, device=DEV), torch.zeros(C, device=DEV)
+    resid = torch.randn(B, H, W, C, device=DEV).to(dtype) if two_out else None
+    pmode = {"replicate": 0, "reflect": 1}[mode]
+
+    def run(fused):
+        p1 = torch.full((B, H + 2, W + 2, C), 7.0, dtype=dtype, device=DEV)
+        p2 = torch.full((B, H + 2, W + 2, C), 7.0, dtype=dtype, device=DEV) if two_out else None
+        kw = dict(resid=resid, resid_mode="post", out2=p2[:, 1:-1, 1:-1]) if two_out else {}
+        ops.conv_gemm([x], wp, C, ksize=ks, src_offsets=[(1, 1)] if ks == 3 else None, out_domain=(B, H, W), bias=bias,
+                      slope=slope, out1=p1[:, 1:-1, 1:-1], ring1=mode if fused else None,
+                      ring2=mode if (fused and two_out) else None, **kw)
+        if not fused:
+            ops.border_fill(p1, pmode)
+            if two_out:
+                ops.border_fill(p2, pmode)
+        torch.cuda.synchronize()
+        return p1, p2
+
+    a, b = run(False), run(True)
+    assert torch.equal(a[0], b[0])
+    if two_out:
+        assert torch.equal(a[1], b[1])
+    assert float(a[0][:, 0].float().abs().max()) > 0          # (the frame was written)
+    with pytest.raises(RuntimeError):                          # fp32 (CUDA-core path): refused, not ignored
+        xf = torch.randn(1, 8, 8, 64, device=DEV)
+        pf = torch.zeros(1, 10, 10, 64, device=DEV)
+        ops.conv_gemm([xf], pack(torch.randn(64, 64, 1, 1, device=DEV), torch.float32), 64, out1=pf[:, 1:-1, 1:-1], ring1=mode)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode", ["replicate", "reflect"])
 def test_padded_conv_forward_and_backward(dtype, mode, cuda_core_bf16_allowed):

@@ -274,6 +274,33 @@ def test_launch_options_are_bitwise_neutral(reproducible_attention_backward):
             assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("mode", ["replicate", "reflect"])
+def test_fused_padding_frames_are_bitwise_neutral(mode, reproducible_attention_backward):
+    """bf16 path: the padding frames written by the producing GEMM's epilogue (PHT_EPI_RING*) instead of pht_border_fill
+    launches -- output, loss and every gradient bit-identical with and without (2 blocks, 32 x 48, both padding modes)."""
+    from pixel_heal_thyself_b200 import _lib
+    from pixel_heal_thyself_b200.models.losses import L1ReconstructionLoss
+    torch.manual_seed(11)
+    x = (torch.randn(2, 3, 32, 48) * 0.5).to(DEV)
+    aux = torch.rand(2, 7, 32, 48).to(DEV)
+    gt = (torch.randn(2, 3, 32, 48) * 0.5).to(DEV)
+    results = []
+    for fused in (True, False):
+        net = make_net(mode, "bf16", num_sa=2)
+        net.engine.no_fused_ring = not fused
+        before = _lib.counters()["other"]
+        out = net(x, aux)
+        launches = _lib.counters()["other"] - before
+        loss = L1ReconstructionLoss()(out, gt)
+        loss.backward()
+        torch.cuda.synchronize()
+        results.append((out.detach().clone(), float(loss), [p.grad.detach().clone() for p in net.parameters()], launches))
+    assert results[0][3] == results[1][3] - 4        # 2 blocks: H1p x 2, the last block's output, D1p
+    assert torch.equal(results[0][0], results[1][0]) and results[0][1] == results[1][1]
+    for a, b in zip(results[0][2], results[1][2]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_film_variant_matches_reference_golden(dtype):
     """use_film=True: the FiLM branch of the AFGSA layer (two 1x1 GEMMs + pht_film_fwd / pht_film_bwd) against the real
