@@ -196,6 +196,10 @@ typedef struct pht_attn_args {
   pht_view resid;           /* optional (ptr may be NULL)                      */
   pht_view out;
   float* lse;
+  int32_t ring;             /* forward only: 1 (replicate) / 2 (reflect): `out` is the INTERIOR view of a padded buffer
+                             * [B][H+2][W+2][C] and the kernel also writes that buffer's 1-pixel frame (what pht_border_fill
+                             * would write afterwards); bf16 tensor-core path only, else PHT_ERR_UNSUPPORTED.  0 = no frame */
+  int32_t pad_;
 } pht_attn_args;
 
 int pht_attn_fwd(const pht_attn_args* args, void* stream);

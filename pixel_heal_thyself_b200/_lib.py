@@ -53,7 +53,7 @@ class AttnArgs(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("heads", C.c_int32),
                 ("head_dim", C.c_int32), ("block", C.c_int32), ("halo", C.c_int32), ("q", PhtView), ("k", PhtView),
                 ("v", PhtView), ("rel_h", C.c_void_p), ("rel_w", C.c_void_p), ("resid", PhtView), ("out", PhtView),
-                ("lse", C.c_void_p)]
+                ("lse", C.c_void_p), ("ring", C.c_int32), ("pad_", C.c_int32)]
 
 
 class AttnBwdArgs(C.Structure):

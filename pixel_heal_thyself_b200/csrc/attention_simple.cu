@@ -340,6 +340,10 @@ int pht_attn_fwd(const pht_attn_args* a, void* stream) {
       return PHT_ERR_UNSUPPORTED;
     }
   }
+  if (a->ring) {
+    set_error("attn_fwd: ring (frame of a padded output) needs the bf16 tensor-core path");
+    return PHT_ERR_UNSUPPORTED;
+  }
   return attn_fwd_simple(a, st);
 }
 

@@ -57,6 +57,8 @@ struct AtP {
   const float* rel_h;
   const float* rel_w;
   float* lse;
+  View out;   // frame stores (ring)
+  int ring;   // 1 / 2: `out` is the interior of a padded buffer whose replicate / reflect frame is written too
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -309,9 +311,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto epilogue = [&](int it, float m, int blk, int pair) {
       const float sum = xsum[xrow] + xsum[128 + xrow];
       const float inv = 1.f / sum;
-      if (P.lse && part == 0) {
-        const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+      const int bx = blk % P.nbx, by = (blk / P.nbx) % P.nby, b = blk / (P.nbx * P.nby);
+      if (P.lse && part == 0)
         P.lse[(((long long)b * P.H + by * 8 + qy) * P.W + bx * 8 + qx) * 4 + pair * 2 + hp] = m + logf(sum);
+      // frame of the padded output buffer: copies of the edge pixel (replicate) or of the pixel next to it (reflect),
+      // stored straight from the registers of the thread that owns it
+      bf16 *d0 = nullptr, *d1 = nullptr, *d2 = nullptr;
+      if (P.ring) {
+        const int x = bx * 8 + qx, y = by * 8 + qy, e0 = P.ring == 2 ? 1 : 0;
+        const int tx = x == e0 ? -1 : (x == P.W - 1 - e0 ? P.W : -2);
+        const int ty = y == e0 ? -1 : (y == P.H - 1 - e0 ? P.H : -2);
+        bf16* base = (bf16*)P.out.ptr + (pair * 2 + hp) * 64 + part * 32;
+        if (tx != -2) d0 = base + view_off(P.out, b, y + P.out.oy, tx + P.out.ox);
+        if (ty != -2) d1 = base + view_off(P.out, b, ty + P.out.oy, x + P.out.ox);
+        if (tx != -2 && ty != -2) d2 = base + view_off(P.out, b, ty + P.out.oy, tx + P.out.ox);
       }
       uint8_t* row = ROs + hp * AT_Q_BYTES + q * 128;
       uint4 ru[4];
@@ -335,7 +348,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int j = 0; j < 4; ++j)
           w[j] = pack_bf16x2(fmaf(__uint_as_float(o[g * 8 + 2 * j]), inv, __uint_as_float(rw[j] << 16)),
                              fmaf(__uint_as_float(o[g * 8 + 2 * j + 1]), inv, __uint_as_float(rw[j] & 0xffff0000u)));
-        *reinterpret_cast<uint4*>(row + (((part * 4 + g) ^ qsw) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+        const uint4 q4 = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(row + (((part * 4 + g) ^ qsw) * 16)) = q4;
+        if (d0) *reinterpret_cast<uint4*>(d0 + g * 8) = q4;
+        if (d1) *reinterpret_cast<uint4*>(d1 + g * 8) = q4;
+        if (d2) *reinterpret_cast<uint4*>(d2 + g * 8) = q4;
       }
       fence_proxy_async();
       mbar_arrive(ro_out);
@@ -461,6 +478,7 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   if (a->H % 8 || a->W % 8) return PHT_OK;  // the CUDA-core entry reports the reference's assertion
   if (!at_view_ok(a->q, 256) || !at_view_ok(a->k, 256) || !at_view_ok(a->v, 256) || !at_view_ok(a->out, 256)) return PHT_OK;
   if (a->resid.ptr && !at_view_ok(a->resid, 256)) return PHT_OK;
+  if (a->ring < 0 || a->ring > 2 || (a->ring && (a->H < 4 || a->W < 4))) return PHT_OK;
   if (!get_encode_fn()) return PHT_OK;
   CUtensorMap tmQ, tmK, tmV, tmR, tmO;
   int rc = at_tmap(&tmQ, a->q, a->B, 8, 8);
@@ -481,6 +499,7 @@ int attn_fwd_tc(const pht_attn_args* a, cudaStream_t st, bool* handled) {
   P.has_resid = a->resid.ptr ? 1 : 0;
   P.residOy = a->resid.oy; P.residOx = a->resid.ox; P.outOy = a->out.oy; P.outOx = a->out.ox;
   P.rel_h = a->rel_h; P.rel_w = a->rel_w; P.lse = a->lse;
+  P.out = make_view(a->out); P.ring = a->ring;
   P.trace = g_attn_trace_on == 2;
   PHT_SMEM_ATTR_ONCE(attn_fwd_tc_kernel, AT_SMEM);
   const int sms = sm_count();

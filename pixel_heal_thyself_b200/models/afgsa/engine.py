@@ -313,8 +313,9 @@ class AfgsaEngine:
             ops.conv_gemm([M], pk[f"b{i}.qk"], 2 * C, out1=QK)
             ops.conv_gemm([X], pk[f"b{i}.v"], C, out1=V)
             ops.attn_fwd(A.lo(QK, C), A.hi(QK, C), V, P[pre + "attention.rel_h"], P[pre + "attention.rel_w"], X1,
-                         heads=self.heads, block=self.block, halo=self.halo, resid=X, lse=lse)
-            ops.border_fill(X1p, mode)
+                         heads=self.heads, block=self.block, halo=self.halo, resid=X, lse=lse, ring=ring)
+            if ring is None:
+                ops.border_fill(X1p, mode)
             ops.conv_gemm([X1p], pk[f"b{i}.ff0"], C, ksize=3, src_offsets=[(1, 1)],
                           bias=P[pre + "feed_forward.0.0.bias"], slope=relu, out1=A.inner(H1p), ring1=ring)
             if ring is None:

@@ -226,9 +226,12 @@ def _attn_args(q, k, v, rel_h, rel_w, heads, block, halo, resid=None, out=None, 
     return a
 
 
-def attn_fwd(q, k, v, rel_h, rel_w, out, *, heads=4, block=8, halo=3, resid=None, lse=None):
+def attn_fwd(q, k, v, rel_h, rel_w, out, *, heads=4, block=8, halo=3, resid=None, lse=None, ring=None):
+    """ring: None | "replicate" | "reflect": ``out`` is the interior view of a padded buffer whose 1-pixel frame is written
+    too (replaces a pht_border_fill launch; tcgen05 path only)."""
     L.require_cuda(q, k, v, rel_h, rel_w, out)
     a = _attn_args(q, k, v, rel_h, rel_w, heads, block, halo, resid, out, lse)
+    a.ring = {None: 0, "replicate": 1, "reflect": 2}[ring]
     L.check(lib.pht_attn_fwd(C.byref(a), L.stream_ptr()), "pht_attn_fwd")
 
 

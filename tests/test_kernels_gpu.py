@@ -390,6 +390,34 @@ def test_attention_forward_backward_matches_oracle(dtype, B, C, H, W, cuda_core_
     assert rel_err(drw.cpu(), rw.grad) < t
 
 
+@pytest.mark.parametrize("mode", ["replicate", "reflect"])
+@pytest.mark.parametrize("B,H,W", [(2, 16, 24), (1, 8, 8), (8, 128, 128)])
+def test_attention_forward_ring_equals_border_fill(mode, B, H, W):
+    """pht_attn_fwd with ``ring``: the kernel also writes the 1-pixel frame of the padded buffer its output lives in;
+    the padded buffer must be bit-identical to (attention into the interior) + pht_border_fill.  Refused in fp32 mode."""
+    ops = _ops()
+    torch.manual_seed(12)
+    C, dt = 256, torch.bfloat16
+    q, k, v, x = (torch.randn(B, H, W, C, device=DEV).to(dt) for _ in range(4))
+    rh, rw = torch.randn(1, 14, 1, 32, device=DEV), torch.randn(1, 1, 14, 32, device=DEV)
+
+    def run(fused):
+        p = torch.full((B, H + 2, W + 2, C), 3.0, dtype=dt, device=DEV)
+        ops.attn_fwd(q, k, v, rh, rw, p[:, 1:-1, 1:-1], resid=x, ring=mode if fused else None)
+        if not fused:
+            ops.border_fill(p, {"replicate": 0, "reflect": 1}[mode])
+        torch.cuda.synchronize()
+        return p
+
+    a, b = run(False), run(True)
+    assert torch.equal(a, b)
+    assert float((a[:, 0].float() - 3.0).abs().max()) > 0
+    with pytest.raises(RuntimeError):
+        qf = torch.randn(1, 8, 8, C, device=DEV)
+        pf = torch.zeros(1, 10, 10, C, device=DEV)
+        ops.attn_fwd(qf, qf, qf, rh, rw, pf[:, 1:-1, 1:-1], ring=mode)
+
+
 def test_attention_rejects_unaligned_maps():
     ops = _ops()
     q = torch.zeros(1, 12, 16, 256, device=DEV)

@@ -295,7 +295,7 @@ def test_fused_padding_frames_are_bitwise_neutral(mode, reproducible_attention_b
         loss.backward()
         torch.cuda.synchronize()
         results.append((out.detach().clone(), float(loss), [p.grad.detach().clone() for p in net.parameters()], launches))
-    assert results[0][3] == results[1][3] - 4        # 2 blocks: H1p x 2, the last block's output, D1p
+    assert results[0][3] == results[1][3] - 6        # 2 blocks: X1p x 2, H1p x 2, the last block's output, D1p
     assert torch.equal(results[0][0], results[1][0]) and results[0][1] == results[1][1]
     for a, b in zip(results[0][2], results[1][2]):
         assert torch.equal(a, b)
