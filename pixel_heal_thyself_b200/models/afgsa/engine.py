@@ -263,11 +263,15 @@ class AfgsaEngine:
         slopeN = self._const("slopeN", [0.0] * 768)
         slopeA = self._const("slopeA", [0.0] * 256 + [LEAKY] * 512)
         mode = self.pad_mode
-        # bf16: the padding frame of a 3x3 convolution's input is written by the epilogue of the GEMM that produces it
-        # (PHT_EPI_RING*) instead of a pht_border_fill launch
+        # bf16: the padding frame of a 3x3 convolution's input is written by the epilogue of the kernel that produces it
+        # (PHT_EPI_RING* / pht_attn_args.ring) instead of a pht_border_fill launch -- for the launch-bound small batches
+        # only: measured +1.2 % at dev (8 x 32 x 32) but -0.6 % at prod (8 x 128 x 128), where a border_fill launch hides
+        # under its neighbours' tails while the extra stores of the edge threads sit on the epilogue's critical path.
+        # PHT_FUSED_RING=1 / 0 forces it on / off.
+        want = os.environ.get("PHT_FUSED_RING", "auto")
+        ring_on = want == "1" or (want not in ("0", "1") and B * H * W <= 65536)
         ring = ("reflect" if net.padding_mode == "reflect" else "replicate") if (
-            T == torch.bfloat16 and H >= 4 and W >= 4 and not getattr(self, "no_fused_ring", False)
-            and os.environ.get("PHT_FUSED_RING", "1") != "0") else None
+            T == torch.bfloat16 and H >= 4 and W >= 4 and ring_on and not getattr(self, "no_fused_ring", False)) else None
         nb = lambda i: i if save else 0          # per-block buffers only when saving for backward
         g = A.get
 
