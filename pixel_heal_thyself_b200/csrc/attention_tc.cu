@@ -317,6 +317,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // frame of the padded output buffer: copies of the edge pixel (replicate) or of the pixel next to it (reflect),
       // stored straight from the registers of the thread that owns it
       bf16 *d0 = nullptr, *d1 = nullptr, *d2 = nullptr;
+#ifndef PHT_NO_RING
       if (P.ring) {
         const int x = bx * 8 + qx, y = by * 8 + qy, e0 = P.ring == 2 ? 1 : 0;
         const int tx = x == e0 ? -1 : (x == P.W - 1 - e0 ? P.W : -2);
@@ -326,6 +327,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (ty != -2) d1 = base + view_off(P.out, b, ty + P.out.oy, x + P.out.ox);
         if (tx != -2 && ty != -2) d2 = base + view_off(P.out, b, ty + P.out.oy, tx + P.out.ox);
       }
+#endif
       uint8_t* row = ROs + hp * AT_Q_BYTES + q * 128;
       uint4 ru[4];
       mbar_wait(ro_in, it & 1);                  // residual tile landed (or staging tile free)

@@ -517,14 +517,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             }
           } else {
             stage_and_store(v, tmOut1, n0 + c0, x0 + P.out1Ox, y0 + P.out1Oy, b);
+#ifndef PHT_NO_RING   /* (A/B builds: tools/ab_ring_build.sh) */
             if ((P.ring & 1) && valid) ring_store(v, P.out1, n0 + c0, b, y, x);
+#endif
           }
         }
         if (P.has_out2) {   // (the host clears RESID_POST / MASK when there is no out2)
           if (AUX && (P.flags & PHT_EPI_RESID_POST)) aux_apply(v, n0 + c0, false);
           if (AUX && (P.flags & PHT_EPI_MASK)) aux_apply(v, n0 + c0, true);
           stage_and_store(v, tmOut2, n0 + c0, x0 + P.out2Ox, y0 + P.out2Oy, b);
+#ifndef PHT_NO_RING
           if ((P.ring & 2) && valid) ring_store(v, P.out2, n0 + c0, b, y, x);
+#endif
         }
       }
       if (warp == 2 || warp == 7) stamp(it, warp == 2 ? 5 : 7);
